@@ -1,0 +1,96 @@
+"""CPU suite: pins the oracle (reference tests over the shims, golden vectors,
+C formulation vs networkx) and checks the C-ABI library loads with every symbol."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import localize_numpy, search_numpy, synth, tn_fast, tn_networkx
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/vsc"), reason="reference tree not mounted")
+def test_unmodified_reference_tests_pass_over_shims():
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, "-m", "oracle.run_reference_tests"], cwd=REPO,
+                         capture_output=True, text=True)
+    assert "reference tests run=20 failures=0 errors=0 skipped=0" in out.stdout, out.stdout + out.stderr
+
+
+def test_restatement_matches_golden_c1(golden_c1):
+    g = golden_c1
+    q, r, noise = list(g["q"]), list(g["r"]), list(g["noise"])
+    for tag, (qq, rr) in {"raw": (q, r), "sn": search_numpy.score_normalize(q, r, noise, beta=1.2)}.items():
+        if tag == "sn":
+            assert np.array_equal(np.stack(qq), g["sn_q"]) and np.array_equal(np.stack(rr), g["sn_r"])
+        cands = search_numpy.candidates(qq, rr, 2400)
+        assert [[a, b + 100] for a, b, _ in cands] == g[f"{tag}_cand_ids"].tolist()
+        assert np.array_equal(np.array([s for _, _, s in cands], np.float32), g[f"{tag}_cand_score"])
+        pairs = search_numpy.search_pairs(qq, rr, 2400)
+        flat = [[a, b + 100] for a, b, ms in pairs for _ in ms]
+        assert flat == g[f"{tag}_pairmatch_ids"].tolist()
+
+
+def test_known_answer_candidates():
+    """tests/test_candidates.py:17-83 of the reference, restated on arrays."""
+    q = [np.eye(3, dtype=np.float32)]
+    refs = [np.array([[0, 0, 0], [0, 0, 0], [0, 1, 0], [0, 2, 0], [0, 0, 0]], np.float32),
+            np.array([[0, 0, 0], [1, 0, 0], [1, 0, 0]], np.float32),
+            np.array([[0, 0, 0], [0, 0, 0.25], [0, 0, 0]], np.float32)]
+    assert search_numpy.candidates(q, refs, 6) == [(0, 0, 2.0), (0, 1, 1.0), (0, 2, 0.25)]
+
+
+def test_tn_golden_and_c_formulation(golden_tn):
+    g = golden_tn
+    for i in range(int(g["n"])):
+        sims = g[f"sims_{i}"]
+        for tag, cfg in (("vsc", dict(tn_max_step=5, min_length=4)), ("default", {})):
+            want = g[f"boxes_{tag}_{i}"].tolist()
+            assert tn_fast.tn(sims, **cfg) == want
+            if sims.size <= 128 * 128:
+                assert tn_networkx.tn(sims, **cfg) == want
+
+
+def test_c_formulation_matches_networkx_random():
+    rng = np.random.default_rng(0)
+    for it in range(250):
+        lq, lr = int(rng.integers(1, 70)), int(rng.integers(1, 70))
+        sims = synth.sim_matrix(rng, lq, lr, bias=[0.5, 0.0][it % 2], quant=[0.0, 8.0, 4.0, 16.0][it % 4])
+        cfg = dict(tn_max_step=[5, 10, 3, 7][it % 4], tn_top_k=[5, 5, 3, 6][(it // 4) % 4],
+                   min_length=[4, 5, 2][it % 3])
+        assert tn_networkx.tn(sims, **cfg) == tn_fast.tn(sims, **cfg), (it, lq, lr, cfg)
+
+
+def test_localize_restatement_matches_golden(golden_tn):
+    g = golden_tn
+    a, b, c = g["loc_a"], g["loc_b"], g["loc_c"]
+    pairs = [(a, g["loc_ts_a"], b, np.arange(30) * 1.0, 1.0), (a, g["loc_ts_a"], c, g["loc_ts_c"], 2.0)]
+    rows = localize_numpy.localize_all(pairs, 0.5, "max_sim", tn_max_step=5, min_length=4)
+    flat = [r for per in rows for r in per]
+    assert np.array_equal(np.array([r[:4] for r in flat]), g["loc_match_ts"])
+    assert np.array_equal(np.array([r[4] for r in flat], np.float32), g["loc_match_score"])
+
+
+def test_library_exports_every_declared_symbol():
+    from vsc2022_b200 import _lib, build_ext
+    build_ext.build_library()
+    lib = _lib.load()
+    header = open(os.path.join(REPO, "include", "vsc_b200.h")).read()
+    declared = set(re.findall(r"\b(vsc_[a-z0-9_]+|vcsl_[a-z0-9_]+|sscd_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no prototypes found in include/vsc_b200.h"
+    for name in declared:
+        assert hasattr(lib, name), f"libvsc_b200.so does not export {name}"
+    assert set(_lib.EXPORTS) == declared
+    assert lib.vsc_abi_version() >= 1
+
+
+def test_product_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from vsc2022_b200 import _lib, vta
+    with pytest.raises(_lib.EngineError):
+        vta.build_vta_model("TN").forward_sim([("a", np.zeros((4, 4), np.float32))])

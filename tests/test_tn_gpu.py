@@ -1,0 +1,115 @@
+"""GPU parity of the TN alignment kernel (through the C ABI) against the oracle.
+
+Bar: bit-exact boxes (integer index work); MaxSim box scores bit-exact (a max over
+float32 inputs has no rounding).
+"""
+import numpy as np
+import pytest
+
+from oracle import synth, tn_fast, tn_networkx
+
+pytestmark = pytest.mark.gpu
+
+VSC_CFG = dict(tn_max_step=5, min_length=4)
+
+
+def run_gpu(sims, force_exact=False, **cfg):
+    from vsc2022_b200 import vta
+    model = vta.build_vta_model("TN", concurrency=16, **cfg)
+    model.force_exact_order = force_exact
+    out = model.forward_sim([(f"k{i}", s) for i, s in enumerate(sims)])
+    assert [k for k, _ in out] == [f"k{i}" for i in range(len(sims))]
+    boxes, n_boxes, maxsim, status = model.last_result.to_host()
+    return [b for _, b in out], maxsim, status
+
+
+@pytest.mark.parametrize("force_exact", [False, True])
+def test_golden_boxes(golden_tn, force_exact):
+    n = int(golden_tn["n"])
+    sims = [golden_tn[f"sims_{i}"] for i in range(n)]
+    for tag, cfg in (("vsc", VSC_CFG), ("default", {})):
+        got, _, _ = run_gpu(sims, force_exact=force_exact, **cfg)
+        for i in range(n):
+            want = golden_tn[f"boxes_{tag}_{i}"].tolist()
+            assert got[i] == want, (tag, i, sims[i].shape)
+
+
+def _random_cases(seed, count, max_len):
+    rng = np.random.default_rng(seed)
+    cases = []
+    for it in range(count):
+        lq, lr = int(rng.integers(1, max_len)), int(rng.integers(1, max_len))
+        quant = [0.0, 8.0, 4.0, 64.0][it % 4]   # coarse grids force exact ties everywhere
+        cases.append(synth.sim_matrix(rng, lq, lr, bias=[0.5, 0.0][it % 2], quant=quant))
+    return cases
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(tn_max_step=5, tn_top_k=5, min_length=4),
+    dict(),                                             # VCSL defaults: 45 slots -> 64-bit masks
+    dict(tn_max_step=3, tn_top_k=3, min_length=2),
+    dict(tn_max_step=7, tn_top_k=8, min_length=3, max_path=4, min_sim=0.45, max_iou=0.1),
+    dict(tn_max_step=13, tn_top_k=5, min_length=5),
+])
+@pytest.mark.parametrize("force_exact", [False, True])
+def test_random_vs_oracle(cfg, force_exact):
+    sims = _random_cases(seed=11, count=240, max_len=90)
+    want = tn_fast.tn_batch(sims, **{**dict(tn_max_step=10, tn_top_k=5, max_path=10, min_sim=0.2,
+                                            min_length=5, max_iou=0.3), **cfg})
+    got, _, status = run_gpu(sims, force_exact=force_exact, **cfg)
+    bad = [i for i in range(len(sims)) if got[i] != want[i]]
+    assert not bad, (bad[:5], [(got[i], want[i]) for i in bad[:2]])
+    if force_exact:
+        assert (status == 1).all()
+
+
+def test_tie_heavy_uses_exact_kernel_and_matches_networkx():
+    rng = np.random.default_rng(3)
+    sims = [synth.sim_matrix(rng, 40, 40, quant=4.0) for _ in range(40)]
+    got, _, status = run_gpu(sims, **VSC_CFG)
+    for s, g in zip(sims, got):
+        assert g == tn_networkx.tn(s, **VSC_CFG)
+    # informational: how many pairs needed the exact-order kernel
+    print("pairs routed to exact-order kernel:", int(status.sum()), "of", len(sims))
+
+
+def test_maxsim_scores():
+    rng = np.random.default_rng(5)
+    sims = [synth.sim_matrix(rng, int(rng.integers(20, 120)), int(rng.integers(20, 120))) for _ in range(64)]
+    got, maxsim, _ = run_gpu(sims, **VSC_CFG)
+    seen = 0
+    for i, s in enumerate(sims):
+        for k, (x1, y1, x2, y2) in enumerate(got[i]):
+            assert maxsim[i, k] == s[x1:x2, y1:y2].max()
+            seen += 1
+    assert seen > 10
+
+
+def test_full_size_pairs_300x300():
+    rng = np.random.default_rng(4)
+    sims = [synth.sim_matrix(rng, 300, 300) for _ in range(192)]
+    want = tn_fast.tn_batch(sims, tn_max_step=5, tn_top_k=5, max_path=10, min_sim=0.2, min_length=4, max_iou=0.3)
+    got, _, _ = run_gpu(sims, **VSC_CFG)
+    assert got == want
+    assert sum(len(b) for b in got) > 100
+
+
+def test_long_rows_and_edge_shapes():
+    rng = np.random.default_rng(6)
+    sims = [synth.sim_matrix(rng, 12, 700), synth.sim_matrix(rng, 700, 12), synth.sim_matrix(rng, 64, 321),
+            synth.sim_matrix(rng, 2, 2), np.zeros((9, 9), np.float32), np.full((30, 30), 0.75, np.float32),
+            synth.sim_matrix(rng, 1, 1)]
+    want = tn_fast.tn_batch(sims, tn_max_step=5, tn_top_k=5, max_path=10, min_sim=0.2, min_length=4, max_iou=0.3)
+    got, _, _ = run_gpu(sims, **VSC_CFG)
+    assert got == want
+
+
+def test_empty_batch_and_bad_params():
+    from vsc2022_b200 import _lib, vta
+    assert vta.build_vta_model("TN").forward_sim([]) == []
+    with pytest.raises(NotImplementedError):
+        vta.build_vta_model("DTW")
+    with pytest.raises(_lib.EngineError):
+        vta.build_vta_model("TN", tn_top_k=9).forward_sim([("a", np.zeros((4, 4), np.float32))])
+    with pytest.raises(_lib.EngineError):
+        vta.build_vta_model("TN", tn_max_step=20).forward_sim([("a", np.zeros((4, 4), np.float32))])

@@ -1,0 +1,77 @@
+"""ctypes binding of libvsc_b200.so (the C ABI declared in include/vsc_b200.h).
+
+The product path has NO CPU fallback: if the CUDA library is missing or there
+is no CUDA device, the first engine call raises.
+"""
+import ctypes
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "csrc", "libvsc_b200.so")
+
+VSC_OK = 0
+
+
+class TnParams(ctypes.Structure):
+    _fields_ = [
+        ("tn_max_step", ctypes.c_int32),
+        ("tn_top_k", ctypes.c_int32),
+        ("max_path", ctypes.c_int32),
+        ("min_sim", ctypes.c_float),
+        ("min_length", ctypes.c_double),
+        ("max_iou", ctypes.c_double),
+    ]
+
+
+EXPORTS = {
+    # name: (restype, argtypes)
+    "vsc_last_error": (ctypes.c_char_p, []),
+    "vsc_abi_version": (ctypes.c_int, []),
+    "vsc_launch_count": (ctypes.c_int64, []),
+    "vcsl_tn_batch": (ctypes.c_int, [
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+        ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(TnParams),
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+        ctypes.c_int32, ctypes.c_void_p]),
+}
+
+_lib = None
+
+
+class EngineError(RuntimeError):
+    """Raised when libvsc_b200.so is unavailable or an entry point reports failure."""
+
+
+def load():
+    """dlopen the library (once) and declare every exported prototype."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EngineError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). vsc2022_b200 has no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in EXPORTS.items():
+        fn = getattr(lib, name)  # AttributeError if the .so lacks a declared symbol
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc != VSC_OK:
+        msg = load().vsc_last_error().decode("utf-8", "replace")
+        raise EngineError(f"{what} failed (code {rc}): {msg}")
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise EngineError("vsc2022_b200 needs a CUDA device (B200, sm_100a); no CPU fallback exists")
+    return torch
+
+
+def launch_count() -> int:
+    return int(load().vsc_launch_count())
