@@ -39,8 +39,11 @@ int vsc_abi_version(void);
  * max(sims[q_min:q_max, r_min:r_max]) (EXCLUSIVE upper bounds, the slice
  * vsc/baseline/localization.py:88-91 scores with; bias NOT subtracted).
  * d_box_maxsim may be NULL.
- * d_status[p]: 0 = done by the fast kernel, 1 = done by the exact-order kernel
- * (a tie between unrelated graph nodes needed the full Kahn order).  May be NULL.
+ * d_status[p] (may be NULL) says which kernel finished pair p:
+ *   0 = fast pipeline (rows 16-byte aligned, lr % 4 == 0, lr <= 512, lr >= tn_top_k),
+ *   2 = general kernel (any shape/alignment, tie-heavy rows),
+ *   1 = exact-order kernel (a tie between unrelated graph nodes needed the full Kahn order).
+ * All three produce identical results; the split is a performance detail.
  * ------------------------------------------------------------------------- */
 typedef struct {
     int32_t tn_max_step;  /* VCSL default 10; vsc passes 5 (sscd_baseline.py:121,131) */

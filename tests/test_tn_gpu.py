@@ -39,6 +39,8 @@ def _random_cases(seed, count, max_len):
     cases = []
     for it in range(count):
         lq, lr = int(rng.integers(1, max_len)), int(rng.integers(1, max_len))
+        if it % 3:
+            lr = max(8, lr & ~3)                # 16-byte aligned rows: eligible for the fast pipeline
         quant = [0.0, 8.0, 4.0, 64.0][it % 4]   # coarse grids force exact ties everywhere
         cases.append(synth.sim_matrix(rng, lq, lr, bias=[0.5, 0.0][it % 2], quant=quant))
     return cases
@@ -61,6 +63,8 @@ def test_random_vs_oracle(cfg, force_exact):
     assert not bad, (bad[:5], [(got[i], want[i]) for i in bad[:2]])
     if force_exact:
         assert (status == 1).all()
+    else:
+        print("status histogram (0 fast pipeline, 2 general, 1 exact):", np.bincount(status, minlength=3))
 
 
 def test_tie_heavy_uses_exact_kernel_and_matches_networkx():
@@ -89,9 +93,10 @@ def test_full_size_pairs_300x300():
     rng = np.random.default_rng(4)
     sims = [synth.sim_matrix(rng, 300, 300) for _ in range(192)]
     want = tn_fast.tn_batch(sims, tn_max_step=5, tn_top_k=5, max_path=10, min_sim=0.2, min_length=4, max_iou=0.3)
-    got, _, _ = run_gpu(sims, **VSC_CFG)
+    got, _, status = run_gpu(sims, **VSC_CFG)
     assert got == want
     assert sum(len(b) for b in got) > 100
+    assert (status == 0).mean() > 0.9, "aligned 300x300 pairs should stay on the fast pipeline"
 
 
 def test_long_rows_and_edge_shapes():

@@ -1,4 +1,6 @@
-// Temporal-network (TN) alignment on B200: one CTA per candidate pair.
+// Temporal-network (TN) alignment, GENERAL kernel: one CTA per candidate pair, any shape or
+// alignment, optional exact Kahn order.  The fast path for aligned rows is tn_pipeline.cu; this
+// kernel finishes whatever the pipeline hands back (ambiguous ties, odd shapes, tie-heavy rows).
 //
 // Replaces vcsl.vta `tn` (alipay/VCSL @ c39269d5, vcsl/vta.py) as called from
 // vsc/baseline/localization.py:44-46,58.  The algorithm contract is
@@ -24,9 +26,14 @@
 
 #include <vector>
 
-#include "common.cuh"
+#include "tn_common.cuh"
 
 namespace {
+
+using vsc::tn::Batch;
+using vsc::tn::WorkList;
+using vsc::tn::kMaxBoxes;
+using vsc::tn::kMaxTop;
 
 using vsc::float_to_key;
 using vsc::kFullMask;
@@ -34,26 +41,15 @@ using vsc::key_to_float;
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kMaxTop = 8;       // tn_top_k limit
 constexpr int kColsPerLane = 10; // phase-1 register tile: 320 columns per pass
-constexpr int kMaxBoxes = 32;    // max_path + 1 limit
 
 struct TnArgs {
-    const float *sims;
-    const int64_t *off;
-    const int32_t *lq;
-    const int32_t *lr;
-    int n_pairs;
-    int step, topk, max_path;
-    float min_sim;
-    double min_length, max_iou;
-    int32_t *boxes;
-    int32_t *n_boxes;
-    float *box_maxsim;
-    int32_t *status;
-    int32_t *redo_count;  // fast kernel appends ambiguous pairs here
-    int32_t *redo_list;
-    int max_nodes, max_lq;
+    Batch b;
+    const int32_t *in_count;   // null: every pair of the batch
+    const int32_t *in_list;
+    int32_t *out_count;        // unresolved pairs (exact_order=false only)
+    int32_t *out_list;
+    int status_code;
 };
 
 struct Scalars {
@@ -217,14 +213,15 @@ __device__ inline void kahn_order(const Smem<MaskT> &s, int n, int lq, int top, 
 }
 
 template <typename MaskT, bool EXACT>
-__global__ void __launch_bounds__(kThreads) tn_kernel(const TnArgs a) {
+__global__ void __launch_bounds__(kThreads) tn_kernel(const TnArgs args) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Batch &a = args.b;
     const Smem<MaskT> s = carve<MaskT, EXACT>(smem_raw, a.max_nodes, a.max_lq);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n_work = EXACT ? *a.redo_count : a.n_pairs;
+    const int n_work = args.in_count ? *args.in_count : a.n_pairs;
 
     for (int work = blockIdx.x; work < n_work; work += gridDim.x) {
-        const int pair = EXACT ? a.redo_list[work] : work;
+        const int pair = args.in_count ? args.in_list[work] : work;
         const int lq = a.lq[pair], lr = a.lr[pair];
         const int top = min(a.topk, lr);
         const int n = lq * top;
@@ -417,13 +414,13 @@ __global__ void __launch_bounds__(kThreads) tn_kernel(const TnArgs a) {
         // ---- phase 4: outputs (+ MaxSim score: max over sims[q_lo:q_hi, r_lo:r_hi], exclusive)
         const bool redo = !EXACT && s.sc->ambiguous;
         if (redo) {
-            if (tid == 0) a.redo_list[atomicAdd(a.redo_count, 1)] = pair;
+            if (tid == 0) args.out_list[atomicAdd(args.out_count, 1)] = pair;
             continue;
         }
         const int nb = s.sc->n_boxes;
         if (tid == 0) {
             a.n_boxes[pair] = nb;
-            if (a.status) a.status[pair] = EXACT ? 1 : 0;
+            if (a.status) a.status[pair] = args.status_code;
         }
         for (int i = tid; i < nb * 4; i += kThreads)
             a.boxes[(size_t)pair * box_cap * 4 + i] = s.sc->boxes[i];
@@ -452,17 +449,19 @@ __global__ void __launch_bounds__(kThreads) tn_kernel(const TnArgs a) {
 
 template <typename MaskT, bool EXACT>
 int launch(const TnArgs &a, int grid, cudaStream_t stream) {
-    const size_t bytes = smem_bytes<MaskT, EXACT>(a.max_nodes, a.max_lq);
+    const size_t bytes = smem_bytes<MaskT, EXACT>(a.b.max_nodes, a.b.max_lq);
     int dev = 0, max_optin = 0;
     VSC_CUDA_CHECK(cudaGetDevice(&dev));
     VSC_CUDA_CHECK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     if (bytes > (size_t)max_optin) {
         vsc::set_error("vcsl_tn_batch: pair with %d graph nodes needs %zu B of shared memory (> %d)",
-                       a.max_nodes, bytes, max_optin);
+                       a.b.max_nodes, bytes, max_optin);
         return VSC_ERR_CAPACITY;
     }
     VSC_CUDA_CHECK(cudaFuncSetAttribute(tn_kernel<MaskT, EXACT>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    VSC_CUDA_CHECK(cudaFuncSetAttribute(tn_kernel<MaskT, EXACT>,
+                                        cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     tn_kernel<MaskT, EXACT><<<grid, kThreads, bytes, stream>>>(a);
     VSC_CUDA_CHECK(cudaGetLastError());
     vsc::count_launch();
@@ -471,63 +470,25 @@ int launch(const TnArgs &a, int grid, cudaStream_t stream) {
 
 }  // namespace
 
-extern "C" int vcsl_tn_batch(const float *d_sims, const int64_t *d_off, const int32_t *d_lq,
-                             const int32_t *d_lr, int32_t n_pairs, int32_t max_lq, int32_t max_lr,
-                             const vsc_tn_params *p, int32_t *d_boxes, int32_t *d_n_boxes,
-                             float *d_box_maxsim, int32_t *d_status, int32_t force_exact_order,
-                             vsc_stream_t stream_) {
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    if (!p || n_pairs < 0) { vsc::set_error("vcsl_tn_batch: bad arguments"); return VSC_ERR_INVALID; }
-    if (n_pairs == 0) return VSC_OK;
-    if (!d_sims || !d_off || !d_lq || !d_lr || !d_boxes || !d_n_boxes) {
-        vsc::set_error("vcsl_tn_batch: null device pointer"); return VSC_ERR_INVALID;
-    }
-    if (p->tn_top_k < 1 || p->tn_top_k > kMaxTop || p->tn_max_step < 1 || p->tn_max_step > 31 ||
-        (p->tn_max_step - 1) * p->tn_top_k > 64 || p->max_path < 0 || p->max_path + 1 > kMaxBoxes) {
-        vsc::set_error("vcsl_tn_batch: unsupported parameters (need tn_top_k<=%d, "
-                       "(tn_max_step-1)*tn_top_k<=64, max_path<%d)", kMaxTop, kMaxBoxes);
-        return VSC_ERR_INVALID;
-    }
-    if (max_lr > 65535 || max_lq < 0 || max_lr < 0) {
-        vsc::set_error("vcsl_tn_batch: max_lr %d out of range (<= 65535)", max_lr);
-        return VSC_ERR_INVALID;
-    }
+namespace vsc {
+namespace tn {
+
+int launch_fused(const Batch &b, bool exact_order, const WorkList *in, const WorkList *out,
+                 int status_code, cudaStream_t stream) {
     TnArgs a;
-    a.sims = d_sims; a.off = d_off; a.lq = d_lq; a.lr = d_lr; a.n_pairs = n_pairs;
-    a.step = p->tn_max_step; a.topk = p->tn_top_k; a.max_path = p->max_path;
-    a.min_sim = p->min_sim; a.min_length = p->min_length; a.max_iou = p->max_iou;
-    a.boxes = d_boxes; a.n_boxes = d_n_boxes; a.box_maxsim = d_box_maxsim; a.status = d_status;
-    a.max_lq = max_lq > 0 ? max_lq : 1;
-    a.max_nodes = a.max_lq * (p->tn_top_k < max_lr ? p->tn_top_k : (max_lr > 0 ? max_lr : 1));
-    if (a.max_nodes > 65535) {
-        vsc::set_error("vcsl_tn_batch: %d graph nodes exceed the 16-bit node index", a.max_nodes);
-        return VSC_ERR_CAPACITY;
-    }
-    int32_t *redo = nullptr;  // [0] = count, [1..] = pair ids
-    VSC_CUDA_CHECK(cudaMallocAsync(&redo, sizeof(int32_t) * ((size_t)n_pairs + 1), stream));
-    a.redo_count = redo; a.redo_list = redo + 1;
-    const bool wide = (p->tn_max_step - 1) * p->tn_top_k > 32;
-    int rc = VSC_OK;
-    if (force_exact_order) {
-        // every pair goes straight to the exact-order kernel
-        std::vector<int32_t> all((size_t)n_pairs + 1);
-        all[0] = n_pairs;
-        for (int i = 0; i < n_pairs; ++i) all[i + 1] = i;
-        cudaError_t e = cudaMemcpyAsync(redo, all.data(), all.size() * sizeof(int32_t),
-                                        cudaMemcpyHostToDevice, stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);  // `all` is a stack-owned staging buffer
-        if (e != cudaSuccess) { vsc::set_error("redo list upload: %s", cudaGetErrorString(e)); rc = VSC_ERR_CUDA; }
-    } else {
-        cudaError_t e = cudaMemsetAsync(redo, 0, sizeof(int32_t), stream);
-        if (e != cudaSuccess) { vsc::set_error("memset: %s", cudaGetErrorString(e)); rc = VSC_ERR_CUDA; }
-        if (rc == VSC_OK)
-            rc = wide ? launch<uint64_t, false>(a, n_pairs, stream) : launch<uint32_t, false>(a, n_pairs, stream);
-    }
-    if (rc == VSC_OK) {
-        // exact-order kernel: persistent grid over the (usually empty) redo list
-        const int grid = n_pairs < 296 ? n_pairs : 296;
-        rc = wide ? launch<uint64_t, true>(a, grid, stream) : launch<uint32_t, true>(a, grid, stream);
-    }
-    cudaFreeAsync(redo, stream);
-    return rc;
+    a.b = b;
+    a.in_count = in ? in->count : nullptr;
+    a.in_list = in ? in->list : nullptr;
+    a.out_count = out ? out->count : nullptr;
+    a.out_list = out ? out->list : nullptr;
+    a.status_code = status_code;
+    // a work list is consumed by a persistent grid (its length is only known on the device)
+    const int grid = in ? (b.n_pairs < 592 ? b.n_pairs : 592) : b.n_pairs;
+    const bool wide = (b.step - 1) * b.topk > 32;
+    if (exact_order)
+        return wide ? launch<uint64_t, true>(a, grid, stream) : launch<uint32_t, true>(a, grid, stream);
+    return wide ? launch<uint64_t, false>(a, grid, stream) : launch<uint32_t, false>(a, grid, stream);
 }
+
+}  // namespace tn
+}  // namespace vsc

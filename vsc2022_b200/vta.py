@@ -74,11 +74,12 @@ def pack_sims(sims: Sequence[np.ndarray]):
     lq = np.fromiter((s.shape[0] for s in sims), dtype=np.int32, count=n)
     lr = np.fromiter((s.shape[1] for s in sims), dtype=np.int32, count=n)
     sizes = lq.astype(np.int64) * lr.astype(np.int64)
+    padded = (sizes + 3) & ~np.int64(3)   # every matrix starts 16-byte aligned (TMA bulk copies)
     off = np.zeros(n, dtype=np.int64)
     if n:
-        off[1:] = np.cumsum(sizes[:-1])
-    total = int(sizes.sum())
-    flat = torch.empty((max(total, 1),), dtype=torch.float32, pin_memory=True)
+        off[1:] = np.cumsum(padded[:-1])
+    total = int(padded.sum())
+    flat = torch.empty((max(total, 1) + 4,), dtype=torch.float32, pin_memory=True)
     view = flat.numpy()
     for s, o, sz in zip(sims, off, sizes):
         if s.ndim != 2:

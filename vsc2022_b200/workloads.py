@@ -30,19 +30,17 @@ def tn_pairs_device(n_pairs: int, lq: int, lr: int, seed: int, device, dim: int 
         n = min(chunk, n_pairs - start)
         a = torch.randn((n, lq, dim), generator=gen, device=device)
         b = torch.randn((n, lr, dim), generator=gen, device=device)
+        rows = torch.arange(lq, device=device)[None, :]
         for copy in range(2):
             use = torch.rand((n,), generator=gen, device=device) < 0.5
             length = torch.randint(min(20, longest), min(80, longest) + 1, (n,), generator=gen, device=device)
             qs = (torch.rand((n,), generator=gen, device=device) * (lq - length + 1).float()).long()
             rs = (torch.rand((n,), generator=gen, device=device) * (lr - length + 1).float()).long()
-            t = torch.arange(longest, device=device)[None, :]
-            valid = (t < length[:, None]) & use[:, None]
-            qi = (qs[:, None] + t).clamp(max=lq - 1)
-            ri = (rs[:, None] + t).clamp(max=lr - 1)
-            src = torch.gather(b, 1, ri[:, :, None].expand(-1, -1, dim))
+            planted = use[:, None] & (rows >= qs[:, None]) & (rows < (qs + length)[:, None])   # [n, lq]
+            src_row = (rs[:, None] + rows - qs[:, None]).clamp(0, lr - 1)
+            src = torch.gather(b, 1, src_row[:, :, None].expand(-1, -1, dim))
             src = src + jitter * torch.randn(src.shape, generator=gen, device=device)
-            cur = torch.gather(a, 1, qi[:, :, None].expand(-1, -1, dim))
-            a.scatter_(1, qi[:, :, None].expand(-1, -1, dim), torch.where(valid[:, :, None], src, cur))
+            a = torch.where(planted[:, :, None], src, a)
         a = torch.nn.functional.normalize(a, dim=2)
         b = torch.nn.functional.normalize(b, dim=2)
         torch.baddbmm(torch.full((1, 1, 1), bias, device=device), a, b.transpose(1, 2), out=sims[start:start + n])
