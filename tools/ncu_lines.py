@@ -35,59 +35,70 @@ def sass_lines(lib, kernel_sub):
     return out
 
 
-def main():
-    rep, lib, sub = sys.argv[1:4]
-    top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+def sections(rep):
     text = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(text)))
-    fn_maps = sass_lines(lib, sub)
-    kernel = None
-    hdr = None
-    per_line = {}
-    total = {"inst": 0, "samp": 0}
-    base = None
+    out, cur = [], None
     for r in rows:
         if r and r[0] == "Kernel Name":
-            kernel = r[1]
-            hdr = None
-            continue
-        if r and r[0] == "Address":
-            hdr = r
-            continue
-        if hdr is None or len(r) < len(hdr) - 2:
-            continue
-        d = dict(zip(hdr, r))
-        try:
-            addr = int(d["Address"], 16) if d["Address"].startswith("0x") else int(d["Address"])
-        except ValueError:
-            continue
-        if base is None:
-            base = addr
-        off = addr - base
-        inst = int(d.get("Instructions Executed") or 0)
-        samp = int(d.get("# Samples") or 0)
-        # pick the function map whose mangled name matches the kernel template args best
-        cand = [k for k in fn_maps if sub in k]
-        key = cand[0] if cand else None
-        line = fn_maps.get(key, {}).get(off, (None, ""))[0] if key else None
-        e = per_line.setdefault(line, [0, 0])
-        e[0] += inst
-        e[1] += samp
-        total["inst"] += inst
-        total["samp"] += samp
-    print(f"kernel: {kernel}\ntotal warp-instructions {total['inst']}  samples {total['samp']}")
+            cur = {"name": r[1], "hdr": None, "rows": []}
+            out.append(cur)
+        elif r and r[0] == "Address" and cur is not None:
+            cur["hdr"] = r
+        elif cur is not None and cur["hdr"] and len(r) >= len(cur["hdr"]) - 2:
+            cur["rows"].append(dict(zip(cur["hdr"], r)))
+    return out
+
+
+def match_fn(fn_maps, sec):
+    """Pick the disassembled function whose first instructions equal the profiled ones."""
+    base = int(sec["rows"][0]["Address"], 16)
+    want = [(int(r["Address"], 16) - base, r["Source"].split()[0] if r["Source"].split() else "") for r in sec["rows"][:40]]
+    best, best_score = None, -1
+    for name, m in fn_maps.items():
+        score = sum(1 for off, op in want if off in m and m[off][1].split() and
+                    (m[off][1].split()[0] == op or (m[off][1].split()[0].startswith("@") and len(m[off][1].split()) > 1 and m[off][1].split()[1] == op)
+                     or (op.startswith("@"))))
+        if score > best_score and len(m) == len(sec["rows"]):
+            best, best_score = name, score
+    if best is None:
+        for name, m in fn_maps.items():
+            if len(m) == len(sec["rows"]):
+                best = name
+    return best
+
+
+def main():
+    rep, lib = sys.argv[1:3]
+    top = int(sys.argv[3]) if len(sys.argv) > 3 else 30
+    fn_maps = sass_lines(lib, "")
     src_cache = {}
-    for line, (inst, samp) in sorted(per_line.items(), key=lambda kv: -kv[1][0])[:top]:
-        txt = ""
-        if line and line[0]:
-            path = glob.glob(os.path.join(os.path.dirname(lib), "**", line[0]), recursive=True) or \
-                glob.glob(os.path.join(os.path.dirname(lib), line[0]))
-            if path:
-                src_cache.setdefault(path[0], open(path[0]).read().splitlines())
-                if line[1] - 1 < len(src_cache[path[0]]):
-                    txt = src_cache[path[0]][line[1] - 1].strip()
-        print(f"{inst / max(total['inst'], 1) * 100:5.1f}% inst  {samp / max(total['samp'], 1) * 100:5.1f}% stall-samples  "
-              f"{line}  {txt[:100]}")
+    for sec in sections(rep):
+        if not sec["rows"]:
+            continue
+        key = match_fn(fn_maps, sec)
+        base = int(sec["rows"][0]["Address"], 16)
+        per_line, ti, ts = {}, 0, 0
+        for d in sec["rows"]:
+            off = int(d["Address"], 16) - base
+            inst = int(d.get("Instructions Executed") or 0)
+            samp = int(d.get("# Samples") or 0)
+            line = fn_maps.get(key, {}).get(off, (None, ""))[0] if key else None
+            e = per_line.setdefault(line, [0, 0])
+            e[0] += inst
+            e[1] += samp
+            ti += inst
+            ts += samp
+        print(f"\n=== {sec['name'][:90]}\n    total warp-instructions {ti}  stall samples {ts}")
+        for line, (inst, samp) in sorted(per_line.items(), key=lambda kv: -kv[1][0])[:top]:
+            txt = ""
+            if line and line[0]:
+                path = glob.glob(os.path.join(os.path.dirname(os.path.abspath(lib)), line[0]))
+                if path:
+                    src_cache.setdefault(path[0], open(path[0]).read().splitlines())
+                    if line[1] - 1 < len(src_cache[path[0]]):
+                        txt = src_cache[path[0]][line[1] - 1].strip()
+            print(f"{inst / max(ti, 1) * 100:5.1f}% inst {samp / max(ts, 1) * 100:5.1f}% stall  {str(line):28s} {txt[:95]}")
 
 
 if __name__ == "__main__":

@@ -15,6 +15,21 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// Stream-ordered scratch comes from the device's default memory pool.  By default the pool hands
+// unused memory back to the driver at every synchronisation, which turns each call into a fresh
+// cudaMalloc; keep it cached instead.
+void keep_pool_cached() {
+    static thread_local int done_for = -1;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev == done_for) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    done_for = dev;
+}
 }  // namespace vsc
 
 extern "C" const char *vsc_last_error(void) { return vsc::g_error; }

@@ -10,6 +10,7 @@ namespace vsc {
 
 void set_error(const char *fmt, ...);
 void count_launch(int n = 1);
+void keep_pool_cached();
 
 #define VSC_CUDA_CHECK(expr)                                                          \
     do {                                                                              \

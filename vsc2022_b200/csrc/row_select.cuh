@@ -8,7 +8,7 @@
 //           keeps the K largest block maxima.  The K-th of them, t, is a lower
 //           bound for the K-th largest element (K distinct elements are >= t),
 //           so every top-K element is >= t and lives in a block whose maximum
-//           is >= t ("hot" block; ~K of them).
+//           is >= t ("hot" block; exactly K of them unless maxima tie).
 //   pass 2  only hot blocks are re-read; elements >= t (about K..K+3 of them)
 //           go to a small candidate list in ascending column order.
 //   select  stable insertion of the candidates into the sorted result.
@@ -29,6 +29,98 @@ __host__ __device__ __forceinline__ float max4(const float4 &v) {
     return fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
 }
 
+// Streaming form used by the TN kernel: pass 1 is fed panel by panel while the row streams
+// through shared memory; pass 2 re-reads the K hot blocks from `row` (global memory / L2).
+template <int K>
+struct RowTopK {
+    float top[K];   // K largest block maxima so far, descending
+    __host__ __device__ __forceinline__ void reset() {
+#pragma unroll
+        for (int i = 0; i < K; ++i) top[i] = -INFINITY;
+    }
+    // one 16-column block held in 4 float4 registers (n_chunks valid, 1..4)
+    __host__ __device__ __forceinline__ float add_block(const float4 *chunk, int n_chunks) {
+        float m = max4(chunk[0]);
+#pragma unroll
+        for (int c = 1; c < 4; ++c)
+            if (c < n_chunks) m = fmaxf(m, max4(chunk[c]));
+        float x = m;  // sorted insert (multiset), branch-free
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            const float hi = fmaxf(top[i], x);
+            x = fminf(top[i], x);
+            top[i] = hi;
+        }
+        return m;
+    }
+    // After every block went through add_block (block maxima in bm[b*stride]): finish the row.
+    // `row` may be any 16-byte aligned pointer to the lr columns.  Returns false on overflow.
+    __host__ __device__ __forceinline__ bool finish(const float *row, int lr, const float *bm, float *cand_val,
+                                                    int *cand_col, int stride, float (&val)[K], int (&col)[K]) const {
+        const float4 *row4 = reinterpret_cast<const float4 *>(row);
+        const int n_chunks = lr >> 2;
+        const int n_blocks = (lr + kBlockCols - 1) / kBlockCols;
+        const float t = top[K - 1];
+        uint32_t hot = 0;
+        for (int b = 0; b < n_blocks; ++b)
+            if (bm[b * stride] >= t) hot |= 1u << b;
+        int n_cand = 0;
+        bool overflow = false;
+        while (hot) {  // exactly K iterations unless block maxima tie
+#if defined(__CUDA_ARCH__)
+            const int b = __ffs(hot) - 1;
+#else
+            const int b = __builtin_ctz(hot);
+#endif
+            hot &= hot - 1;
+            const int c0 = b * 4;
+            // branch-free hit mask over the block's 16 columns, then one short loop per hit
+            uint32_t hits = 0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (c0 + c < n_chunks) {
+                    const float4 v = row4[c0 + c];
+                    hits |= (v.x >= t ? 1u : 0u) << (4 * c) | (v.y >= t ? 2u : 0u) << (4 * c) |
+                            (v.z >= t ? 4u : 0u) << (4 * c) | (v.w >= t ? 8u : 0u) << (4 * c);
+                }
+            }
+            while (hits) {
+#if defined(__CUDA_ARCH__)
+                const int k = __ffs(hits) - 1;
+#else
+                const int k = __builtin_ctz(hits);
+#endif
+                hits &= hits - 1;
+                if (n_cand < kMaxCand) {
+                    cand_val[n_cand * stride] = row[c0 * 4 + k];
+                    cand_col[n_cand * stride] = c0 * 4 + k;
+                    ++n_cand;
+                } else {
+                    overflow = true;
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < K; ++i) { val[i] = -INFINITY; col[i] = 0x7fffffff; }
+        for (int j = 0; j < n_cand; ++j) {  // candidates arrive in ascending column order
+            float x = cand_val[j * stride];
+            int xc = cand_col[j * stride];
+            bool placed = false;
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+                placed = placed || (x > val[i]);  // strict: an equal earlier column stays ahead
+                if (placed) {
+                    const float tv = val[i]; const int tc = col[i];
+                    val[i] = x; col[i] = xc;
+                    x = tv; xc = tc;
+                }
+            }
+        }
+        return !overflow;
+    }
+};
+
+// Whole row at once (host tests, and rows that already sit in one buffer).
 // row: 16-byte aligned, lr % 4 == 0, lr <= kBlockCols * kMaxRowBlocks, lr >= K.
 // bm / cand_val / cand_col: per-thread scratch, element i at [i * stride].
 template <int K>
@@ -38,74 +130,17 @@ __host__ __device__ __forceinline__ bool select_row(const float *row, int lr, fl
     const float4 *row4 = reinterpret_cast<const float4 *>(row);
     const int n_chunks = lr >> 2;
     const int n_blocks = (lr + kBlockCols - 1) / kBlockCols;
-    float top[K];
-#pragma unroll
-    for (int i = 0; i < K; ++i) top[i] = -INFINITY;
-    uint32_t hot = 0;
+    RowTopK<K> sel;
+    sel.reset();
     for (int b = 0; b < n_blocks; ++b) {
-        const int c0 = b * 4;
-        float m = max4(row4[c0]);
+        float4 chunk[4];
+        const int left = n_chunks - b * 4;
 #pragma unroll
-        for (int c = 1; c < 4; ++c)
-            if (c0 + c < n_chunks) m = fmaxf(m, max4(row4[c0 + c]));
-        bm[b * stride] = m;
-        if (m >= top[K - 1]) hot |= 1u << b;  // may still be hot once t is final
-        float x = m;                          // sorted insert (multiset), branch-free
-#pragma unroll
-        for (int i = 0; i < K; ++i) {
-            const float hi = fmaxf(top[i], x);
-            x = fminf(top[i], x);
-            top[i] = hi;
-        }
+        for (int c = 0; c < 4; ++c)
+            if (c < left) chunk[c] = row4[b * 4 + c];
+        bm[b * stride] = sel.add_block(chunk, left < 4 ? left : 4);
     }
-    const float t = top[K - 1];
-    int n_cand = 0;
-    bool overflow = false;
-    while (hot) {
-#if defined(__CUDA_ARCH__)
-        const int b = __ffs(hot) - 1;
-#else
-        const int b = __builtin_ctz(hot);
-#endif
-        hot &= hot - 1;
-        if (!(bm[b * stride] >= t)) continue;
-        const int c0 = b * 4;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            if (c0 + c >= n_chunks) break;
-            const float4 v = row4[c0 + c];
-            const float e[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (e[k] >= t) {
-                    if (n_cand < kMaxCand) {
-                        cand_val[n_cand * stride] = e[k];
-                        cand_col[n_cand * stride] = (c0 + c) * 4 + k;
-                        ++n_cand;
-                    } else {
-                        overflow = true;
-                    }
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < K; ++i) { val[i] = -INFINITY; col[i] = 0x7fffffff; }
-    for (int j = 0; j < n_cand; ++j) {  // candidates arrive in ascending column order
-        float x = cand_val[j * stride];
-        int xc = cand_col[j * stride];
-        bool placed = false;
-#pragma unroll
-        for (int i = 0; i < K; ++i) {
-            placed = placed || (x > val[i]);  // strict: an equal earlier column stays ahead
-            if (placed) {
-                const float tv = val[i]; const int tc = col[i];
-                val[i] = x; col[i] = xc;
-                x = tv; xc = tc;
-            }
-        }
-    }
-    return !overflow;
+    return sel.finish(row, lr, bm, cand_val, cand_col, stride, val, col);
 }
 
 }  // namespace vsc

@@ -4,8 +4,8 @@
 // Contract: oracle/tn_networkx.py.  Four launches per batch, all on one stream:
 //
 //   T1  tn_topk_kernel   HBM-bound.  Persistent warps; each lane pulls ITS OWN row of a 32-row
-//                        tile into shared memory with one cp.async.bulk (TMA bulk copy, mbarrier
-//                        completion, two stages) and selects the exact top-K of the row
+//                        tile through shared memory in 64-column panels (cp.async.bulk = TMA bulk copy, mbarrier
+//                        completion, three stages) and selects the exact top-K of the row
 //                        (row_select.cuh).  The similarity matrices are read from HBM once;
 //                        the node table (ref index + similarity per node, 6 B) is written out.
 //   T1e tn_edges_kernel  one thread per source row: constraints C1-C4 -> predecessor bit-masks.
@@ -39,13 +39,10 @@ using vsc::tn::kMaxTop;
 struct Workspace {
     uint16_t *ref_of;   // [P][N]
     float *sim_of;      // [P][N]
-    void *pred;         // [P][N] uint32 or uint64
-    void *zero;         // [P][N]
+    void *pz;           // [P][N][2] uint32 or uint64: {predecessor mask, zeroed-edge mask}
     float *dist;        // [P][N]
     int8_t *slot;       // [P][N]
     uint16_t *gen;      // [P][N]
-    uint16_t *chain;    // [P][max_lq]
-    uint32_t *lbest;    // [P][max_lq]  max dist bits per row layer
     uint8_t *skip;      // [P] 1 = handed to the general kernel
     int32_t *cursor;    // T1 pair counter
 };
@@ -79,34 +76,48 @@ __device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t b
                  : "memory");
 }
 
+// Ampere-style 16-byte async copy global -> shared (bypasses L1); one commit group per panel.
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // ------------------------------------------------------------------ T1: row top-K
-constexpr int kT1Warps = 2;
+// A warp owns 32 rows (one per lane in the compute phase) and streams them through shared memory
+// in 64-column panels.  The panel fill is warp-cooperative: 16 lanes x 16 B cover one 256-byte row
+// segment, so every cp.async instruction moves two fully coalesced segments into a padded panel
+// (pitch 68 words -> conflict-free LDS.128 for the thread-per-row reads); kStages panels per warp
+// are in flight.  (Measured: one cp.async.bulk per lane and panel -- 12.8 M 256-byte TMA bulk
+// copies per batch -- was TMA-issue-bound at ~27 cycles/op/SM, 2.4 TB/s; see profiles/.)
+// Pass 1 (block maxima + K best maxima) runs on the panels; at the end of a row the K hot blocks
+// are re-read straight from global memory (L2 hits) for the exact selection.
+constexpr int kT1Warps = 6;
 constexpr int kT1Threads = kT1Warps * 32;
 constexpr int kTileRows = 32;
-constexpr int kStages = 2;
+constexpr int kPanelCols = 64;
+constexpr int kPanelPitch = 68;
+constexpr int kStages = 3;
+constexpr int kPanelBytes = kTileRows * kPanelPitch * 4;
 
-__host__ __device__ inline int tile_pitch(int max_lr) {  // words; (pitch/4) odd -> LDS.128 conflict-free
-    int p = (max_lr + 3) & ~3;
-    if (((p >> 2) & 1) == 0) p += 4;
-    return p;
-}
-__host__ __device__ inline size_t t1_warp_bytes(int pitch) {
-    return (size_t)kStages * kTileRows * pitch * 4            // tiles
-           + (size_t)vsc::kMaxRowBlocks * 32 * 4              // block maxima
-           + (size_t)vsc::kMaxCand * 32 * 8                   // candidates (value, column)
-           + 64;                                              // mbarriers (+pad)
-}
-
-struct Cursor {
-    int pair, row0, lq, lr;
+struct Cursor {   // one panel of work
+    int pair, row0, col0, lq, lr;
     const float *base;
+};
+
+struct alignas(128) T1Smem {   // per warp
+    float panel[kStages][kTileRows * kPanelPitch];
+    float bm[vsc::kMaxRowBlocks * 32];
+    float cand_val[vsc::kMaxCand * 32];
+    int cand_col[vsc::kMaxCand * 32];
+    Cursor ring[kStages];
 };
 
 struct T1Args {
     Batch b;
     Workspace w;
     WorkList out;
-    int pitch;
 };
 
 // Claim the next pair this warp can process; pairs it cannot take go to the general kernel.
@@ -128,7 +139,7 @@ __device__ inline bool claim_pair(const T1Args &a, int lane, Cursor &c) {
             continue;
         }
         if (lq <= 0) continue;  // nothing to read; T2 reports zero boxes
-        c.pair = p; c.row0 = 0; c.lq = lq; c.lr = lr; c.base = a.b.sims + off;
+        c.pair = p; c.row0 = 0; c.col0 = 0; c.lq = lq; c.lr = lr; c.base = a.b.sims + off;
         return true;
     }
 }
@@ -137,74 +148,91 @@ template <int K>
 __global__ void __launch_bounds__(kT1Threads, 1) tn_topk_kernel(const T1Args a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int pitch = a.pitch;
-    unsigned char *mine = smem_raw + (size_t)warp * ((t1_warp_bytes(pitch) + 127) / 128 * 128);
-    float *tile = reinterpret_cast<float *>(mine);
-    float *bm = tile + (size_t)kStages * kTileRows * pitch;
-    float *cand_val = bm + vsc::kMaxRowBlocks * 32;
-    int *cand_col = reinterpret_cast<int *>(cand_val + vsc::kMaxCand * 32);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(cand_col + vsc::kMaxCand * 32);
+    T1Smem &sm = reinterpret_cast<T1Smem *>(smem_raw)[warp];
 
-    if (lane == 0) {
-        for (int s = 0; s < kStages; ++s) mbar_init(&bar[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-
-    auto issue = [&](const Cursor &c, int stage) {
-        const int rows = min(kTileRows, c.lq - c.row0);
-        const uint32_t row_bytes = (uint32_t)c.lr * 4u;
-        if (lane == 0) mbar_expect_tx(&bar[stage], row_bytes * rows);
-        __syncwarp();
-        if (lane < rows)
-            bulk_load(tile + ((size_t)stage * kTileRows + lane) * pitch,
-                      c.base + (size_t)(c.row0 + lane) * c.lr, row_bytes, &bar[stage]);
+    Cursor ic;                       // next panel to request
+    bool more = claim_pair(a, lane, ic);
+    const int half = lane >> 4, ch = (lane & 15) * 4;  // fill role: row parity, column offset
+    auto issue = [&](int stage) {    // request panel `ic` into `stage`, then step `ic`
+        if (lane == 0) sm.ring[stage] = ic;
+        if (ic.col0 + ch < ic.lr) {
+            const float *src = ic.base + (size_t)(ic.row0 + half) * ic.lr + ic.col0 + ch;
+            float *dst = &sm.panel[stage][half * kPanelPitch + ch];
+            const int rows = ic.lq - ic.row0 - half;  // rows left for this lane's parity
+#pragma unroll
+            for (int i = 0; i < kTileRows / 2; ++i)
+                if (2 * i < rows) cp_async16(dst + 2 * i * kPanelPitch, src + (size_t)2 * i * ic.lr);
+        }
+        cp_async_commit();
+        ic.col0 += kPanelCols;
+        if (ic.col0 >= ic.lr) {
+            ic.col0 = 0; ic.row0 += kTileRows;
+            if (ic.row0 >= ic.lq) more = claim_pair(a, lane, ic);
+        }
     };
 
-    Cursor cur;
-    bool have = claim_pair(a, lane, cur);
-    if (have) issue(cur, 0);
-    int stage = 0;
-    uint32_t parity = 0;  // bit s = phase parity of stage s
+    unsigned issued = 0, consumed = 0;
+    for (; issued < kStages - 1 && more; ++issued) issue(issued);
+    vsc::RowTopK<K> sel;
+    sel.reset();
     bool pair_overflow = false;
-    while (have) {
-        Cursor nxt = cur;
-        bool have_next = true;
-        if (cur.row0 + kTileRows < cur.lq) nxt.row0 = cur.row0 + kTileRows;
-        else have_next = claim_pair(a, lane, nxt);
-        if (have_next) issue(nxt, stage ^ 1);
-
-        mbar_wait(&bar[stage], (parity >> stage) & 1u);
-        parity ^= 1u << stage;
-
-        const int row = cur.row0 + lane;
+    while (consumed < issued) {
+        if (more) { issue(issued % kStages); ++issued; }
+        else cp_async_commit();      // empty group keeps the wait depth constant at the tail
+        const int stage = consumed % kStages;
+        cp_async_wait<kStages - 1>();
+        __syncwarp();                // every lane's copies for this panel have landed
+        const Cursor c = sm.ring[stage];
+        const int row = c.row0 + lane;
+        const bool last_panel = c.col0 + kPanelCols >= c.lr;
         bool ok = true;
-        if (row < cur.lq) {
-            float val[K]; int col[K];
-            ok = vsc::select_row<K>(tile + ((size_t)stage * kTileRows + lane) * pitch, cur.lr, bm + lane,
-                                    cand_val + lane, cand_col + lane, 32, val, col);
-            const size_t node = (size_t)cur.pair * a.b.max_nodes + (size_t)row * K;
+        if (row < c.lq) {
+            if (c.col0 == 0) sel.reset();
+            const float4 *src = reinterpret_cast<const float4 *>(&sm.panel[stage][lane * kPanelPitch]);
+            const int chunks = (min(kPanelCols, c.lr - c.col0)) >> 2;
 #pragma unroll
-            for (int i = 0; i < K; ++i) {
-                a.w.ref_of[node + i] = (uint16_t)col[i];
-                a.w.sim_of[node + i] = val[i];
+            for (int blk = 0; blk < kPanelCols / vsc::kBlockCols; ++blk) {
+                const int left = chunks - blk * 4;
+                if (left <= 0) break;
+                float4 v[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (k < left) v[k] = src[blk * 4 + k];
+                sm.bm[(c.col0 / vsc::kBlockCols + blk) * 32 + lane] = sel.add_block(v, left < 4 ? left : 4);
+            }
+            if (last_panel) {
+                float val[K]; int col[K];
+                ok = sel.finish(c.base + (size_t)row * c.lr, c.lr, sm.bm + lane, sm.cand_val + lane,
+                                sm.cand_col + lane, 32, val, col);
+                const size_t node = (size_t)c.pair * a.b.max_nodes + (size_t)row * K;
+#pragma unroll
+                for (int i = 0; i < K; ++i) {
+                    a.w.ref_of[node + i] = (uint16_t)col[i];
+                    a.w.sim_of[node + i] = val[i];
+                }
             }
         }
-        pair_overflow |= __any_sync(kFullMask, !ok);
-        if (!have_next || nxt.pair != cur.pair) {
-            if (pair_overflow && lane == 0) {
-                a.w.skip[cur.pair] = 1;
-                a.out.list[atomicAdd(a.out.count, 1)] = cur.pair;
+        if (last_panel) {
+            pair_overflow |= __any_sync(kFullMask, !ok);
+            if (c.row0 + kTileRows >= c.lq) {  // last tile of the pair
+                if (pair_overflow && lane == 0) {
+                    a.w.skip[c.pair] = 1;
+                    a.out.list[atomicAdd(a.out.count, 1)] = c.pair;
+                }
+                pair_overflow = false;
             }
-            pair_overflow = false;
         }
         __syncwarp();  // every lane is done with `stage` before it is refilled
-        cur = nxt; have = have_next; stage ^= 1;
+        ++consumed;
     }
 }
 
 // ------------------------------------------------------------------ T1e: edges
-template <typename MaskT>
+// One thread per source row.  Per destination row the K*K rank combinations are screened for
+// constraint C2 with two instructions each into a hit mask; only the hits (about one per three
+// row pairs) go through C3 (no ref already linked from this row inside [r_src, r_dst]), C4
+// (destination similarity >= min_sim) and the atomic OR into the destination's predecessor mask.
+template <typename MaskT, int K>
 __global__ void __launch_bounds__(256) tn_edges_kernel(const Batch b, const Workspace w) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int pair = (int)(idx / b.max_lq);
@@ -212,54 +240,80 @@ __global__ void __launch_bounds__(256) tn_edges_kernel(const Batch b, const Work
     const int q_src = (int)(idx - (long long)pair * b.max_lq);
     const int lq = b.lq[pair];
     if (q_src >= lq || w.skip[pair]) return;
-    const int K = b.topk, step = b.step;
+    const int step = b.step;
     const size_t nb = (size_t)pair * b.max_nodes;
     const uint16_t *ref_of = w.ref_of + nb;
     const float *sim_of = w.sim_of + nb;
-    MaskT *pred = reinterpret_cast<MaskT *>(w.pred) + nb;
+    MaskT *pz = reinterpret_cast<MaskT *>(w.pz) + 2 * nb;
 
-    int r_src[kMaxTop]; uint32_t window[kMaxTop];  // window[a]: refs linked from this row, relative to r_src[a]
+    int r_src[K]; uint32_t window[K];  // window[a]: refs linked from this row, relative to r_src[a]
 #pragma unroll
-    for (int x = 0; x < kMaxTop; ++x) {
-        r_src[x] = x < K ? (int)ref_of[q_src * K + x] : INT_MIN / 2;
-        window[x] = 0;
-    }
+    for (int x = 0; x < K; ++x) { r_src[x] = ref_of[q_src * K + x]; window[x] = 0; }
     const int q_end = min(lq, q_src + step);
     for (int q_dst = q_src + 1; q_dst < q_end; ++q_dst) {
-        uint32_t accepted = 0;
-        for (int bb = 0; bb < K; ++bb) {
-            const int vd = q_dst * K + bb;
-            if (!(sim_of[vd] >= b.min_sim)) continue;  // C4
-            const int rd = ref_of[vd];
-            MaskT bits = 0;
+        const uint16_t *r_dst = ref_of + q_dst * K;
+        uint32_t hits[K];  // hits[x]: destination ranks b with 0 < r_dst[b] - r_src[x] < step (C2)
 #pragma unroll
-            for (int x = 0; x < kMaxTop; ++x) {
-                const int d = rd - r_src[x];
-                if (d > 0 && d < step && !(window[x] & ((2u << d) - 1u)))  // C2, C3
-                    bits |= (MaskT)1 << ((step - 1 - (q_dst - q_src)) * K + x);
-            }
-            if (bits) {
+        for (int x = 0; x < K; ++x) hits[x] = 0;
+#pragma unroll
+        for (int bb = 0; bb < K; ++bb) {
+            const int rd = r_dst[bb];
+#pragma unroll
+            for (int x = 0; x < K; ++x)
+                hits[x] |= ((unsigned)(rd - r_src[x] - 1) < (unsigned)(step - 1) ? 1u : 0u) << bb;
+        }
+        uint32_t accepted = 0;
+        const int slot0 = (step - 1 - (q_dst - q_src)) * K;
+#pragma unroll
+        for (int x = 0; x < K; ++x) {
+            uint32_t h = hits[x];
+            while (h) {
+                const int bb = __ffs(h) - 1; h &= h - 1;
+                const int d = (int)r_dst[bb] - r_src[x];
+                if (window[x] & ((2u << d) - 1u)) continue;              // C3
+                if (!(sim_of[q_dst * K + bb] >= b.min_sim)) continue;    // C4
                 accepted |= 1u << bb;
+                const MaskT bit = (MaskT)1 << (slot0 + x);
                 if (sizeof(MaskT) == 8)
-                    atomicOr(reinterpret_cast<unsigned long long *>(&pred[vd]), (unsigned long long)bits);
+                    atomicOr(reinterpret_cast<unsigned long long *>(&pz[2 * (q_dst * K + bb)]), (unsigned long long)bit);
                 else
-                    atomicOr(reinterpret_cast<unsigned int *>(&pred[vd]), (unsigned int)bits);
+                    atomicOr(reinterpret_cast<unsigned int *>(&pz[2 * (q_dst * K + bb)]), (unsigned int)bit);
             }
         }
-        for (int bb = 0; bb < K; ++bb) {
-            if (!((accepted >> bb) & 1)) continue;
-            const int rd = ref_of[q_dst * K + bb];
+        while (accepted) {  // refs linked in this step constrain the later destination rows
+            const int bb = __ffs(accepted) - 1; accepted &= accepted - 1;
+            const int rd = r_dst[bb];
 #pragma unroll
-            for (int x = 0; x < kMaxTop; ++x) {
+            for (int x = 0; x < K; ++x) {
                 const int d = rd - r_src[x];
-                if (d >= 0 && d < step) window[x] |= 1u << d;
+                if ((unsigned)d < (unsigned)step) window[x] |= 1u << d;
             }
         }
     }
 }
 
+template <typename MaskT>
+void launch_edges(const Batch &b, const Workspace &w, int grid, cudaStream_t stream) {
+    switch (b.topk) {
+        case 1: tn_edges_kernel<MaskT, 1><<<grid, 256, 0, stream>>>(b, w); break;
+        case 2: tn_edges_kernel<MaskT, 2><<<grid, 256, 0, stream>>>(b, w); break;
+        case 3: tn_edges_kernel<MaskT, 3><<<grid, 256, 0, stream>>>(b, w); break;
+        case 4: tn_edges_kernel<MaskT, 4><<<grid, 256, 0, stream>>>(b, w); break;
+        case 5: tn_edges_kernel<MaskT, 5><<<grid, 256, 0, stream>>>(b, w); break;
+        case 6: tn_edges_kernel<MaskT, 6><<<grid, 256, 0, stream>>>(b, w); break;
+        case 7: tn_edges_kernel<MaskT, 7><<<grid, 256, 0, stream>>>(b, w); break;
+        default: tn_edges_kernel<MaskT, 8><<<grid, 256, 0, stream>>>(b, w); break;
+    }
+}
+
 // ------------------------------------------------------------------ T2: longest-path sweeps
-constexpr int kT2Threads = 128;  // 4 warps = 16 pairs per CTA
+// Four pairs per warp: an octet of lanes owns one pair, lane `sub` owns rank `sub` of the current
+// row layer.  Distances of the last 32 layers live in a shared-memory window (the relaxation only
+// looks step-1 <= 30 layers back), as do the per-layer maxima, the best-predecessor slots and the
+// current chain; the read-only node data is prefetched one layer ahead from global memory.
+constexpr int kT2Warps = 4;
+constexpr int kT2Threads = kT2Warps * 32;
+constexpr int kWin = 32;  // window depth in layers (power of two, >= tn_max_step - 1)
 
 __device__ __forceinline__ uint32_t oct_max(uint32_t v, unsigned mask) {
     v = max(v, __shfl_xor_sync(mask, v, 1));
@@ -277,118 +331,142 @@ __device__ __forceinline__ int oct_add(int v, unsigned mask) {
     return v + __shfl_xor_sync(mask, v, 4);
 }
 
-template <typename MaskT>
-struct PairState {
-    const MaskT *pred; MaskT *zero;
-    const float *sim_of; const uint16_t *ref_of;
-    float *dist; int8_t *slot; uint16_t *gen; uint16_t *chain; uint32_t *lbest;
-};
+template <typename MaskT> struct PZ;
+template <> struct PZ<uint32_t> { using type = uint2; };
+template <> struct PZ<uint64_t> { using type = ulonglong2; };
 
-// One lane relaxes its own node: FIRST maximal predecessor in ascending slot order.
+__host__ __device__ inline size_t t2_pair_bytes(int max_nodes, int max_lq) {
+    size_t b = (size_t)kWin * 8 * 4 + (size_t)kWin * 8 * 2;   // distance + generation windows
+    b += (size_t)max_lq * 4 + (size_t)max_lq * 2;            // layer maxima, chain
+    b += ((size_t)max_nodes + 15) / 16 * 16;                  // best-predecessor slots
+    return (b + 15) / 16 * 16;
+}
+
+// One lane relaxes its own node against the distance window: FIRST maximal predecessor in
+// ascending slot order (networkx keeps the first maximum).
 template <typename MaskT, bool FIRST>
-__device__ __forceinline__ void relax_node(const PairState<MaskT> &s, const int16_t *slot_off, int v,
-                                           int layer_base, float &best, int &best_slot, int &gen) {
-    MaskT pm = s.pred[v];
+__device__ __forceinline__ void relax_node(MaskT pm, MaskT zm, float w, int q, const float *wdist,
+                                           const uint16_t *wgen, const uint8_t *slot_oa, float &best,
+                                           int &best_slot, int &gen) {
     best = 0.0f; best_slot = -1; gen = 0;
-    if (!pm) return;
-    const MaskT zm = FIRST ? (MaskT)0 : s.zero[v];
-    const float w = s.sim_of[v];
     while (pm) {
         const int sl = sizeof(MaskT) == 8 ? __ffsll((long long)pm) - 1 : __ffs((int)pm) - 1;
         pm &= pm - 1;
-        const int src = layer_base + slot_off[sl];
-        const float cand = s.dist[src] + (((zm >> sl) & 1) ? 0.0f : w);
+        const int oa = slot_oa[sl];
+        const int wi = ((q - (oa >> 3)) & (kWin - 1)) * 8 + (oa & 7);
+        const float cand = wdist[wi] + (((zm >> sl) & 1) ? 0.0f : w);
         if (best_slot < 0 || cand > best) { best = cand; best_slot = sl; }
-        if (FIRST) gen = max(gen, (int)s.gen[src] + 1);
+        if (FIRST) gen = max(gen, (int)wgen[wi] + 1);
     }
-    if (!(best >= 0.0f)) { best = 0.0f; best_slot = -1; }  // networkx: negative best -> (0, v)
+    if (best_slot >= 0 && !(best >= 0.0f)) { best = 0.0f; best_slot = -1; }  // networkx: negative best -> (0, v)
 }
 
 template <typename MaskT>
 __global__ void __launch_bounds__(kT2Threads) tn_dp_kernel(const Batch b, const Workspace w, const WorkList out) {
-    __shared__ int16_t slot_off[64];
+    extern __shared__ __align__(16) unsigned char t2_smem[];
+    __shared__ uint8_t slot_oa[64];  // slot -> (layers back << 3) | source rank
     const int K = b.topk, step = b.step;
     if (threadIdx.x < 64) {
         const int sl = threadIdx.x;
-        slot_off[sl] = (int16_t)(sl % K - (step - 1 - sl / K) * K);
+        slot_oa[sl] = (uint8_t)(((step - 1 - sl / K) << 3) | (sl % K));
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, sub = lane & 7, oct = lane >> 3;
     const unsigned om = 0xFFu << (oct * 8);
-    const int pair = (blockIdx.x * (kT2Threads / 32) + (threadIdx.x >> 5)) * 4 + oct;
+    const int pair = (blockIdx.x * kT2Warps + (threadIdx.x >> 5)) * 4 + oct;
     if (pair >= b.n_pairs || w.skip[pair]) return;  // whole octet leaves together
+
+    unsigned char *mine = t2_smem + (size_t)((threadIdx.x >> 5) * 4 + oct) * t2_pair_bytes(b.max_nodes, b.max_lq);
+    float *wdist = reinterpret_cast<float *>(mine);
+    uint32_t *lbest = reinterpret_cast<uint32_t *>(wdist + kWin * 8);
+    uint16_t *wgen = reinterpret_cast<uint16_t *>(lbest + b.max_lq);
+    uint16_t *chain = wgen + kWin * 8;
+    int8_t *slot = reinterpret_cast<int8_t *>(chain + b.max_lq);
 
     const int lq = b.lq[pair];
     const int box_cap = b.max_path + 1;
     int32_t *boxes = b.boxes + (size_t)pair * box_cap * 4;
     const size_t nb = (size_t)pair * b.max_nodes;
-    PairState<MaskT> s;
-    s.pred = reinterpret_cast<const MaskT *>(w.pred) + nb;
-    s.zero = reinterpret_cast<MaskT *>(w.zero) + nb;
-    s.sim_of = w.sim_of + nb; s.ref_of = w.ref_of + nb;
-    s.dist = w.dist + nb; s.slot = w.slot + nb; s.gen = w.gen + nb;
-    s.chain = w.chain + (size_t)pair * b.max_lq;
-    s.lbest = w.lbest + (size_t)pair * b.max_lq;
+    using PZT = typename PZ<MaskT>::type;
+    PZT *pz = reinterpret_cast<PZT *>(w.pz) + nb;
+    const float *sim_of = w.sim_of + nb;
+    const uint16_t *ref_of = w.ref_of + nb;
+    float *dist = w.dist + nb;
+    uint16_t *gen = w.gen + nb;
     const bool ranked = sub < K;
 
-    // first sweep: every layer
-    for (int q = 0; q < lq; ++q) {
-        const int base = q * K, v = base + sub;
-        float d = 0.0f;
-        if (ranked) {
-            int sl, g;
-            relax_node<MaskT, true>(s, slot_off, v, base, d, sl, g);
-            s.dist[v] = d; s.slot[v] = (int8_t)sl; s.gen[v] = (uint16_t)g; s.zero[v] = 0;
+    for (int i = sub; i < kWin * 8; i += 8) { wdist[i] = 0.0f; wgen[i] = 0; }
+    __syncwarp(om);
+
+    // ---- first sweep: every layer; node data prefetched one layer ahead
+    {
+        PZT nx_pz = {}; float nx_w = 0.0f;
+        if (ranked && lq > 0) { nx_pz = pz[sub]; nx_w = sim_of[sub]; }
+        for (int q = 0; q < lq; ++q) {
+            const int v = q * K + sub;
+            const PZT cur = nx_pz; const float wv = nx_w;
+            if (ranked && q + 1 < lq) { nx_pz = pz[v + K]; nx_w = sim_of[v + K]; }
+            float d = 0.0f; int sl = -1, g = 0;
+            if (ranked) {
+                relax_node<MaskT, true>((MaskT)cur.x, (MaskT)0, wv, q, wdist, wgen, slot_oa, d, sl, g);
+                dist[v] = d; gen[v] = (uint16_t)g; slot[v] = (int8_t)sl;
+            }
+            // slot q & 31 held layer q-32, which nobody reads any more (step-1 <= 30)
+            wdist[(q & (kWin - 1)) * 8 + sub] = d;
+            wgen[(q & (kWin - 1)) * 8 + sub] = (uint16_t)g;
+            const uint32_t lm = oct_max(__float_as_uint(d), om);  // dist >= +0: bits are ordered
+            if (sub == 0) lbest[q] = lm;
+            __syncwarp(om);
         }
-        const uint32_t lm = oct_max(ranked ? __float_as_uint(d) : 0u, om);  // dist >= +0: bits are ordered
-        if (sub == 0) s.lbest[q] = lm;
-        __syncwarp(om);
     }
 
     int n_boxes = 0;
     bool ambiguous = false;
     for (int round = 0; round <= b.max_path; ++round) {
-        // end node: maximum distance; ties -> smallest Kahn generation
+        // ---- end node: maximum distance; ties -> smallest Kahn generation
         uint32_t mk = 0;
-        for (int q = sub; q < lq; q += 8) mk = max(mk, s.lbest[q]);
+        for (int q = sub; q < lq; q += 8) mk = max(mk, lbest[q]);
         mk = oct_max(mk, om);
         if (mk == 0u) break;  // only zero-length paths left: networkx returns [source]
         int bg = INT_MAX, bv = -1, cnt = 0;
         for (int q = sub; q < lq; q += 8) {
-            if (s.lbest[q] != mk) continue;
+            if (lbest[q] != mk) continue;
             for (int r = 0; r < K; ++r) {
                 const int v = q * K + r;
-                if (__float_as_uint(s.dist[v]) != mk) continue;
-                const int g = s.gen[v];
+                if (__float_as_uint(dist[v]) != mk) continue;
+                const int g = gen[v];
                 if (g < bg) { bg = g; bv = v; cnt = 1; }
                 else if (g == bg) ++cnt;
             }
         }
         const int g_min = oct_min(bg, om);
-        const bool mine = bg == g_min;
-        if (oct_add(mine ? cnt : 0, om) > 1) { ambiguous = true; break; }
-        const unsigned who = __ballot_sync(om, mine) & om;
+        const bool mine_best = bg == g_min;
+        if (oct_add(mine_best ? cnt : 0, om) > 1) { ambiguous = true; break; }
+        const unsigned who = __ballot_sync(om, mine_best) & om;
         const int end = __shfl_sync(om, bv, __ffs(who) - 1);
 
+        // ---- walk the chain back, zero its edges, score it, filter the box (one lane)
         int q_first_dst = 0, q_last = 0;
         if (sub == 0) {
             int len = 0;
             for (int v = end;;) {
-                s.chain[len++] = (uint16_t)v;
-                const int sl = s.slot[v];
+                chain[len++] = (uint16_t)v;
+                const int sl = slot[v];
                 if (sl < 0) break;
-                s.zero[v] |= (MaskT)1 << sl;  // spent edge
-                v = (v / K) * K + slot_off[sl];
+                MaskT *zp = reinterpret_cast<MaskT *>(&pz[v]) + 1;
+                *zp |= (MaskT)1 << sl;  // spent edge
+                const int oa = slot_oa[sl];
+                v = (v / K - (oa >> 3)) * K + (oa & 7);
             }
             float score = 0.0f;
-            for (int i = len - 1; i >= 0; --i) score += s.sim_of[s.chain[i]];
-            const int first = s.chain[len - 1], last = s.chain[0];
-            q_first_dst = (len >= 2 ? (int)s.chain[len - 2] : last) / K;
+            for (int i = len - 1; i >= 0; --i) score += sim_of[chain[i]];
+            const int first = chain[len - 1], last = chain[0];
+            q_first_dst = (len >= 2 ? (int)chain[len - 2] : last) / K;
             q_last = last / K;
             int q_lo = 0, q_hi = 0, r_lo = 0, r_hi = 0;
             if (score > 0.0f) {  // q and (by C2) r increase strictly along a chain
                 q_lo = first / K; q_hi = q_last;
-                r_lo = s.ref_of[first]; r_hi = s.ref_of[last];
+                r_lo = ref_of[first]; r_hi = ref_of[last];
             }
             const double mean_extent = (double)(r_hi - r_lo + q_hi - q_lo) / 2.0;
             double worst = 0.0;
@@ -417,23 +495,32 @@ __global__ void __launch_bounds__(kT2Threads) tn_dp_kernel(const Batch b, const 
         __syncwarp(om);
         if (round == b.max_path) break;
 
-        // incremental sweep: layers before the first zeroed edge keep their distances, and the
-        // wave dies `step-1` layers after the last distance that changed
+        // ---- incremental sweep: layers before the first zeroed edge keep their distances, and
+        // the wave dies `step-1` layers after the last distance that changed
+        for (int o = 1; o < step; ++o) {  // refill the window behind the start layer
+            const int qq = q_first_dst - o;
+            if (qq >= 0) wdist[(qq & (kWin - 1)) * 8 + sub] = ranked ? dist[qq * K + sub] : 0.0f;
+        }
+        __syncwarp(om);
         int last_changed = INT_MIN / 2;
+        PZT nx_pz = {}; float nx_w = 0.0f, nx_old = 0.0f;
+        if (ranked) { const int v0 = q_first_dst * K + sub; nx_pz = pz[v0]; nx_w = sim_of[v0]; nx_old = dist[v0]; }
         for (int q = q_first_dst; q < lq && (q <= q_last || q <= last_changed + step - 1); ++q) {
-            const int base = q * K, v = base + sub;
-            float d = 0.0f;
+            const int v = q * K + sub;
+            const PZT cur = nx_pz; const float wv = nx_w, before = nx_old;
+            if (ranked && q + 1 < lq) { nx_pz = pz[v + K]; nx_w = sim_of[v + K]; nx_old = dist[v + K]; }
+            float d = 0.0f; int sl = -1, g = 0;
             bool changed = false;
             if (ranked) {
-                int sl, g;
-                const uint32_t before = __float_as_uint(s.dist[v]);
-                relax_node<MaskT, false>(s, slot_off, v, base, d, sl, g);
-                changed = __float_as_uint(d) != before;
-                s.dist[v] = d; s.slot[v] = (int8_t)sl;
+                relax_node<MaskT, false>((MaskT)cur.x, (MaskT)cur.y, wv, q, wdist, wgen, slot_oa, d, sl, g);
+                changed = __float_as_uint(d) != __float_as_uint(before);
+                if (changed) dist[v] = d;
+                slot[v] = (int8_t)sl;
             }
+            wdist[(q & (kWin - 1)) * 8 + sub] = d;
             if (__ballot_sync(om, changed) & om) last_changed = q;
-            const uint32_t lm = oct_max(ranked ? __float_as_uint(d) : 0u, om);
-            if (sub == 0) s.lbest[q] = lm;
+            const uint32_t lm = oct_max(__float_as_uint(d), om);
+            if (sub == 0) lbest[q] = lm;
             __syncwarp(om);
         }
     }
@@ -484,9 +571,7 @@ int launch_topk(const T1Args &a, int grid, size_t smem, cudaStream_t stream) {
     return VSC_OK;
 }
 
-size_t t1_smem_bytes(int max_lr) {
-    return kT1Warps * ((t1_warp_bytes(tile_pitch(max_lr)) + 127) / 128 * 128);
-}
+size_t t1_smem_bytes() { return sizeof(T1Smem) * kT1Warps; }
 
 }  // namespace
 
@@ -497,8 +582,9 @@ bool pipeline_supported(const Batch &b) {
     if (b.max_lr > vsc::kBlockCols * vsc::kMaxRowBlocks || b.max_lr < b.topk) return false;
     if (b.topk < 1 || b.topk > kMaxTop) return false;
     if ((reinterpret_cast<uintptr_t>(b.sims) & 15u) != 0) return false;
-    if (b.max_nodes > 65535) return false;
-    return t1_smem_bytes(b.max_lr) <= 227 * 1024;
+    if (b.max_nodes > 65535 || b.step - 1 > kWin) return false;
+    if (t2_pair_bytes(b.max_nodes, b.max_lq) * kT2Warps * 4 > 200 * 1024) return false;
+    return t1_smem_bytes() <= 227 * 1024;
 }
 
 int launch_pipeline(const Batch &b, const WorkList &out, cudaStream_t stream) {
@@ -508,35 +594,31 @@ int launch_pipeline(const Batch &b, const WorkList &out, cudaStream_t stream) {
     // one stream-ordered allocation, carved by alignment
     size_t sz = 0;
     auto take = [&](size_t bytes) { size_t at = sz; sz += (bytes + 255) / 256 * 256; return at; };
-    const size_t o_pred = take(P * N * mask_bytes), o_zero = take(P * N * mask_bytes);
-    const size_t o_sim = take(P * N * 4), o_dist = take(P * N * 4), o_lbest = take(P * L * 4);
-    const size_t o_ref = take(P * N * 2), o_gen = take(P * N * 2), o_chain = take(P * L * 2);
-    const size_t o_slot = take(P * N), o_skip = take(P), o_cursor = take(4);
+    const size_t o_pz = take(P * N * mask_bytes * 2);
+    const size_t o_sim = take(P * N * 4), o_dist = take(P * N * 4);
+    const size_t o_ref = take(P * N * 2), o_gen = take(P * N * 2);
+    const size_t o_skip = take(P), o_cursor = take(4);
     unsigned char *base = nullptr;
     VSC_CUDA_CHECK(cudaMallocAsync(&base, sz, stream));
     Workspace w;
-    w.pred = base + o_pred; w.zero = base + o_zero;
+    w.pz = base + o_pz;
     w.sim_of = reinterpret_cast<float *>(base + o_sim); w.dist = reinterpret_cast<float *>(base + o_dist);
-    w.lbest = reinterpret_cast<uint32_t *>(base + o_lbest);
     w.ref_of = reinterpret_cast<uint16_t *>(base + o_ref); w.gen = reinterpret_cast<uint16_t *>(base + o_gen);
-    w.chain = reinterpret_cast<uint16_t *>(base + o_chain);
-    w.slot = reinterpret_cast<int8_t *>(base + o_slot);
     w.skip = base + o_skip; w.cursor = reinterpret_cast<int32_t *>(base + o_cursor);
     int rc = VSC_OK;
     auto fail = [&](cudaError_t e, const char *what) {
         if (e != cudaSuccess && rc == VSC_OK) { vsc::set_error("%s: %s", what, cudaGetErrorString(e)); rc = VSC_ERR_CUDA; }
     };
-    fail(cudaMemsetAsync(w.pred, 0, P * N * mask_bytes, stream), "memset pred");
+    fail(cudaMemsetAsync(w.pz, 0, P * N * mask_bytes * 2, stream), "memset edge masks");
     fail(cudaMemsetAsync(w.skip, 0, (o_cursor - o_skip) + 4, stream), "memset flags");
 
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (rc == VSC_OK) {
-        T1Args a; a.b = b; a.w = w; a.out = out; a.pitch = tile_pitch(b.max_lr);
-        const size_t smem = t1_smem_bytes(b.max_lr);
-        const int per_sm = (int)((227 * 1024) / (smem + 1024)) > 0 ? (int)((227 * 1024) / (smem + 1024)) : 1;
-        const int grid = sms * per_sm;
+        T1Args a; a.b = b; a.w = w; a.out = out;
+        const size_t smem = t1_smem_bytes();
+        const int grid = sms;  // persistent: one CTA of kT1Warps warps per SM
         switch (b.topk) {
             case 1: rc = launch_topk<1>(a, grid, smem, stream); break;
             case 2: rc = launch_topk<2>(a, grid, smem, stream); break;
@@ -552,16 +634,22 @@ int launch_pipeline(const Batch &b, const WorkList &out, cudaStream_t stream) {
     if (rc == VSC_OK) {
         const long long threads = (long long)b.n_pairs * b.max_lq;
         const int grid = (int)((threads + 255) / 256);
-        if (wide) tn_edges_kernel<uint64_t><<<grid, 256, 0, stream>>>(b, w);
-        else tn_edges_kernel<uint32_t><<<grid, 256, 0, stream>>>(b, w);
+        if (wide) launch_edges<uint64_t>(b, w, grid, stream);
+        else launch_edges<uint32_t>(b, w, grid, stream);
         fail(cudaGetLastError(), "tn_edges_kernel");
         vsc::count_launch();
     }
     if (rc == VSC_OK) {
-        const int pairs_per_cta = (kT2Threads / 32) * 4;
+        const int pairs_per_cta = kT2Warps * 4;
         const int grid = (b.n_pairs + pairs_per_cta - 1) / pairs_per_cta;
-        if (wide) tn_dp_kernel<uint64_t><<<grid, kT2Threads, 0, stream>>>(b, w, out);
-        else tn_dp_kernel<uint32_t><<<grid, kT2Threads, 0, stream>>>(b, w, out);
+        const size_t smem = t2_pair_bytes(b.max_nodes, b.max_lq) * pairs_per_cta;
+        if (wide) {
+            fail(cudaFuncSetAttribute(tn_dp_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+            tn_dp_kernel<uint64_t><<<grid, kT2Threads, smem, stream>>>(b, w, out);
+        } else {
+            fail(cudaFuncSetAttribute(tn_dp_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+            tn_dp_kernel<uint32_t><<<grid, kT2Threads, smem, stream>>>(b, w, out);
+        }
         fail(cudaGetLastError(), "tn_dp_kernel");
         vsc::count_launch();
     }
@@ -586,6 +674,7 @@ extern "C" int vcsl_tn_batch(const float *d_sims, const int64_t *d_off, const in
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (!p || n_pairs < 0) { vsc::set_error("vcsl_tn_batch: bad arguments"); return VSC_ERR_INVALID; }
     if (n_pairs == 0) return VSC_OK;
+    vsc::keep_pool_cached();
     if (!d_sims || !d_off || !d_lq || !d_lr || !d_boxes || !d_n_boxes) {
         vsc::set_error("vcsl_tn_batch: null device pointer"); return VSC_ERR_INVALID;
     }
