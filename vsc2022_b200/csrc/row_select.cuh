@@ -54,36 +54,46 @@ struct RowTopK {
         return m;
     }
     // After every block went through add_block (block maxima in bm[b*stride]): finish the row.
-    // `row` may be any 16-byte aligned pointer to the lr columns.  Returns false on overflow.
+    // `row` may be any 16-byte aligned pointer to the lr columns (global memory on the device: the
+    // K hot blocks are L2 hits).  `stash`: 16 floats of per-thread scratch.  Returns false on overflow.
     __host__ __device__ __forceinline__ bool finish(const float *row, int lr, const float *bm, float *cand_val,
-                                                    int *cand_col, int stride, float (&val)[K], int (&col)[K]) const {
+                                                    int *cand_col, int stride, float *stash, float (&val)[K],
+                                                    int (&col)[K]) const {
         const float4 *row4 = reinterpret_cast<const float4 *>(row);
+        float4 *stash4 = reinterpret_cast<float4 *>(stash);
         const int n_chunks = lr >> 2;
         const int n_blocks = (lr + kBlockCols - 1) / kBlockCols;
         const float t = top[K - 1];
+        const float4 none = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
         uint32_t hot = 0;
         for (int b = 0; b < n_blocks; ++b)
             if (bm[b * stride] >= t) hot |= 1u << b;
         int n_cand = 0;
         bool overflow = false;
-        while (hot) {  // exactly K iterations unless block maxima tie
+        float4 nxt[4];
+        int b_next = -1;
+        auto fetch = [&]() {  // start loading the next hot block (exactly K of them unless maxima tie)
+            if (!hot) { b_next = -1; return; }
 #if defined(__CUDA_ARCH__)
-            const int b = __ffs(hot) - 1;
+            b_next = __ffs(hot) - 1;
 #else
-            const int b = __builtin_ctz(hot);
+            b_next = __builtin_ctz(hot);
 #endif
             hot &= hot - 1;
-            const int c0 = b * 4;
-            // branch-free hit mask over the block's 16 columns, then one short loop per hit
-            uint32_t hits = 0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) nxt[c] = b_next * 4 + c < n_chunks ? row4[b_next * 4 + c] : none;
+        };
+        fetch();
+        while (b_next >= 0) {
+            const int c0 = b_next * 4;
+            uint32_t hits = 0;  // branch-free hit mask over the block's 16 columns
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                if (c0 + c < n_chunks) {
-                    const float4 v = row4[c0 + c];
-                    hits |= (v.x >= t ? 1u : 0u) << (4 * c) | (v.y >= t ? 2u : 0u) << (4 * c) |
-                            (v.z >= t ? 4u : 0u) << (4 * c) | (v.w >= t ? 8u : 0u) << (4 * c);
-                }
+                stash4[c] = nxt[c];
+                hits |= ((nxt[c].x >= t ? 1u : 0u) | (nxt[c].y >= t ? 2u : 0u) | (nxt[c].z >= t ? 4u : 0u) |
+                         (nxt[c].w >= t ? 8u : 0u)) << (4 * c);
             }
+            fetch();  // overlaps the next block's L2 latency with the (short) hit loop
             while (hits) {
 #if defined(__CUDA_ARCH__)
                 const int k = __ffs(hits) - 1;
@@ -92,7 +102,7 @@ struct RowTopK {
 #endif
                 hits &= hits - 1;
                 if (n_cand < kMaxCand) {
-                    cand_val[n_cand * stride] = row[c0 * 4 + k];
+                    cand_val[n_cand * stride] = stash[k];
                     cand_col[n_cand * stride] = c0 * 4 + k;
                     ++n_cand;
                 } else {
@@ -140,7 +150,8 @@ __host__ __device__ __forceinline__ bool select_row(const float *row, int lr, fl
             if (c < left) chunk[c] = row4[b * 4 + c];
         bm[b * stride] = sel.add_block(chunk, left < 4 ? left : 4);
     }
-    return sel.finish(row, lr, bm, cand_val, cand_col, stride, val, col);
+    alignas(16) float stash[16];
+    return sel.finish(row, lr, bm, cand_val, cand_col, stride, stash, val, col);
 }
 
 }  // namespace vsc

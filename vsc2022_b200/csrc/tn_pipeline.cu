@@ -37,15 +37,20 @@ using vsc::tn::kMaxTop;
 
 // ------------------------------------------------------------------ workspace
 struct Workspace {
-    uint16_t *ref_of;   // [P][N]
-    float *sim_of;      // [P][N]
-    void *pz;           // [P][N][2] uint32 or uint64: {predecessor mask, zeroed-edge mask}
-    float *dist;        // [P][N]
-    int8_t *slot;       // [P][N]
-    uint16_t *gen;      // [P][N]
+    uint16_t *ref_of;   // [P][N] reference frame of node
+    void *rec;          // [P][N] NodeRec: {predecessor mask, zeroed-edge mask, similarity, distance}
+    uint16_t *gen;      // [P][N] Kahn generation
+    int rec_bytes, sim_off;  // record size and byte offset of the similarity inside it
     uint8_t *skip;      // [P] 1 = handed to the general kernel
     int32_t *cursor;    // T1 pair counter
 };
+
+template <typename MaskT>
+struct alignas(16) NodeRec {
+    MaskT pred, zero;
+    float sim, dist;
+};
+static_assert(sizeof(NodeRec<uint32_t>) == 16 && sizeof(NodeRec<uint64_t>) == 32, "record layout");
 
 // ------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -77,8 +82,9 @@ __device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t b
 }
 
 // Ampere-style 16-byte async copy global -> shared (bypasses L1); one commit group per panel.
-__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+template <int OFFSET>
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0+%2], [%1], 16;" ::"r"(dst_smem), "l"(src), "n"(OFFSET) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -93,13 +99,14 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // copies per batch -- was TMA-issue-bound at ~27 cycles/op/SM, 2.4 TB/s; see profiles/.)
 // Pass 1 (block maxima + K best maxima) runs on the panels; at the end of a row the K hot blocks
 // are re-read straight from global memory (L2 hits) for the exact selection.
-constexpr int kT1Warps = 6;
+constexpr int kT1Warps = 8;
 constexpr int kT1Threads = kT1Warps * 32;
 constexpr int kTileRows = 32;
 constexpr int kPanelCols = 64;
 constexpr int kPanelPitch = 68;
-constexpr int kStages = 3;
+constexpr int kStages = 2;
 constexpr int kPanelBytes = kTileRows * kPanelPitch * 4;
+constexpr int kStashPitch = 20;
 
 struct Cursor {   // one panel of work
     int pair, row0, col0, lq, lr;
@@ -111,6 +118,7 @@ struct alignas(128) T1Smem {   // per warp
     float bm[vsc::kMaxRowBlocks * 32];
     float cand_val[vsc::kMaxCand * 32];
     int cand_col[vsc::kMaxCand * 32];
+    float stash[32 * kStashPitch];   // 16 floats per lane, pitch 20 words: conflict-free STS.128
     Cursor ring[kStages];
 };
 
@@ -153,15 +161,22 @@ __global__ void __launch_bounds__(kT1Threads, 1) tn_topk_kernel(const T1Args a) 
     Cursor ic;                       // next panel to request
     bool more = claim_pair(a, lane, ic);
     const int half = lane >> 4, ch = (lane & 15) * 4;  // fill role: row parity, column offset
+    const uint32_t panel_s = smem_u32(&sm.panel[0][0]) + (uint32_t)(half * kPanelPitch + ch) * 4u;
     auto issue = [&](int stage) {    // request panel `ic` into `stage`, then step `ic`
         if (lane == 0) sm.ring[stage] = ic;
         if (ic.col0 + ch < ic.lr) {
             const float *src = ic.base + (size_t)(ic.row0 + half) * ic.lr + ic.col0 + ch;
-            float *dst = &sm.panel[stage][half * kPanelPitch + ch];
-            const int rows = ic.lq - ic.row0 - half;  // rows left for this lane's parity
-#pragma unroll
-            for (int i = 0; i < kTileRows / 2; ++i)
-                if (2 * i < rows) cp_async16(dst + 2 * i * kPanelPitch, src + (size_t)2 * i * ic.lr);
+            const uint32_t dst = panel_s + (uint32_t)stage * kPanelBytes;
+            const int n = (ic.lq - ic.row0 - half + 1) >> 1;  // rows of this lane's parity left in the pair
+            const size_t stride = (size_t)2 * ic.lr;
+#define VSC_COPY_ROW(I)                                                        \
+            if ((I) < n) cp_async16<(I) * 2 * kPanelPitch * 4>(dst, src);        \
+            src += stride;
+            VSC_COPY_ROW(0) VSC_COPY_ROW(1) VSC_COPY_ROW(2) VSC_COPY_ROW(3)
+            VSC_COPY_ROW(4) VSC_COPY_ROW(5) VSC_COPY_ROW(6) VSC_COPY_ROW(7)
+            VSC_COPY_ROW(8) VSC_COPY_ROW(9) VSC_COPY_ROW(10) VSC_COPY_ROW(11)
+            VSC_COPY_ROW(12) VSC_COPY_ROW(13) VSC_COPY_ROW(14) VSC_COPY_ROW(15)
+#undef VSC_COPY_ROW
         }
         cp_async_commit();
         ic.col0 += kPanelCols;
@@ -203,12 +218,19 @@ __global__ void __launch_bounds__(kT1Threads, 1) tn_topk_kernel(const T1Args a) 
             if (last_panel) {
                 float val[K]; int col[K];
                 ok = sel.finish(c.base + (size_t)row * c.lr, c.lr, sm.bm + lane, sm.cand_val + lane,
-                                sm.cand_col + lane, 32, val, col);
+                                sm.cand_col + lane, 32, sm.stash + lane * kStashPitch, val, col);
                 const size_t node = (size_t)c.pair * a.b.max_nodes + (size_t)row * K;
+                unsigned char *rec = static_cast<unsigned char *>(a.w.rec) + node * a.w.rec_bytes;
 #pragma unroll
                 for (int i = 0; i < K; ++i) {
                     a.w.ref_of[node + i] = (uint16_t)col[i];
-                    a.w.sim_of[node + i] = val[i];
+                    // whole record in 16-byte stores: masks and distance start at zero
+                    if (a.w.rec_bytes == 16) {
+                        *reinterpret_cast<float4 *>(rec + i * 16) = make_float4(0.f, 0.f, val[i], 0.f);
+                    } else {
+                        *reinterpret_cast<float4 *>(rec + i * 32) = make_float4(0.f, 0.f, 0.f, 0.f);
+                        *reinterpret_cast<float4 *>(rec + i * 32 + 16) = make_float4(val[i], 0.f, 0.f, 0.f);
+                    }
                 }
             }
         }
@@ -243,8 +265,7 @@ __global__ void __launch_bounds__(256) tn_edges_kernel(const Batch b, const Work
     const int step = b.step;
     const size_t nb = (size_t)pair * b.max_nodes;
     const uint16_t *ref_of = w.ref_of + nb;
-    const float *sim_of = w.sim_of + nb;
-    MaskT *pz = reinterpret_cast<MaskT *>(w.pz) + 2 * nb;
+    NodeRec<MaskT> *rec = static_cast<NodeRec<MaskT> *>(w.rec) + nb;
 
     int r_src[K]; uint32_t window[K];  // window[a]: refs linked from this row, relative to r_src[a]
 #pragma unroll
@@ -271,13 +292,13 @@ __global__ void __launch_bounds__(256) tn_edges_kernel(const Batch b, const Work
                 const int bb = __ffs(h) - 1; h &= h - 1;
                 const int d = (int)r_dst[bb] - r_src[x];
                 if (window[x] & ((2u << d) - 1u)) continue;              // C3
-                if (!(sim_of[q_dst * K + bb] >= b.min_sim)) continue;    // C4
+                if (!(rec[q_dst * K + bb].sim >= b.min_sim)) continue;   // C4
                 accepted |= 1u << bb;
                 const MaskT bit = (MaskT)1 << (slot0 + x);
                 if (sizeof(MaskT) == 8)
-                    atomicOr(reinterpret_cast<unsigned long long *>(&pz[2 * (q_dst * K + bb)]), (unsigned long long)bit);
+                    atomicOr(reinterpret_cast<unsigned long long *>(&rec[q_dst * K + bb].pred), (unsigned long long)bit);
                 else
-                    atomicOr(reinterpret_cast<unsigned int *>(&pz[2 * (q_dst * K + bb)]), (unsigned int)bit);
+                    atomicOr(reinterpret_cast<unsigned int *>(&rec[q_dst * K + bb].pred), (unsigned int)bit);
             }
         }
         while (accepted) {  // refs linked in this step constrain the later destination rows
@@ -308,52 +329,39 @@ void launch_edges(const Batch &b, const Workspace &w, int grid, cudaStream_t str
 
 // ------------------------------------------------------------------ T2: longest-path sweeps
 // Four pairs per warp: an octet of lanes owns one pair, lane `sub` owns rank `sub` of the current
-// row layer.  Distances of the last 32 layers live in a shared-memory window (the relaxation only
-// looks step-1 <= 30 layers back), as do the per-layer maxima, the best-predecessor slots and the
-// current chain; the read-only node data is prefetched one layer ahead from global memory.
+// row layer.  Distances of the last D >= step-1 layers live in a shared-memory window, as do the
+// per-layer maxima, the best-predecessor slots and the current chain; the 16-byte node record
+// (masks, similarity, distance) is prefetched one layer ahead with a single 128-bit load.  The
+// grid is sized so that every pair of a batch is resident at once: the kernel is a chain of
+// dependent shared-memory operations, so throughput comes from pairs in flight, not from IPC.
 constexpr int kT2Warps = 4;
 constexpr int kT2Threads = kT2Warps * 32;
-constexpr int kWin = 32;  // window depth in layers (power of two, >= tn_max_step - 1)
 
-__device__ __forceinline__ uint32_t oct_max(uint32_t v, unsigned mask) {
-    v = max(v, __shfl_xor_sync(mask, v, 1));
-    v = max(v, __shfl_xor_sync(mask, v, 2));
-    return max(v, __shfl_xor_sync(mask, v, 4));
+__host__ __device__ inline int window_depth(int step) {  // power of two >= step-1
+    int d = 1;
+    while (d < step - 1) d <<= 1;
+    return d;
 }
-__device__ __forceinline__ int oct_min(int v, unsigned mask) {
-    v = min(v, __shfl_xor_sync(mask, v, 1));
-    v = min(v, __shfl_xor_sync(mask, v, 2));
-    return min(v, __shfl_xor_sync(mask, v, 4));
-}
-__device__ __forceinline__ int oct_add(int v, unsigned mask) {
-    v += __shfl_xor_sync(mask, v, 1);
-    v += __shfl_xor_sync(mask, v, 2);
-    return v + __shfl_xor_sync(mask, v, 4);
-}
-
-template <typename MaskT> struct PZ;
-template <> struct PZ<uint32_t> { using type = uint2; };
-template <> struct PZ<uint64_t> { using type = ulonglong2; };
-
-__host__ __device__ inline size_t t2_pair_bytes(int max_nodes, int max_lq) {
-    size_t b = (size_t)kWin * 8 * 4 + (size_t)kWin * 8 * 2;   // distance + generation windows
-    b += (size_t)max_lq * 4 + (size_t)max_lq * 2;            // layer maxima, chain
-    b += ((size_t)max_nodes + 15) / 16 * 16;                  // best-predecessor slots
+__host__ __device__ inline size_t t2_pair_bytes(int max_nodes, int max_lq, int step) {
+    const size_t d = (size_t)window_depth(step);
+    size_t b = d * 8 * 4 + d * 8 * 2;                     // distance + generation windows
+    b += (size_t)max_lq * 4 + (size_t)max_lq * 2;        // layer maxima, chain
+    b += (size_t)max_nodes;                               // best-predecessor slots
     return (b + 15) / 16 * 16;
 }
 
 // One lane relaxes its own node against the distance window: FIRST maximal predecessor in
 // ascending slot order (networkx keeps the first maximum).
-template <typename MaskT, bool FIRST>
-__device__ __forceinline__ void relax_node(MaskT pm, MaskT zm, float w, int q, const float *wdist,
-                                           const uint16_t *wgen, const uint8_t *slot_oa, float &best,
+template <typename MaskT, int K, bool FIRST>
+__device__ __forceinline__ void relax_node(MaskT pm, MaskT zm, float w, int q, int step, int wmask,
+                                           const float *wdist, const uint16_t *wgen, float &best,
                                            int &best_slot, int &gen) {
     best = 0.0f; best_slot = -1; gen = 0;
     while (pm) {
         const int sl = sizeof(MaskT) == 8 ? __ffsll((long long)pm) - 1 : __ffs((int)pm) - 1;
         pm &= pm - 1;
-        const int oa = slot_oa[sl];
-        const int wi = ((q - (oa >> 3)) & (kWin - 1)) * 8 + (oa & 7);
+        const int grp = sl / K;  // compile-time divisor
+        const int wi = ((q - (step - 1 - grp)) & wmask) * 8 + (sl - grp * K);
         const float cand = wdist[wi] + (((zm >> sl) & 1) ? 0.0f : w);
         if (best_slot < 0 || cand > best) { best = cand; best_slot = sl; }
         if (FIRST) gen = max(gen, (int)wgen[wi] + 1);
@@ -361,60 +369,54 @@ __device__ __forceinline__ void relax_node(MaskT pm, MaskT zm, float w, int q, c
     if (best_slot >= 0 && !(best >= 0.0f)) { best = 0.0f; best_slot = -1; }  // networkx: negative best -> (0, v)
 }
 
-template <typename MaskT>
+template <typename MaskT, int K>
 __global__ void __launch_bounds__(kT2Threads) tn_dp_kernel(const Batch b, const Workspace w, const WorkList out) {
     extern __shared__ __align__(16) unsigned char t2_smem[];
-    __shared__ uint8_t slot_oa[64];  // slot -> (layers back << 3) | source rank
-    const int K = b.topk, step = b.step;
-    if (threadIdx.x < 64) {
-        const int sl = threadIdx.x;
-        slot_oa[sl] = (uint8_t)(((step - 1 - sl / K) << 3) | (sl % K));
-    }
-    __syncthreads();
+    const int step = b.step;
     const int lane = threadIdx.x & 31, sub = lane & 7, oct = lane >> 3;
     const unsigned om = 0xFFu << (oct * 8);
     const int pair = (blockIdx.x * kT2Warps + (threadIdx.x >> 5)) * 4 + oct;
     if (pair >= b.n_pairs || w.skip[pair]) return;  // whole octet leaves together
 
-    unsigned char *mine = t2_smem + (size_t)((threadIdx.x >> 5) * 4 + oct) * t2_pair_bytes(b.max_nodes, b.max_lq);
+    const int depth = window_depth(step), wmask = depth - 1;
+    unsigned char *mine = t2_smem + (size_t)((threadIdx.x >> 5) * 4 + oct) * t2_pair_bytes(b.max_nodes, b.max_lq, step);
     float *wdist = reinterpret_cast<float *>(mine);
-    uint32_t *lbest = reinterpret_cast<uint32_t *>(wdist + kWin * 8);
+    uint32_t *lbest = reinterpret_cast<uint32_t *>(wdist + depth * 8);
     uint16_t *wgen = reinterpret_cast<uint16_t *>(lbest + b.max_lq);
-    uint16_t *chain = wgen + kWin * 8;
+    uint16_t *chain = wgen + depth * 8;
     int8_t *slot = reinterpret_cast<int8_t *>(chain + b.max_lq);
 
     const int lq = b.lq[pair];
     const int box_cap = b.max_path + 1;
     int32_t *boxes = b.boxes + (size_t)pair * box_cap * 4;
     const size_t nb = (size_t)pair * b.max_nodes;
-    using PZT = typename PZ<MaskT>::type;
-    PZT *pz = reinterpret_cast<PZT *>(w.pz) + nb;
-    const float *sim_of = w.sim_of + nb;
+    using Rec = NodeRec<MaskT>;
+    Rec *rec = static_cast<Rec *>(w.rec) + nb;
     const uint16_t *ref_of = w.ref_of + nb;
-    float *dist = w.dist + nb;
     uint16_t *gen = w.gen + nb;
     const bool ranked = sub < K;
 
-    for (int i = sub; i < kWin * 8; i += 8) { wdist[i] = 0.0f; wgen[i] = 0; }
+    for (int i = sub; i < depth * 8; i += 8) { wdist[i] = 0.0f; wgen[i] = 0; }
     __syncwarp(om);
 
-    // ---- first sweep: every layer; node data prefetched one layer ahead
+    // ---- first sweep: every layer; node record prefetched one layer ahead
     {
-        PZT nx_pz = {}; float nx_w = 0.0f;
-        if (ranked && lq > 0) { nx_pz = pz[sub]; nx_w = sim_of[sub]; }
+        Rec nx = {};
+        if (ranked && lq > 0) nx = rec[sub];
         for (int q = 0; q < lq; ++q) {
             const int v = q * K + sub;
-            const PZT cur = nx_pz; const float wv = nx_w;
-            if (ranked && q + 1 < lq) { nx_pz = pz[v + K]; nx_w = sim_of[v + K]; }
+            const Rec cur = nx;
+            if (ranked && q + 1 < lq) nx = rec[v + K];
             float d = 0.0f; int sl = -1, g = 0;
             if (ranked) {
-                relax_node<MaskT, true>((MaskT)cur.x, (MaskT)0, wv, q, wdist, wgen, slot_oa, d, sl, g);
-                dist[v] = d; gen[v] = (uint16_t)g; slot[v] = (int8_t)sl;
+                relax_node<MaskT, K, true>(cur.pred, (MaskT)0, cur.sim, q, step, wmask, wdist, wgen, d, sl, g);
+                if (cur.pred) { rec[v].dist = d; gen[v] = (uint16_t)g; }  // nodes without predecessors stay (0, self, gen 0)
+                slot[v] = (int8_t)sl;
             }
-            // slot q & 31 held layer q-32, which nobody reads any more (step-1 <= 30)
-            wdist[(q & (kWin - 1)) * 8 + sub] = d;
-            wgen[(q & (kWin - 1)) * 8 + sub] = (uint16_t)g;
-            const uint32_t lm = oct_max(__float_as_uint(d), om);  // dist >= +0: bits are ordered
+            // window slot q & wmask held layer q-depth, which nobody reads any more
+            wdist[(q & wmask) * 8 + sub] = d;
+            wgen[(q & wmask) * 8 + sub] = (uint16_t)g;
+            const uint32_t lm = __reduce_max_sync(om, __float_as_uint(d));  // dist >= +0: bits are ordered
             if (sub == 0) lbest[q] = lm;
             __syncwarp(om);
         }
@@ -426,22 +428,22 @@ __global__ void __launch_bounds__(kT2Threads) tn_dp_kernel(const Batch b, const 
         // ---- end node: maximum distance; ties -> smallest Kahn generation
         uint32_t mk = 0;
         for (int q = sub; q < lq; q += 8) mk = max(mk, lbest[q]);
-        mk = oct_max(mk, om);
+        mk = __reduce_max_sync(om, mk);
         if (mk == 0u) break;  // only zero-length paths left: networkx returns [source]
         int bg = INT_MAX, bv = -1, cnt = 0;
         for (int q = sub; q < lq; q += 8) {
             if (lbest[q] != mk) continue;
             for (int r = 0; r < K; ++r) {
                 const int v = q * K + r;
-                if (__float_as_uint(dist[v]) != mk) continue;
+                if (__float_as_uint(rec[v].dist) != mk) continue;
                 const int g = gen[v];
                 if (g < bg) { bg = g; bv = v; cnt = 1; }
                 else if (g == bg) ++cnt;
             }
         }
-        const int g_min = oct_min(bg, om);
+        const int g_min = __reduce_min_sync(om, bg);
         const bool mine_best = bg == g_min;
-        if (oct_add(mine_best ? cnt : 0, om) > 1) { ambiguous = true; break; }
+        if (__reduce_add_sync(om, mine_best ? cnt : 0) > 1) { ambiguous = true; break; }
         const unsigned who = __ballot_sync(om, mine_best) & om;
         const int end = __shfl_sync(om, bv, __ffs(who) - 1);
 
@@ -453,13 +455,12 @@ __global__ void __launch_bounds__(kT2Threads) tn_dp_kernel(const Batch b, const 
                 chain[len++] = (uint16_t)v;
                 const int sl = slot[v];
                 if (sl < 0) break;
-                MaskT *zp = reinterpret_cast<MaskT *>(&pz[v]) + 1;
-                *zp |= (MaskT)1 << sl;  // spent edge
-                const int oa = slot_oa[sl];
-                v = (v / K - (oa >> 3)) * K + (oa & 7);
+                rec[v].zero |= (MaskT)1 << sl;  // spent edge
+                const int grp = sl / K;
+                v = (v / K - (step - 1 - grp)) * K + (sl - grp * K);
             }
             float score = 0.0f;
-            for (int i = len - 1; i >= 0; --i) score += sim_of[chain[i]];
+            for (int i = len - 1; i >= 0; --i) score += rec[chain[i]].sim;
             const int first = chain[len - 1], last = chain[0];
             q_first_dst = (len >= 2 ? (int)chain[len - 2] : last) / K;
             q_last = last / K;
@@ -499,27 +500,27 @@ __global__ void __launch_bounds__(kT2Threads) tn_dp_kernel(const Batch b, const 
         // the wave dies `step-1` layers after the last distance that changed
         for (int o = 1; o < step; ++o) {  // refill the window behind the start layer
             const int qq = q_first_dst - o;
-            if (qq >= 0) wdist[(qq & (kWin - 1)) * 8 + sub] = ranked ? dist[qq * K + sub] : 0.0f;
+            if (qq >= 0) wdist[(qq & wmask) * 8 + sub] = ranked ? rec[qq * K + sub].dist : 0.0f;
         }
         __syncwarp(om);
         int last_changed = INT_MIN / 2;
-        PZT nx_pz = {}; float nx_w = 0.0f, nx_old = 0.0f;
-        if (ranked) { const int v0 = q_first_dst * K + sub; nx_pz = pz[v0]; nx_w = sim_of[v0]; nx_old = dist[v0]; }
+        Rec nx = {};
+        if (ranked) nx = rec[q_first_dst * K + sub];
         for (int q = q_first_dst; q < lq && (q <= q_last || q <= last_changed + step - 1); ++q) {
             const int v = q * K + sub;
-            const PZT cur = nx_pz; const float wv = nx_w, before = nx_old;
-            if (ranked && q + 1 < lq) { nx_pz = pz[v + K]; nx_w = sim_of[v + K]; nx_old = dist[v + K]; }
+            const Rec cur = nx;
+            if (ranked && q + 1 < lq) nx = rec[v + K];
             float d = 0.0f; int sl = -1, g = 0;
             bool changed = false;
             if (ranked) {
-                relax_node<MaskT, false>((MaskT)cur.x, (MaskT)cur.y, wv, q, wdist, wgen, slot_oa, d, sl, g);
-                changed = __float_as_uint(d) != __float_as_uint(before);
-                if (changed) dist[v] = d;
+                relax_node<MaskT, K, false>(cur.pred, cur.zero, cur.sim, q, step, wmask, wdist, wgen, d, sl, g);
+                changed = __float_as_uint(d) != __float_as_uint(cur.dist);
+                if (changed) rec[v].dist = d;
                 slot[v] = (int8_t)sl;
             }
-            wdist[(q & (kWin - 1)) * 8 + sub] = d;
+            wdist[(q & wmask) * 8 + sub] = d;
             if (__ballot_sync(om, changed) & om) last_changed = q;
-            const uint32_t lm = oct_max(__float_as_uint(d), om);
+            const uint32_t lm = __reduce_max_sync(om, __float_as_uint(d));
             if (sub == 0) lbest[q] = lm;
             __syncwarp(om);
         }
@@ -532,6 +533,31 @@ __global__ void __launch_bounds__(kT2Threads) tn_dp_kernel(const Batch b, const 
             b.n_boxes[pair] = n_boxes;
             if (b.status) b.status[pair] = 0;
         }
+    }
+}
+
+template <typename MaskT, int K>
+cudaError_t launch_dp_k(const Batch &b, const Workspace &w, const WorkList &out, int grid, size_t smem,
+                        cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(tn_dp_kernel<MaskT, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(tn_dp_kernel<MaskT, K>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (e != cudaSuccess) return e;
+    tn_dp_kernel<MaskT, K><<<grid, kT2Threads, smem, stream>>>(b, w, out);
+    return cudaGetLastError();
+}
+template <typename MaskT>
+cudaError_t launch_dp(const Batch &b, const Workspace &w, const WorkList &out, int grid, size_t smem,
+                      cudaStream_t stream) {
+    switch (b.topk) {
+        case 1: return launch_dp_k<MaskT, 1>(b, w, out, grid, smem, stream);
+        case 2: return launch_dp_k<MaskT, 2>(b, w, out, grid, smem, stream);
+        case 3: return launch_dp_k<MaskT, 3>(b, w, out, grid, smem, stream);
+        case 4: return launch_dp_k<MaskT, 4>(b, w, out, grid, smem, stream);
+        case 5: return launch_dp_k<MaskT, 5>(b, w, out, grid, smem, stream);
+        case 6: return launch_dp_k<MaskT, 6>(b, w, out, grid, smem, stream);
+        case 7: return launch_dp_k<MaskT, 7>(b, w, out, grid, smem, stream);
+        default: return launch_dp_k<MaskT, 8>(b, w, out, grid, smem, stream);
     }
 }
 
@@ -582,34 +608,32 @@ bool pipeline_supported(const Batch &b) {
     if (b.max_lr > vsc::kBlockCols * vsc::kMaxRowBlocks || b.max_lr < b.topk) return false;
     if (b.topk < 1 || b.topk > kMaxTop) return false;
     if ((reinterpret_cast<uintptr_t>(b.sims) & 15u) != 0) return false;
-    if (b.max_nodes > 65535 || b.step - 1 > kWin) return false;
-    if (t2_pair_bytes(b.max_nodes, b.max_lq) * kT2Warps * 4 > 200 * 1024) return false;
+    if (b.max_nodes > 65535) return false;
+    if (t2_pair_bytes(b.max_nodes, b.max_lq, b.step) * kT2Warps * 4 > 200 * 1024) return false;
     return t1_smem_bytes() <= 227 * 1024;
 }
 
 int launch_pipeline(const Batch &b, const WorkList &out, cudaStream_t stream) {
     const bool wide = (b.step - 1) * b.topk > 32;
-    const size_t mask_bytes = wide ? 8 : 4;
-    const size_t P = (size_t)b.n_pairs, N = (size_t)b.max_nodes, L = (size_t)b.max_lq;
+        const size_t P = (size_t)b.n_pairs, N = (size_t)b.max_nodes, L = (size_t)b.max_lq;
     // one stream-ordered allocation, carved by alignment
     size_t sz = 0;
     auto take = [&](size_t bytes) { size_t at = sz; sz += (bytes + 255) / 256 * 256; return at; };
-    const size_t o_pz = take(P * N * mask_bytes * 2);
-    const size_t o_sim = take(P * N * 4), o_dist = take(P * N * 4);
+    const size_t rec_bytes = wide ? sizeof(NodeRec<uint64_t>) : sizeof(NodeRec<uint32_t>);
+    const size_t o_rec = take(P * N * rec_bytes);
     const size_t o_ref = take(P * N * 2), o_gen = take(P * N * 2);
     const size_t o_skip = take(P), o_cursor = take(4);
     unsigned char *base = nullptr;
     VSC_CUDA_CHECK(cudaMallocAsync(&base, sz, stream));
     Workspace w;
-    w.pz = base + o_pz;
-    w.sim_of = reinterpret_cast<float *>(base + o_sim); w.dist = reinterpret_cast<float *>(base + o_dist);
+    w.rec = base + o_rec; w.rec_bytes = (int)rec_bytes; w.sim_off = wide ? 16 : 8;
     w.ref_of = reinterpret_cast<uint16_t *>(base + o_ref); w.gen = reinterpret_cast<uint16_t *>(base + o_gen);
     w.skip = base + o_skip; w.cursor = reinterpret_cast<int32_t *>(base + o_cursor);
     int rc = VSC_OK;
     auto fail = [&](cudaError_t e, const char *what) {
         if (e != cudaSuccess && rc == VSC_OK) { vsc::set_error("%s: %s", what, cudaGetErrorString(e)); rc = VSC_ERR_CUDA; }
     };
-    fail(cudaMemsetAsync(w.pz, 0, P * N * mask_bytes * 2, stream), "memset edge masks");
+    fail(cudaMemsetAsync(w.gen, 0, P * N * 2, stream), "memset generations");
     fail(cudaMemsetAsync(w.skip, 0, (o_cursor - o_skip) + 4, stream), "memset flags");
 
     int dev = 0, sms = 148;
@@ -642,14 +666,9 @@ int launch_pipeline(const Batch &b, const WorkList &out, cudaStream_t stream) {
     if (rc == VSC_OK) {
         const int pairs_per_cta = kT2Warps * 4;
         const int grid = (b.n_pairs + pairs_per_cta - 1) / pairs_per_cta;
-        const size_t smem = t2_pair_bytes(b.max_nodes, b.max_lq) * pairs_per_cta;
-        if (wide) {
-            fail(cudaFuncSetAttribute(tn_dp_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
-            tn_dp_kernel<uint64_t><<<grid, kT2Threads, smem, stream>>>(b, w, out);
-        } else {
-            fail(cudaFuncSetAttribute(tn_dp_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
-            tn_dp_kernel<uint32_t><<<grid, kT2Threads, smem, stream>>>(b, w, out);
-        }
+        const size_t smem = t2_pair_bytes(b.max_nodes, b.max_lq, b.step) * pairs_per_cta;
+        fail(wide ? launch_dp<uint64_t>(b, w, out, grid, smem, stream)
+                  : launch_dp<uint32_t>(b, w, out, grid, smem, stream), "tn_dp_kernel");
         fail(cudaGetLastError(), "tn_dp_kernel");
         vsc::count_launch();
     }
