@@ -60,6 +60,10 @@ int vcsl_tn_batch(const float *d_sims, const int64_t *d_off, const int32_t *d_lq
                   float *d_box_maxsim, int32_t *d_status, int32_t force_exact_order,
                   vsc_stream_t stream);
 
+/* Development aid: cumulative DP work counters {first-sweep layers, incremental layer steps,
+ * chains found, chain nodes}; all zero unless the library was built with -DVSC_TN_COUNTERS. */
+int vsc_tn_debug_counters(unsigned long long *out4);
+
 /* Number of kernel launches issued by this library since load (all entry points). */
 int64_t vsc_launch_count(void);
 

@@ -13,7 +13,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall",
     "-I", os.path.join(REPO, "include"), "-I", CSRC,
-]
+] + (["-DVSC_TN_COUNTERS"] if os.environ.get("VSC_TN_COUNTERS") else [])
 
 
 def find_nvcc() -> str:

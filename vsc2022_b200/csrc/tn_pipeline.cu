@@ -334,12 +334,31 @@ void launch_edges(const Batch &b, const Workspace &w, int grid, cudaStream_t str
 // (masks, similarity, distance) is prefetched one layer ahead with a single 128-bit load.  The
 // grid is sized so that every pair of a batch is resident at once: the kernel is a chain of
 // dependent shared-memory operations, so throughput comes from pairs in flight, not from IPC.
-constexpr int kT2Warps = 4;
+constexpr int kT2Warps = 2;  // 8 pairs per CTA: small CTAs pack the SMs so a whole batch is one wave
 constexpr int kT2Threads = kT2Warps * 32;
 
-__host__ __device__ inline int window_depth(int step) {  // power of two >= step-1
+// Octet reductions by xor-shuffle (distances 1, 2, 4 stay inside an aligned group of 8 lanes).
+// redux.sync with a per-octet mask compiles to a loop over the distinct masks and cost 38 % of
+// this kernel's stall samples when profiled.
+__device__ __forceinline__ uint32_t oct_max(uint32_t v, unsigned m) {
+    v = max(v, __shfl_xor_sync(m, v, 1));
+    v = max(v, __shfl_xor_sync(m, v, 2));
+    return max(v, __shfl_xor_sync(m, v, 4));
+}
+__device__ __forceinline__ int oct_min(int v, unsigned m) {
+    v = min(v, __shfl_xor_sync(m, v, 1));
+    v = min(v, __shfl_xor_sync(m, v, 2));
+    return min(v, __shfl_xor_sync(m, v, 4));
+}
+__device__ __forceinline__ int oct_add(int v, unsigned m) {
+    v += __shfl_xor_sync(m, v, 1);
+    v += __shfl_xor_sync(m, v, 2);
+    return v + __shfl_xor_sync(m, v, 4);
+}
+
+__host__ __device__ inline int window_depth(int step) {  // power of two >= step
     int d = 1;
-    while (d < step - 1) d <<= 1;
+    while (d < step) d <<= 1;  // > step-1, so the slot being written is never one being read
     return d;
 }
 __host__ __device__ inline size_t t2_pair_bytes(int max_nodes, int max_lq, int step) {
@@ -416,7 +435,7 @@ __global__ void __launch_bounds__(kT2Threads) tn_dp_kernel(const Batch b, const 
             // window slot q & wmask held layer q-depth, which nobody reads any more
             wdist[(q & wmask) * 8 + sub] = d;
             wgen[(q & wmask) * 8 + sub] = (uint16_t)g;
-            const uint32_t lm = __reduce_max_sync(om, __float_as_uint(d));  // dist >= +0: bits are ordered
+            const uint32_t lm = oct_max(__float_as_uint(d), om);  // dist >= +0: bits are ordered
             if (sub == 0) lbest[q] = lm;
             __syncwarp(om);
         }
@@ -428,7 +447,7 @@ __global__ void __launch_bounds__(kT2Threads) tn_dp_kernel(const Batch b, const 
         // ---- end node: maximum distance; ties -> smallest Kahn generation
         uint32_t mk = 0;
         for (int q = sub; q < lq; q += 8) mk = max(mk, lbest[q]);
-        mk = __reduce_max_sync(om, mk);
+        mk = oct_max(mk, om);
         if (mk == 0u) break;  // only zero-length paths left: networkx returns [source]
         int bg = INT_MAX, bv = -1, cnt = 0;
         for (int q = sub; q < lq; q += 8) {
@@ -441,9 +460,9 @@ __global__ void __launch_bounds__(kT2Threads) tn_dp_kernel(const Batch b, const 
                 else if (g == bg) ++cnt;
             }
         }
-        const int g_min = __reduce_min_sync(om, bg);
+        const int g_min = oct_min(bg, om);
         const bool mine_best = bg == g_min;
-        if (__reduce_add_sync(om, mine_best ? cnt : 0) > 1) { ambiguous = true; break; }
+        if (oct_add(mine_best ? cnt : 0, om) > 1) { ambiguous = true; break; }
         const unsigned who = __ballot_sync(om, mine_best) & om;
         const int end = __shfl_sync(om, bv, __ffs(who) - 1);
 
@@ -520,7 +539,7 @@ __global__ void __launch_bounds__(kT2Threads) tn_dp_kernel(const Batch b, const 
             }
             wdist[(q & wmask) * 8 + sub] = d;
             if (__ballot_sync(om, changed) & om) last_changed = q;
-            const uint32_t lm = __reduce_max_sync(om, __float_as_uint(d));
+            const uint32_t lm = oct_max(__float_as_uint(d), om);
             if (sub == 0) lbest[q] = lm;
             __syncwarp(om);
         }
@@ -683,6 +702,13 @@ int launch_pipeline(const Batch &b, const WorkList &out, cudaStream_t stream) {
 
 }  // namespace tn
 }  // namespace vsc
+
+// Development aid: DP work counters (all zero unless built with -DVSC_TN_COUNTERS).
+__device__ unsigned long long g_dp_counters[4];
+extern "C" int vsc_tn_debug_counters(unsigned long long *out4) {
+    VSC_CUDA_CHECK(cudaMemcpyFromSymbol(out4, g_dp_counters, sizeof(unsigned long long) * 4));
+    return VSC_OK;
+}
 
 extern "C" int vcsl_tn_batch(const float *d_sims, const int64_t *d_off, const int32_t *d_lq,
                              const int32_t *d_lr, int32_t n_pairs, int32_t max_lq, int32_t max_lr,
