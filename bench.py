@@ -1,0 +1,273 @@
+#!/usr/bin/env python3
+"""Headline benchmark: query-ref pairs localized / second (BASELINE.json metric).
+
+Workload (config.workload = "c4_tn_localization"): BASELINE.json configs[3] -- per GPU 8000
+candidate pairs, each a 300x300 float32 frame-similarity matrix (sims = Q.R^T + 0.5 from
+L2-normalised descriptors with 0-2 planted diagonal copies), temporal-network alignment with the
+vsc2022 parameters (tn_max_step=5, tn_top_k=5, max_path=10, min_sim=0.2, min_length=4, max_iou=0.3).
+One step = one pass of the hot path over the whole batch.
+
+  value   device time only: similarity matrices already resident in HBM (2.88 GB per GPU, larger
+          than the 126 MB L2, so no flush is needed between steps); CUDA events on the launch stream.
+  e2e     the same batch through the public host-buffer API (vcsl.vta-style TN.forward_packed):
+          pinned host matrices -> H2D -> kernels -> boxes D2H, all inside the timed region.
+  roofline  HBM: algorithmic bytes = 4*Lq*Lr per pair over the device time of the
+          whole TN pipeline call; per-kernel times are listed under roofline.stages_ms.
+  cpu_baseline  the oracle's port of the reference CPU path (VCSL TN on networkx, one process per
+          host core) on a bounded sample of the same workload -- a reported baseline, not a target.
+
+`--impl reference` runs only that CPU arm (bounded sample per step) and prints the same JSON shape.
+Multi-GPU (`torchrun ... bench.py --gpus N`): pairs are independent, every rank aligns its own 8000
+pairs (weak scaling), no data-path collective; time = max over ranks.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+PAIRS_PER_GPU = 8000
+LQ = LR = 300
+TN_CFG = dict(tn_max_step=5, tn_top_k=5, max_path=10, min_sim=0.2, min_length=4, max_iou=0.3)
+METRIC = "query-ref pairs localized/sec"
+UNIT = "pairs/s"
+
+
+def measured_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+            nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def summary(self):
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def _tn_job(args):
+    from oracle import tn_networkx
+    return tn_networkx.tn(args, **TN_CFG)
+
+
+def cpu_reference_run(n_pairs, seed):
+    """The reference CPU path (oracle port: VCSL TN on networkx) over all host cores."""
+    import multiprocessing as mp
+    import numpy as np
+    from oracle import synth
+    rng = np.random.default_rng(seed)
+    sims = [synth.sim_matrix(rng, LQ, LR, dim=64, max_copies=2, bias=0.5) for _ in range(n_pairs)]
+    cores = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(cores) as pool:
+        boxes = pool.map(_tn_job, sims, chunksize=max(1, n_pairs // (cores * 4)))
+    dt = time.perf_counter() - t0
+    return n_pairs / dt, cores, dt, sum(len(b) for b in boxes)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    sample = 64
+    rates = []
+    for step in range(args.warmup + args.steps):
+        rate, cores, dt, _ = cpu_reference_run(sample, seed=100 + step)
+        if step >= args.warmup:
+            rates.append(rate)
+    value = statistics.mean(rates)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sample / value,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "c4_tn_localization", "pairs_per_step": sample, "lq": LQ, "lr": LR, **TN_CFG},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} pairs of {LQ}x{LR} per step; VCSL TN restated on networkx "
+                                   f"(real VCSL/FAISS not installable here), multiprocessing.Pool({cores})"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_gpu(args, rank, local_rank, world):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from vsc2022_b200 import _lib, vta, workloads
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    n = PAIRS_PER_GPU
+    w = workloads.tn_pairs_device(n, LQ, LR, seed=4 + rank, device=dev)
+    model = vta.build_vta_model("TN", concurrency=16, **{k: v for k, v in TN_CFG.items()})
+    stream = torch.cuda.current_stream(dev)
+
+    def device_step():
+        return model.align_device(w.sims, w.off, w.lq, w.lr, n, LQ, LR, want_maxsim=False)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---------------- value: device-resident inputs
+    for _ in range(max(args.warmup, 3)):
+        res = device_step()
+    lib.vsc_tn_set_profiling(1)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    launches0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        res = device_step()
+    ev1.record(stream)
+    barrier()
+    sampler.stop_flag = True
+    launches = _lib.launch_count() - launches0
+    ms = ev0.elapsed_time(ev1) / args.steps
+    import ctypes
+    stage = (ctypes.c_float * 4)()
+    lib.vsc_tn_last_stage_ms(stage)
+    lib.vsc_tn_set_profiling(0)
+    _, n_boxes, _, status = res.to_host()
+
+    # ---------------- e2e: pinned host buffers through the host-facing API
+    host_sims = torch.empty(w.sims.numel() + 4, dtype=torch.float32, pin_memory=True)
+    host_sims[:w.sims.numel()].copy_(w.sims)
+    off_h, lq_h, lr_h = w.off.cpu().numpy(), w.lq.cpu().numpy(), w.lr.cpu().numpy()
+    for _ in range(2):
+        boxes_h = model.forward_packed(host_sims, off_h, lq_h, lr_h)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 5))
+    for _ in range(e2e_steps):
+        boxes_h = model.forward_packed(host_sims, off_h, lq_h, lr_h)
+    torch.cuda.synchronize(dev)
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    h2d = w.sims.numel() * 4 + off_h.nbytes + lq_h.nbytes + lr_h.nbytes
+    d2h = n * (TN_CFG["max_path"] + 1) * 4 * 4 + n * 4
+
+    # ---------------- max over ranks
+    times = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms_max, e2e_ms_max = times.tolist()
+
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        algo_bytes = n * 4 * LQ * LR
+        achieved = algo_bytes / (ms_max * 1e-3) / 1e9
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            rate, cores, dt, _ = cpu_reference_run(96, seed=4)
+            cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"96 pairs of {LQ}x{LR} ({dt:.1f} s): VCSL TN restated on networkx "
+                             f"(real VCSL not installable here), multiprocessing.Pool({cores})"}
+        line = {
+            "metric": METRIC, "value": world * n / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "c4_tn_localization", "pairs_per_gpu": n, "lq": LQ, "lr": LR, **TN_CFG,
+                       "l2": "inputs (2.88 GB/GPU) larger than L2; no flush needed",
+                       "parallelism": f"pairs sharded over {world} GPU(s), no data-path collective"},
+            "clocks": sampler.summary(),
+            "e2e": {"value": world * n / (e2e_ms_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_max,
+                    "api": "vsc2022_b200.vta.TN.forward_packed (pinned host similarity matrices in, boxes out)"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": achieved / peaks["hbm_gbs"], "peak_source": peak_src,
+                         "kernel": "TN pipeline of one vcsl_tn_batch call (tn_topk + tn_edges + tn_dp)",
+                         "algorithmic_bytes_per_launch": algo_bytes,
+                         "traffic": TRAFFIC_BYTES_PER_CALL,
+                         "stages_ms": {"tn_topk_kernel": stage[0], "tn_edges_kernel": stage[1],
+                                       "tn_dp_kernel": stage[2]},
+                         "tn_topk_frac": algo_bytes / (stage[0] * 1e-3) / 1e9 / peaks["hbm_gbs"] if stage[0] > 0 else None},
+            "cpu_baseline": cpu,
+            "result_check": {"boxes_per_pair": float(np.mean(n_boxes)),
+                             "pairs_on_fast_pipeline": int((status == 0).sum()),
+                             "pairs_on_general_kernel": int((status == 2).sum()),
+                             "pairs_on_exact_order_kernel": int((status == 1).sum())},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum over the three kernels of one call, from the ncu capture
+# committed under profiles/ (profiles/r01_tn_launches.csv); None until a capture exists.
+TRAFFIC_BYTES_PER_CALL = 3.80e9  # tn_topk 2.917+0.209, tn_edges 0.196+0.055, tn_dp 0.319+0.115 GB (profiles/r01_tn_summary.md)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if args.gpus != world:
+        if world == 1 and args.gpus > 1:
+            sys.exit(f"--gpus {args.gpus} needs torchrun --nproc-per-node {args.gpus}")
+    run_gpu(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

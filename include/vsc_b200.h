@@ -60,6 +60,12 @@ int vcsl_tn_batch(const float *d_sims, const int64_t *d_off, const int32_t *d_lq
                   float *d_box_maxsim, int32_t *d_status, int32_t force_exact_order,
                   vsc_stream_t stream);
 
+/* Per-stage device timing of the TN fast pipeline (CUDA events recorded on the caller's stream
+ * around each stage).  vsc_tn_last_stage_ms fills {row top-K, edges, sweeps, MaxSim} in ms for the
+ * most recent vcsl_tn_batch call; synchronise the stream first. */
+int vsc_tn_set_profiling(int on);
+int vsc_tn_last_stage_ms(float *out4);
+
 /* Development aid: cumulative DP work counters {first-sweep layers, incremental layer steps,
  * chains found, chain nodes}; all zero unless the library was built with -DVSC_TN_COUNTERS. */
 int vsc_tn_debug_counters(unsigned long long *out4);

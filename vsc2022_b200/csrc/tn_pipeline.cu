@@ -623,6 +623,17 @@ size_t t1_smem_bytes() { return sizeof(T1Smem) * kT1Warps; }
 namespace vsc {
 namespace tn {
 
+// Optional per-stage device timing of the last pipeline call (vsc_tn_set_profiling).
+static bool g_profile = false;
+static cudaEvent_t g_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+static bool g_ev_valid = false;
+static void mark(int i, cudaStream_t stream) {
+    if (!g_profile) return;
+    if (!g_ev[i]) cudaEventCreate(&g_ev[i]);
+    cudaEventRecord(g_ev[i], stream);
+    if (i == 4) g_ev_valid = true;
+}
+
 bool pipeline_supported(const Batch &b) {
     if (b.max_lr > vsc::kBlockCols * vsc::kMaxRowBlocks || b.max_lr < b.topk) return false;
     if (b.topk < 1 || b.topk > kMaxTop) return false;
@@ -658,6 +669,7 @@ int launch_pipeline(const Batch &b, const WorkList &out, cudaStream_t stream) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    mark(0, stream);
     if (rc == VSC_OK) {
         T1Args a; a.b = b; a.w = w; a.out = out;
         const size_t smem = t1_smem_bytes();
@@ -674,6 +686,7 @@ int launch_pipeline(const Batch &b, const WorkList &out, cudaStream_t stream) {
         }
         vsc::count_launch();
     }
+    mark(1, stream);
     if (rc == VSC_OK) {
         const long long threads = (long long)b.n_pairs * b.max_lq;
         const int grid = (int)((threads + 255) / 256);
@@ -682,6 +695,7 @@ int launch_pipeline(const Batch &b, const WorkList &out, cudaStream_t stream) {
         fail(cudaGetLastError(), "tn_edges_kernel");
         vsc::count_launch();
     }
+    mark(2, stream);
     if (rc == VSC_OK) {
         const int pairs_per_cta = kT2Warps * 4;
         const int grid = (b.n_pairs + pairs_per_cta - 1) / pairs_per_cta;
@@ -691,17 +705,33 @@ int launch_pipeline(const Batch &b, const WorkList &out, cudaStream_t stream) {
         fail(cudaGetLastError(), "tn_dp_kernel");
         vsc::count_launch();
     }
+    mark(3, stream);
     if (rc == VSC_OK && b.box_maxsim) {
         tn_maxsim_kernel<<<(b.n_pairs + 3) / 4, 128, 0, stream>>>(b, w);
         fail(cudaGetLastError(), "tn_maxsim_kernel");
         vsc::count_launch();
     }
+    mark(4, stream);
     cudaFreeAsync(base, stream);
     return rc;
 }
 
 }  // namespace tn
 }  // namespace vsc
+
+extern "C" int vsc_tn_set_profiling(int on) {
+    vsc::tn::g_profile = on != 0;
+    vsc::tn::g_ev_valid = false;
+    return VSC_OK;
+}
+// Device time (ms) of the stages of the most recent fast-pipeline call: row top-K, edges,
+// longest-path sweeps, MaxSim.  The caller must have synchronised the stream.
+extern "C" int vsc_tn_last_stage_ms(float *out4) {
+    using namespace vsc::tn;
+    if (!g_profile || !g_ev_valid) { vsc::set_error("vsc_tn_last_stage_ms: no profiled call"); return VSC_ERR_INVALID; }
+    for (int i = 0; i < 4; ++i) VSC_CUDA_CHECK(cudaEventElapsedTime(&out4[i], g_ev[i], g_ev[i + 1]));
+    return VSC_OK;
+}
 
 // Development aid: DP work counters (all zero unless built with -DVSC_TN_COUNTERS).
 __device__ unsigned long long g_dp_counters[4];

@@ -108,6 +108,22 @@ class TN:
         return tn_batch_device(d_sims, d_off, d_lq, d_lr, n_pairs, max_lq, max_lr, self.params,
                                want_maxsim, self.force_exact_order)
 
+    def forward_packed(self, host_sims, off: np.ndarray, lq: np.ndarray, lr: np.ndarray, want_maxsim=False):
+        """Host-buffer entry point: `host_sims` is ONE (ideally pinned) float32 torch tensor holding every
+        matrix, matrix i at element offset off[i] (multiple of 4 for the fast path) with shape lq[i] x lr[i].
+        Copies in, aligns, copies the boxes out.  Returns (boxes[n, max_path+1, 4], n_boxes[n], maxsim|None)."""
+        torch = _lib.require_cuda()
+        dev = self._device()
+        n = len(off)
+        d_sims = host_sims.to(dev, non_blocking=True)
+        d_off = torch.from_numpy(np.ascontiguousarray(off, dtype=np.int64)).to(dev, non_blocking=True)
+        meta = torch.from_numpy(np.concatenate([lq, lr]).astype(np.int32)).to(dev, non_blocking=True)
+        res = self.align_device(d_sims, d_off, meta[:n], meta[n:], n, int(lq.max()) if n else 0,
+                                int(lr.max()) if n else 0, want_maxsim=want_maxsim)
+        self.last_result = res
+        boxes, n_boxes, maxsim, _ = res.to_host()
+        return boxes, n_boxes, maxsim
+
     def forward_sim(self, data: Sequence[Tuple[str, np.ndarray]]) -> List[Tuple[str, List[List[int]]]]:
         torch = _lib.require_cuda()
         data = list(data)
