@@ -70,6 +70,43 @@ int vsc_tn_last_stage_ms(float *out4);
  * chains found, chain nodes}; all zero unless the library was built with -DVSC_TN_COUNTERS. */
 int vsc_tn_debug_counters(unsigned long long *out4);
 
+/* -------------------------------------------------------------------------
+ * Stage B: descriptor similarity on tensor cores (tcgen05 / TMEM / TMA).
+ * Replaces the FAISS IndexFlat arithmetic behind vsc/index.py:142-177 and
+ * vsc/baseline/score_normalization.py:87-96.
+ *
+ * Operands are K-major bf16 panels [rows][k] (k a multiple of 64, 16-byte aligned) produced by
+ * vsc_prepare_operand from fp32 descriptors x[n][d] (row stride ld):
+ *   mode 0  bf16(x), zero padded to kpad                      -> [n][kpad]
+ *   mode 1  query side of the 3-term split  [hi | hi | lo]     -> [n][3*kpad]
+ *   mode 2  reference side of the split     [hi | lo | hi]     -> [n][3*kpad]
+ * so that one GEMM with k = 3*kpad yields hi.hi + hi.lo + lo.hi (fp32-class products).
+ * *d_lo_flag (may be NULL) is OR-ed with 1 when some lo != 0, i.e. x is not bf16-representable.
+ * ------------------------------------------------------------------------- */
+int vsc_prepare_operand(const float *d_x, int64_t n, int32_t d, int64_t ld, int32_t kpad, int32_t mode,
+                        void *d_out_bf16, int32_t *d_lo_flag, vsc_stream_t stream);
+int vsc_row_sqnorm(const float *d_x, int64_t n, int32_t d, int64_t ld, float *d_out, vsc_stream_t stream);
+
+/* C[m][n] = A . B^T in fp32 (tests, per-pair similarity matrices). */
+int vsc_gemm_store(const void *d_a, int64_t m, const void *d_b, int64_t n, int32_t k, float *d_c, int64_t ldc,
+                   vsc_stream_t stream);
+/* d_rowmax[i] = max_j A_i . B_j  -- FAISS index.search(x, 1) similarities
+ * (score_normalization.py:93-96) without materialising the matrix. */
+int vsc_gemm_rowmax(const void *d_a, int64_t m, const void *d_b, int64_t n, int32_t k, float *d_rowmax,
+                    vsc_stream_t stream);
+/* FAISS index.search(x, 1) proper (index.py:169-174 with k = 1): best score and its column per row, lowest
+ * column on exact ties.  d_scratch: m x 8 bytes of workspace. */
+int vsc_gemm_rowargmax(const void *d_a, int64_t m, const void *d_b, int64_t n, int32_t k, float *d_score,
+                       int64_t *d_col, unsigned long long *d_scratch, vsc_stream_t stream);
+/* FAISS range_search (index.py:147-154): counts the scores strictly beyond count_thr into
+ * d_counters[1] and appends (score, row + row_offset, col + col_offset) of those strictly beyond
+ * emit_thr at d_counters[0]++ (entries past `capacity` are dropped but still counted).
+ * metric_l2 = 0: inner product, "beyond" = greater;  1: squared L2 = a_norm + b_norm - 2 a.b, "beyond" = smaller. */
+int vsc_gemm_emit(const void *d_a, int64_t m, const void *d_b, int64_t n, int32_t k, const float *d_a_norm,
+                  const float *d_b_norm, int32_t metric_l2, float count_thr, float emit_thr, int64_t row_offset,
+                  int64_t col_offset, float *d_score, int32_t *d_row, int32_t *d_col, uint64_t capacity,
+                  unsigned long long *d_counters, vsc_stream_t stream);
+
 /* Number of kernel launches issued by this library since load (all entry points). */
 int64_t vsc_launch_count(void);
 

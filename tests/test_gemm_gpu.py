@@ -1,0 +1,104 @@
+"""GPU parity of the tcgen05 descriptor GEMM and its fused epilogues.
+
+Inputs live on a coarse grid (multiples of 1/16 in [-4, 4]) so that every product and every partial sum
+is exact in float32: the result is then independent of summation order and must equal the float32
+reference BIT FOR BIT.  Arbitrary float32 inputs go through the 3-term bf16 split and are compared with a
+float64 reference within 2e-6 * sum|a_k b_k| (tolerance stated here).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def grid(rng, shape):
+    return (rng.integers(-64, 65, size=shape) / 16.0).astype(np.float32)
+
+
+def to_dev(x):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+@pytest.mark.parametrize("m,n,d", [(128, 256, 64), (300, 700, 512), (1, 5, 64), (129, 257, 130), (1000, 2049, 512),
+                                   (64, 64, 512), (2, 3, 3)])
+def test_store_exact_on_grid(m, n, d):
+    from vsc2022_b200 import gemm
+    rng = np.random.default_rng(m * 7 + n)
+    a, b = grid(rng, (m, d)), grid(rng, (n, d))
+    oa, ob = gemm.prepare_pair(to_dev(a), to_dev(b))
+    assert not oa.split, "grid values are bf16-representable: single pass expected"
+    c = gemm.gemm_store(oa, ob).cpu().numpy()
+    assert np.array_equal(c, a @ b.T)
+
+
+def test_split_precision_on_arbitrary_fp32():
+    from vsc2022_b200 import gemm
+    rng = np.random.default_rng(3)
+    a = rng.normal(size=(257, 511)).astype(np.float32)
+    b = rng.normal(size=(513, 511)).astype(np.float32)
+    a /= np.linalg.norm(a, axis=1, keepdims=True)
+    b /= np.linalg.norm(b, axis=1, keepdims=True)
+    oa, ob = gemm.prepare_pair(to_dev(a), to_dev(b))
+    assert oa.split and oa.k == 3 * 512
+    c = gemm.gemm_store(oa, ob).cpu().numpy().astype(np.float64)
+    ref = a.astype(np.float64) @ b.astype(np.float64).T
+    bound = 2e-6 * (np.abs(a).astype(np.float64) @ np.abs(b).astype(np.float64).T) + 1e-7
+    assert (np.abs(c - ref) <= bound).all(), float(np.abs(c - ref).max())
+    # unit-norm rows: absolute error of the 3-term split stays below 2e-6 (float32 sgemm: ~1e-7)
+    assert np.abs(c - ref).max() <= 2e-6, float(np.abs(c - ref).max())
+
+
+def test_rowmax_exact_on_grid():
+    from vsc2022_b200 import gemm
+    rng = np.random.default_rng(5)
+    a, b = grid(rng, (777, 512)), grid(rng, (3001, 512))
+    oa, ob = gemm.prepare_pair(to_dev(a), to_dev(b))
+    got = gemm.gemm_rowmax(oa, ob).cpu().numpy()
+    assert np.array_equal(got, (a @ b.T).max(axis=1))
+
+
+@pytest.mark.parametrize("metric_l2", [False, True])
+def test_emit_counts_and_entries(metric_l2):
+    import torch
+    from vsc2022_b200 import gemm
+    rng = np.random.default_rng(9)
+    a, b = grid(rng, (500, 128)), grid(rng, (1300, 128))
+    da, db = to_dev(a), to_dev(b)
+    oa, ob = gemm.prepare_pair(da, db)
+    ip = a @ b.T
+    if metric_l2:
+        an, bn = (a * a).sum(1, dtype=np.float32), (b * b).sum(1, dtype=np.float32)
+        s = (an[:, None] + bn[None, :] - np.float32(2.0) * ip).astype(np.float32)
+        count_thr, emit_thr = np.float32(np.quantile(s, 0.02)), np.float32(np.quantile(s, 0.01))
+        want = s < emit_thr
+        n_count = int((s < count_thr).sum())
+    else:
+        s = ip
+        count_thr, emit_thr = np.float32(np.quantile(s, 0.98)), np.float32(np.quantile(s, 0.99))
+        want = s > emit_thr
+        n_count = int((s > count_thr).sum())
+    hits = gemm.HitBuffer(int(want.sum()) + 100, da.device)
+    gemm.gemm_emit(oa, ob, hits, float(count_thr), float(emit_thr), metric_l2=metric_l2,
+                   a_norm=gemm.row_sqnorm(da) if metric_l2 else None,
+                   b_norm=gemm.row_sqnorm(db) if metric_l2 else None, row_offset=10, col_offset=20)
+    stored, counted = hits.read_counters()
+    assert stored == int(want.sum()) and counted == n_count
+    rows = hits.row[:stored].cpu().numpy() - 10
+    cols = hits.col[:stored].cpu().numpy() - 20
+    sc = hits.score[:stored].cpu().numpy()
+    got = np.zeros_like(want)
+    got[rows, cols] = True
+    assert np.array_equal(got, want)
+    assert np.array_equal(sc, s[rows, cols])
+
+
+def test_emit_capacity_overflow_is_counted_not_written():
+    from vsc2022_b200 import gemm
+    rng = np.random.default_rng(11)
+    a, b = grid(rng, (256, 64)), grid(rng, (512, 64))
+    oa, ob = gemm.prepare_pair(to_dev(a), to_dev(b))
+    hits = gemm.HitBuffer(1000, oa.panel.device)
+    gemm.gemm_emit(oa, ob, hits, -1e10, -1e10)
+    stored, counted = hits.read_counters()
+    assert stored == 256 * 512 and counted == 256 * 512

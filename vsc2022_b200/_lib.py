@@ -31,6 +31,23 @@ EXPORTS = {
     "vsc_tn_debug_counters": (ctypes.c_int, [ctypes.c_void_p]),
     "vsc_tn_set_profiling": (ctypes.c_int, [ctypes.c_int]),
     "vsc_tn_last_stage_ms": (ctypes.c_int, [ctypes.c_void_p]),
+    "vsc_prepare_operand": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int64,
+                                           ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
+                                           ctypes.c_void_p]),
+    "vsc_row_sqnorm": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int64,
+                                      ctypes.c_void_p, ctypes.c_void_p]),
+    "vsc_gemm_store": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
+                                      ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
+    "vsc_gemm_rowmax": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
+                                       ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]),
+    "vsc_gemm_rowargmax": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
+                                          ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                          ctypes.c_void_p]),
+    "vsc_gemm_emit": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
+                                     ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
+                                     ctypes.c_float, ctypes.c_float, ctypes.c_int64, ctypes.c_int64,
+                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64,
+                                     ctypes.c_void_p, ctypes.c_void_p]),
     "vcsl_tn_batch": (ctypes.c_int, [
         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
         ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(TnParams),

@@ -1,0 +1,463 @@
+// Descriptor similarity GEMM on 5th-generation tensor cores (tcgen05 + TMEM + TMA), sm_100a.
+//
+//   S[i][j] = sum_k A[i][k] * B[j][k]      A: queries [M][K] bf16, B: references [N][K] bf16,
+//                                           both K-major (row-major, K contiguous), fp32 accumulate.
+//
+// Replaces the FAISS flat-index arithmetic behind vsc/index.py:142-177 (range / kNN search) and
+// vsc/baseline/score_normalization.py:93-96 (1-NN against the noise set).  The similarity matrix is
+// never written to memory: each 128x256 accumulator tile is consumed straight out of tensor memory
+// by one of three fused epilogues
+//   STORE   write the fp32 tile (tests, small per-pair matrices)
+//   ROWMAX  per-row maximum over all references (score normalisation's 1-NN similarity)
+//   EMIT    count scores beyond `count_thr`, append (score, i, j) of those beyond `emit_thr`
+//           (strict comparisons, inner product or squared-L2 metric)
+//
+// Kernel anatomy (persistent, one CTA per SM, 192 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2D tiles (SWIZZLE_128B) into a 4-stage ring
+//   warp 1      allocates TMEM; one lane issues tcgen05.mma (M128 x N256 x K16, cta_group::1)
+//   warps 2-5   epilogue: tcgen05.ld 32 columns at a time from one of two accumulator buffers
+//               (512 TMEM columns), so the epilogue of tile t overlaps the MMAs of tile t+1
+// Tile order: m fastest, so concurrently running CTAs share the same reference tile in L2 while the
+// whole query matrix stays L2-resident; references stream from HBM once.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace {
+
+using vsc::kFullMask;
+
+constexpr int BM = 128, BN = 256, BK = 64;
+constexpr int STAGES = 4;
+constexpr int UMMA_K = 16;
+constexpr int kThreads = 192;
+constexpr uint32_t kStageBytesA = BM * BK * 2, kStageBytesB = BN * BK * 2;
+constexpr uint32_t kTmemCols = 512;  // two 256-column fp32 accumulators
+
+enum Epilogue { EPI_STORE = 0, EPI_ROWMAX = 1, EPI_EMIT = 2, EPI_ROWARGMAX = 3 };
+
+struct GemmArgs {
+    int64_t M, N;
+    int K;  // multiple of BK
+    // STORE
+    float *c; int64_t ldc;
+    // ROWMAX: order-preserving keys (vsc::float_to_key), combined with atomicMax
+    uint32_t *rowmax_key;
+    // ROWARGMAX: (key << 32) | (0xFFFFFFFF - column): atomicMax keeps the best score, lowest column on ties
+    unsigned long long *rowbest;
+    // EMIT
+    const float *a_norm, *b_norm;  // squared norms (L2 metric) or null
+    int metric_l2;
+    float count_thr, emit_thr;
+    int64_t row_offset, col_offset;  // added to the emitted indices
+    float *out_score; int32_t *out_row, *out_col;
+    unsigned long long capacity;
+    unsigned long long *counters;  // [0] entries claimed (may exceed capacity), [1] hits beyond count_thr
+};
+
+struct SharedStorage {
+    alignas(1024) uint8_t a[STAGES][kStageBytesA];
+    alignas(1024) uint8_t b[STAGES][kStageBytesB];
+    alignas(8) uint64_t full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2];
+    uint32_t tmem_base;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int x, int y, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint64_t *bar) {  // arrives on `bar` when all prior MMAs retire
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                 uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 32 lanes x 32 columns of fp32: thread t of the warp receives row (lane base + t), columns c..c+31
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory matrix descriptor, K-major operand, SWIZZLE_128B: rows of 128 B (64 bf16), groups of
+// 8 rows form one 1024-byte swizzle atom (stride byte offset 1024); leading byte offset unused.
+__device__ __forceinline__ uint64_t umma_desc_k_major_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);          // [0,14)  start address >> 4
+    d |= (uint64_t)1 << 16;                                // [16,30) leading byte offset >> 4 (ignored)
+    d |= (uint64_t)(1024 >> 4) << 32;                      // [32,46) stride byte offset >> 4
+    d |= (uint64_t)1 << 46;                                // [46,48) descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                                // [61,64) layout: SWIZZLE_128B
+    return d;
+}
+// Instruction descriptor, kind::f16: D fp32, A/B bf16, both K-major, shape M x N.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
+    return (1u << 4)                     // D format: fp32
+           | (1u << 7) | (1u << 10)      // A, B format: bf16
+           | ((uint32_t)(n >> 3) << 17)  // N / 8
+           | ((uint32_t)(m >> 4) << 24); // M / 16
+}
+
+// ---------------------------------------------------------------- epilogues (one thread = one accumulator row)
+// `valid` = number of in-range columns of this 32-column chunk (1..32): bounds are applied to the
+// bit masks, not per element.
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(const GemmArgs &g, float &best, int64_t &best_col, int64_t row,
+                                               int64_t col0, int valid, const uint32_t (&acc)[32], int lane) {
+    const bool row_ok = row < g.M;
+    const uint32_t valid_mask = valid >= 32 ? 0xFFFFFFFFu : ((1u << valid) - 1u);
+    if (EPI == EPI_STORE) {
+        if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (j < valid) g.c[row * g.ldc + col0 + j] = __uint_as_float(acc[j]);
+        }
+    } else if (EPI == EPI_ROWARGMAX) {
+        int arg = -1;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const float v = __uint_as_float(acc[j]);
+            if (j < valid && v > best) { best = v; arg = j; }  // strict: the first (lowest) column wins ties
+        }
+        if (arg >= 0) best_col = col0 + arg;
+    } else if (EPI == EPI_ROWMAX) {
+        if (valid >= 32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) best = fmaxf(best, __uint_as_float(acc[j]));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (j < valid) best = fmaxf(best, __uint_as_float(acc[j]));
+        }
+    } else {
+        // EMIT: strict comparisons; IP keeps larger scores, squared-L2 keeps smaller distances
+        uint32_t hits = 0, counted = 0;
+        float s[32];
+        const float emit_thr = g.emit_thr, count_thr = g.count_thr;
+        const bool two = emit_thr != count_thr;  // uniform: the common case has one threshold
+        if (!g.metric_l2) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                s[j] = __uint_as_float(acc[j]);
+                hits |= (s[j] > emit_thr ? 1u : 0u) << j;
+            }
+            counted = hits;
+            if (two) {
+                counted = 0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) counted |= (s[j] > count_thr ? 1u : 0u) << j;
+            }
+        } else {
+            const float an = row_ok ? g.a_norm[row] : 0.0f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float bn = j < valid ? g.b_norm[col0 + j] : 0.0f;
+                s[j] = an + bn - 2.0f * __uint_as_float(acc[j]);
+                hits |= (s[j] < emit_thr ? 1u : 0u) << j;
+                counted |= (s[j] < count_thr ? 1u : 0u) << j;
+            }
+        }
+        const uint32_t keep = row_ok ? valid_mask : 0u;
+        hits &= keep; counted &= keep;
+        if (!__any_sync(kFullMask, (hits | counted) != 0)) return;  // the common case once the radius is tight
+        // warp-aggregated claim of output slots
+        const int n_hit = __popc(hits);
+        int incl = n_hit, total_cnt = __popc(counted);
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int up = __shfl_up_sync(kFullMask, incl, d);
+            if (lane >= d) incl += up;
+            total_cnt += __shfl_xor_sync(kFullMask, total_cnt, d);
+        }
+        const int total_hit = __shfl_sync(kFullMask, incl, 31);
+        unsigned long long base = 0;
+        if (lane == 0) {
+            if (total_hit) base = atomicAdd(&g.counters[0], (unsigned long long)total_hit);
+            if (total_cnt) atomicAdd(&g.counters[1], (unsigned long long)total_cnt);
+        }
+        base = __shfl_sync(kFullMask, base, 0);
+        unsigned long long at = base + (unsigned long long)(incl - n_hit);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            if ((hits >> j) & 1) {
+                if (at < g.capacity) {
+                    g.out_score[at] = s[j];
+                    g.out_row[at] = (int32_t)(row + g.row_offset);
+                    g.out_col[at] = (int32_t)(col0 + j + g.col_offset);
+                }
+                ++at;
+            }
+        }
+    }
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant__ CUtensorMap tma_a,
+                                                           const __grid_constant__ CUtensorMap tma_b,
+                                                           const GemmArgs g) {
+    extern __shared__ uint8_t smem_raw[];
+    SharedStorage &sm = *reinterpret_cast<SharedStorage *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t m_tiles = (g.M + BM - 1) / BM, n_tiles = (g.N + BN - 1) / BN;
+    const int64_t tiles = m_tiles * n_tiles;
+    const int k_blocks = g.K / BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&sm.tmem_full[s], 1); mbar_init(&sm.tmem_empty[s], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // one full warp allocates all 512 TMEM columns and publishes the base address
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = sm.tmem_base;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_a) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_b) : "memory");
+            int stage = 0; uint32_t phase = 0;
+            for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+                const int m_blk = (int)(t % m_tiles), n_blk = (int)(t / m_tiles);
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(&sm.empty[stage], phase ^ 1);
+                    mbar_expect_tx(&sm.full[stage], kStageBytesA + kStageBytesB);
+                    tma_load_2d(sm.a[stage], &tma_a, kb * BK, m_blk * BM, &sm.full[stage]);
+                    tma_load_2d(sm.b[stage], &tma_b, kb * BK, n_blk * BN, &sm.full[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (single thread) =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+            int stage = 0; uint32_t phase = 0;
+            uint32_t it = 0;
+            for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+                const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+                mbar_wait(&sm.tmem_empty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
+                tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(&sm.full[stage], phase);          // TMA bytes have landed
+                    tcgen05_fence_after();
+                    const uint64_t da = umma_desc_k_major_sw128(smem_u32(sm.a[stage]));
+                    const uint64_t db = umma_desc_k_major_sw128(smem_u32(sm.b[stage]));
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k)       // +32 bytes along K inside the swizzle row
+                        tcgen05_mma_bf16(tmem_d, da + (uint64_t)(k * UMMA_K * 2 >> 4), db + (uint64_t)(k * UMMA_K * 2 >> 4),
+                                         idesc, (kb | k) != 0);
+                    tcgen05_commit(&sm.empty[stage]);           // frees the smem slot once these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                tcgen05_commit(&sm.tmem_full[acc]);             // accumulator complete -> epilogue
+            }
+        }
+    } else {
+        // ===== epilogue warps: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32) =====
+        const int quad = warp & 3;
+        uint32_t it = 0;
+        for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+            const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+            const int64_t m_blk = t % m_tiles, n_blk = t / m_tiles;
+            const int64_t row = m_blk * BM + quad * 32 + lane;
+            float best = -INFINITY;
+            int64_t best_col = -1;
+            mbar_wait(&sm.tmem_full[acc], acc_phase);
+            tcgen05_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                const int64_t col0 = n_blk * BN + c * 32;
+                if (col0 >= g.N) break;
+                const int valid = (int)(g.N - col0 < 32 ? g.N - col0 : 32);
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + c * 32, v);
+                epilogue_chunk<EPI>(g, best, best_col, row, col0, valid, v, lane);
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.tmem_empty[acc]);
+            if (EPI == EPI_ROWMAX && row < g.M)
+                atomicMax(&g.rowmax_key[row], vsc::float_to_key(best));
+            if (EPI == EPI_ROWARGMAX && row < g.M && best_col >= 0)
+                atomicMax(&g.rowbest[row], ((unsigned long long)vsc::float_to_key(best) << 32) |
+                                               (unsigned long long)(0xFFFFFFFFu - (uint32_t)best_col));
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+    }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2D bf16 tensor [rows][k], K contiguous; box = box_rows x 64 elements, 128-byte swizzle.
+int make_map(CUtensorMap *map, const void *ptr, int64_t rows, int k, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { vsc::set_error("cuTensorMapEncodeTiled entry point not available"); return VSC_ERR_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)k * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { vsc::set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return VSC_ERR_CUDA; }
+    return VSC_OK;
+}
+
+template <int EPI>
+int launch(const void *a, const void *b, const GemmArgs &g, cudaStream_t stream) {
+    if (g.M <= 0 || g.N <= 0) return VSC_OK;
+    if (g.K <= 0 || g.K % BK != 0) { vsc::set_error("gemm: K=%d must be a positive multiple of %d", g.K, BK); return VSC_ERR_INVALID; }
+    if ((reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(b) & 15)) {
+        vsc::set_error("gemm: operands must be 16-byte aligned"); return VSC_ERR_INVALID;
+    }
+    CUtensorMap ma, mb;
+    int rc = make_map(&ma, a, g.M, g.K, BM);
+    if (rc != VSC_OK) return rc;
+    rc = make_map(&mb, b, g.N, g.K, BN);
+    if (rc != VSC_OK) return rc;
+    const size_t smem = sizeof(SharedStorage) + 1024;
+    VSC_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0, sms = 148;
+    VSC_CUDA_CHECK(cudaGetDevice(&dev));
+    VSC_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int64_t tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
+    const int grid = (int)(tiles < sms ? tiles : sms);
+    gemm_kernel<EPI><<<grid, kThreads, smem, stream>>>(ma, mb, g);
+    VSC_CUDA_CHECK(cudaGetLastError());
+    vsc::count_launch();
+    return VSC_OK;
+}
+
+__global__ void fill_u32(uint32_t *p, int64_t n, uint32_t v) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+__global__ void unpack_rowbest(const unsigned long long *packed, float *score, int64_t *col, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long p = packed[i];
+    score[i] = p ? vsc::key_to_float((uint32_t)(p >> 32)) : -INFINITY;
+    col[i] = p ? (int64_t)(0xFFFFFFFFu - (uint32_t)(p & 0xFFFFFFFFull)) : -1;
+}
+__global__ void keys_to_float(const uint32_t *k, float *out, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = vsc::key_to_float(k[i]);
+}
+
+}  // namespace
+
+extern "C" int vsc_gemm_store(const void *d_a, int64_t m, const void *d_b, int64_t n, int32_t k, float *d_c,
+                              int64_t ldc, vsc_stream_t stream) {
+    GemmArgs g = {};
+    g.M = m; g.N = n; g.K = k; g.c = d_c; g.ldc = ldc;
+    return launch<EPI_STORE>(d_a, d_b, g, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vsc_gemm_rowmax(const void *d_a, int64_t m, const void *d_b, int64_t n, int32_t k, float *d_rowmax,
+                               vsc_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (m <= 0) return VSC_OK;
+    GemmArgs g = {};
+    g.M = m; g.N = n; g.K = k;
+    // the fp32 output buffer doubles as the key buffer: keys first, converted in place afterwards
+    g.rowmax_key = reinterpret_cast<uint32_t *>(d_rowmax);
+    fill_u32<<<(unsigned)((m + 255) / 256), 256, 0, stream>>>(g.rowmax_key, m, 0x007FFFFFu);  // key of -inf
+    vsc::count_launch();
+    int rc = launch<EPI_ROWMAX>(d_a, d_b, g, stream);
+    if (rc != VSC_OK) return rc;
+    keys_to_float<<<(unsigned)((m + 255) / 256), 256, 0, stream>>>(g.rowmax_key, d_rowmax, m);
+    VSC_CUDA_CHECK(cudaGetLastError());
+    vsc::count_launch();
+    return VSC_OK;
+}
+
+extern "C" int vsc_gemm_rowargmax(const void *d_a, int64_t m, const void *d_b, int64_t n, int32_t k, float *d_score,
+                                  int64_t *d_col, unsigned long long *d_scratch, vsc_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (m <= 0) return VSC_OK;
+    GemmArgs g = {};
+    g.M = m; g.N = n; g.K = k; g.rowbest = d_scratch;
+    VSC_CUDA_CHECK(cudaMemsetAsync(d_scratch, 0, sizeof(unsigned long long) * (size_t)m, stream));
+    int rc = launch<EPI_ROWARGMAX>(d_a, d_b, g, stream);
+    if (rc != VSC_OK) return rc;
+    unpack_rowbest<<<(unsigned)((m + 255) / 256), 256, 0, stream>>>(d_scratch, d_score, d_col, m);
+    VSC_CUDA_CHECK(cudaGetLastError());
+    vsc::count_launch();
+    return VSC_OK;
+}
+
+extern "C" int vsc_gemm_emit(const void *d_a, int64_t m, const void *d_b, int64_t n, int32_t k, const float *d_a_norm,
+                             const float *d_b_norm, int32_t metric_l2, float count_thr, float emit_thr,
+                             int64_t row_offset, int64_t col_offset, float *d_score, int32_t *d_row, int32_t *d_col,
+                             uint64_t capacity, unsigned long long *d_counters, vsc_stream_t stream) {
+    if (metric_l2 && (!d_a_norm || !d_b_norm)) { vsc::set_error("vsc_gemm_emit: L2 metric needs squared norms"); return VSC_ERR_INVALID; }
+    GemmArgs g = {};
+    g.M = m; g.N = n; g.K = k;
+    g.a_norm = d_a_norm; g.b_norm = d_b_norm; g.metric_l2 = metric_l2;
+    g.count_thr = count_thr; g.emit_thr = emit_thr; g.row_offset = row_offset; g.col_offset = col_offset;
+    g.out_score = d_score; g.out_row = d_row; g.out_col = d_col; g.capacity = capacity; g.counters = d_counters;
+    return launch<EPI_EMIT>(d_a, d_b, g, static_cast<cudaStream_t>(stream));
+}

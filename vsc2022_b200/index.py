@@ -1,0 +1,342 @@
+"""`vsc.index` mirror: frame-level descriptor index with global-threshold search, on the GPU.
+
+Same public surface as the reference (vsc/index.py): VideoMetadata, VideoFeature, PairMatch, PairMatches,
+VideoIndex(dim, codec_str="Flat", metric=METRIC_INNER_PRODUCT).add(db).search(queries, global_k), plus the
+`.index` attribute other reference code reaches into (`.index.metric_type`, `.index.search(x, k)`,
+`.index.ntotal`).  The arithmetic FAISS did -- the all-pairs similarity and the range / kNN selection -- runs in
+csrc/gemm_tc.cu (tcgen05 GEMM with fused threshold-emit and row-max epilogues); the radius schedule of
+faiss.contrib.exhaustive_search.range_search_max_results is followed step by step so ties behave identically.
+"""
+import collections
+import logging
+from dataclasses import dataclass
+from typing import Iterable, List, NamedTuple, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib, gemm
+
+METRIC_INNER_PRODUCT = 0   # == faiss.METRIC_INNER_PRODUCT
+METRIC_L2 = 1              # == faiss.METRIC_L2
+
+SearchIndices = Tuple[int, int, float]
+
+
+@dataclass
+class VideoMetadata:
+    video_id: str
+    timestamps: np.ndarray  # N (one instant per frame) or Nx2 (start, end)
+
+    def __len__(self):
+        return self.timestamps.shape[0]
+
+    def get_timestamps(self, idx: int) -> Tuple[float, float]:
+        t = self.timestamps[idx]
+        return (t, t) if self.timestamps.ndim == 1 else (t[0], t[1])
+
+
+@dataclass
+class VideoFeature(VideoMetadata):
+    feature: np.ndarray
+
+    def __post_init__(self):
+        assert self.feature.shape[0] == len(self.timestamps), "Mismatched timestamps / feature size"
+
+    def metadata(self):
+        return VideoMetadata(video_id=self.video_id, timestamps=self.timestamps)
+
+    def dimensions(self):
+        return self.feature.shape[1]
+
+
+class PairMatch(NamedTuple):
+    query_timestamps: Tuple[float, float]
+    ref_timestamps: Tuple[float, float]
+    score: float
+
+
+@dataclass
+class PairMatches:
+    query_id: str
+    ref_id: str
+    matches: List[PairMatch]
+
+    def records(self):
+        for m in self.matches:
+            yield {"query_id": self.query_id, "ref_id": self.ref_id,
+                   "query_start": m.query_timestamps[0], "query_end": m.query_timestamps[1],
+                   "ref_start": m.ref_timestamps[0], "ref_end": m.ref_timestamps[1], "score": m.score}
+
+
+def exponential_batches(n: int, start: int = 32, limit: int = 20000):
+    """Row ranges of faiss.contrib.exhaustive_search.exponential_query_iterator (32, 64, ... doubling while < 20000)."""
+    size, at = start, 0
+    while at < n:
+        yield at, min(n, at + size)
+        at += size
+        if size < limit:
+            size *= 2
+
+
+class FlatIndex:
+    """The `.index` object: a brute-force (FAISS "Flat") index whose search runs on the GPU."""
+
+    def __init__(self, d: int, metric_type: int = METRIC_INNER_PRODUCT, device=None, precise: bool = True):
+        self.d, self.metric_type, self.precise = int(d), int(metric_type), precise
+        self._device = device
+        self._host_chunks: List[np.ndarray] = []
+        self._xb = None          # float32 CUDA tensor [ntotal, d]
+        self._ntotal = 0
+
+    @property
+    def ntotal(self) -> int:
+        return self._ntotal
+
+    def device(self):
+        torch = _lib.require_cuda()
+        return torch.device(self._device) if self._device is not None else torch.device("cuda", torch.cuda.current_device())
+
+    def add(self, x: np.ndarray):
+        x = np.array(x, dtype=np.float32, copy=True, order="C")  # the index owns a copy (FAISS semantics)
+        assert x.ndim == 2 and x.shape[1] == self.d
+        self._host_chunks.append(x)
+        self._ntotal += x.shape[0]
+        self._xb = None
+
+    def add_device(self, x):
+        """Append descriptors that already live on the device (float32 CUDA tensor [n, d])."""
+        torch = _lib.require_cuda()
+        base = self.database()
+        self._xb = x.clone() if base is None or base.shape[0] == 0 else torch.cat([base, x])
+        self._host_chunks = []
+        self._ntotal = self._xb.shape[0]
+
+    def database(self):
+        torch = _lib.require_cuda()
+        if self._xb is None and (self._host_chunks or self._ntotal == 0):
+            host = np.concatenate(self._host_chunks) if self._host_chunks else np.zeros((0, self.d), np.float32)
+            self._xb = torch.from_numpy(host).to(self.device())
+        elif self._host_chunks:
+            self._xb = torch.cat([self._xb, torch.from_numpy(np.concatenate(self._host_chunks)).to(self.device())])
+        self._host_chunks = []
+        return self._xb
+
+    # ---- FAISS-style entry points ------------------------------------------------------------------------
+    def _to_device(self, x):
+        torch = _lib.require_cuda()
+        if isinstance(x, np.ndarray):
+            return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(self.device())
+        return x.to(self.device(), torch.float32)
+
+    def search(self, x, k: int):
+        """(D, I): the k best database entries per row of x, best first (faiss IndexFlat.search)."""
+        torch = _lib.require_cuda()
+        xq = self._to_device(x)
+        xb = self.database()
+        nq, nb = xq.shape[0], xb.shape[0]
+        keep_max = self.metric_type == METRIC_INNER_PRODUCT
+        D = np.full((nq, k), -np.inf if keep_max else np.inf, dtype=np.float32)
+        I = np.full((nq, k), -1, dtype=np.int64)
+        if nq == 0 or nb == 0:
+            return D, I
+        oa, ob = gemm.prepare_pair(xq, xb, self.precise)
+        if k == 1 and keep_max:
+            best, col = gemm.gemm_rowargmax(oa, ob)   # fused epilogue: nothing is materialised
+            D[:, 0], I[:, 0] = best.cpu().numpy(), col.cpu().numpy()
+            return D, I
+        kk = min(k, nb)
+        d, i = self._knn_dense(xq, xb, oa, ob, kk)
+        D[:, :kk], I[:, :kk] = d, i
+        return D, I
+
+    def max_similarity(self, x):
+        """max_j <x_i, db_j> per row as a device tensor -- all score normalisation needs from search(x, 1)."""
+        assert self.metric_type == METRIC_INNER_PRODUCT
+        xq = self._to_device(x)
+        oa, ob = gemm.prepare_pair(xq, self.database(), self.precise)
+        return gemm.gemm_rowmax(oa, ob)
+
+    def _knn_dense(self, xq, xb, oa, ob, k):
+        """General k: per-row top-k from stored score tiles (row blocks sized to ~1 GiB of scores)."""
+        torch = _lib.require_cuda()
+        nq, nb = oa.rows, ob.rows
+        keep_max = self.metric_type == METRIC_INNER_PRODUCT
+        qn = bn = None
+        if not keep_max:
+            qn, bn = gemm.row_sqnorm(xq), gemm.row_sqnorm(xb)
+        step = max(1, min(nq, (1 << 28) // max(nb, 1)))
+        D = np.empty((nq, k), np.float32)
+        I = np.empty((nq, k), np.int64)
+        for r0 in range(0, nq, step):
+            r1 = min(nq, r0 + step)
+            sub = gemm.Operand(oa.panel[r0:r1], r1 - r0, oa.k, oa.split)
+            s = gemm.gemm_store(sub, ob)
+            if not keep_max:
+                s = qn[r0:r1, None] + bn[None, :] - 2.0 * s
+            # stable order: best first, equal scores by ascending database index
+            order = torch.sort(-s if keep_max else s, dim=1, stable=True).indices[:, :k]
+            D[r0:r1] = torch.gather(s, 1, order).cpu().numpy()
+            I[r0:r1] = order.cpu().numpy()
+        return D, I
+
+    def range_search_max_results(self, x, max_results: int, min_results: int, capacity: Optional[int] = None):
+        """faiss.contrib.exhaustive_search.range_search_max_results over exponential query batches.
+
+        Returns device tensors (score, query_row, db_row) of every result FAISS would return -- all pairs whose
+        score beats the final radius, strictly -- plus that radius.  The schedule is followed literally: per batch
+        a range search with the CURRENT radius; when the running total exceeds max_results, the radius becomes the
+        (min_results+1)-th best stored score and everything stored is re-filtered with the strict comparison.
+
+        Invariants ("beyond" = greater for inner product, smaller for L2):
+          total  = number of results FAISS holds now (every pair seen so far beyond `radius`)
+          held   = results kept in the device buffer = every pair seen so far beyond `prune`
+          prune  is `radius` unless the buffer overflowed inside a batch; then it is the (min_results+1)-th best
+                 held score, which the next tightening can only move further, so nothing FAISS would finally
+                 keep is lost, while `total` still counts every hit beyond `radius` (the emit epilogue counts
+                 with one threshold and stores with the other).
+        """
+        torch = _lib.require_cuda()
+        xq = self._to_device(x)
+        xb = self.database()
+        dev = xq.device
+        keep_max = self.metric_type == METRIC_INNER_PRODUCT
+        radius = -1e10 if keep_max else 1e10
+        nq, nb = xq.shape[0], xb.shape[0]
+        if nq == 0 or nb == 0:
+            z = torch.empty(0, dtype=torch.int64, device=dev)
+            return torch.empty(0, device=dev), z, z.clone(), radius
+        oa, ob = gemm.prepare_pair(xq, xb, self.precise)
+        qn = bn = None
+        if not keep_max:
+            qn, bn = gemm.row_sqnorm(xq), gemm.row_sqnorm(xb)
+        if capacity is None:
+            capacity = max(4 * max_results, min(32 * nb, 1 << 26)) + 65536
+        hits = gemm.HitBuffer(int(capacity), dev)
+        held, total, prune = 0, 0, radius
+        unbounded = True   # radius still at its initial value: every pair is a hit, emission size is known
+        for b0, b1 in exponential_batches(nq):
+            r0 = b0
+            rows = b1 - b0
+            while r0 < b1:
+                rows = max(1, min(rows, b1 - r0))
+                room = hits.capacity - held
+                if unbounded and prune == radius and rows * nb > room:
+                    rows = room // nb          # known emission: size the slice instead of trying
+                if rows >= 1:
+                    hits.counters[0] = held
+                    hits.counters[1] = 0
+                    gemm.gemm_emit(oa, ob, hits, radius, prune, metric_l2=not keep_max, a_norm=qn, b_norm=bn,
+                                   row_offset=r0, rows=slice(r0, r0 + rows))
+                    stored, counted = hits.read_counters()
+                if rows < 1 or stored > hits.capacity:
+                    # does not fit: forget this launch, prune (or grow), retry with fewer rows
+                    if held > min_results + 1:
+                        prune = self._kth_best(hits.score[:held], min_results + 1, keep_max)
+                        held = self._refilter(hits, held, prune, keep_max)
+                    else:
+                        hits = self._grow(hits, held, 2 * hits.capacity + nb)
+                    rows = max(1, rows // 2)
+                    continue
+                held, total = stored, total + counted
+                r0 += rows
+                rows = b1 - r0
+            if total > max_results:
+                radius = self._kth_best(hits.score[:held], min_results + 1, keep_max)
+                held = self._refilter(hits, held, radius, keep_max)
+                total, prune, unbounded = held, radius, False
+        return hits.score[:held], hits.row[:held].long(), hits.col[:held].long(), radius
+
+    @staticmethod
+    def _kth_best(scores, k: int, keep_max: bool) -> float:
+        """The k-th best stored score (k-th largest for IP, k-th smallest for L2) as a Python float."""
+        import torch
+        if keep_max:
+            return float(torch.topk(scores, k, largest=True, sorted=True).values[-1])
+        return float(torch.topk(scores, k, largest=False, sorted=True).values[-1])
+
+    @staticmethod
+    def _refilter(hits, held: int, radius: float, keep_max: bool) -> int:
+        import torch
+        sc = hits.score[:held]
+        keep = sc > radius if keep_max else sc < radius
+        n = int(keep.sum())
+        hits.score[:n] = sc[keep]
+        hits.row[:n] = hits.row[:held][keep]
+        hits.col[:n] = hits.col[:held][keep]
+        return n
+
+    @staticmethod
+    def _grow(hits, held, capacity):
+        new = gemm.HitBuffer(capacity, hits.score.device)
+        new.score[:held], new.row[:held], new.col[:held] = hits.score[:held], hits.row[:held], hits.col[:held]
+        return new
+
+
+def index_factory(d: int, description: str = "Flat", metric: int = METRIC_L2) -> FlatIndex:
+    if description != "Flat":
+        raise NotImplementedError(f"only the brute-force 'Flat' index used by vsc2022 is provided, got {description!r}")
+    return FlatIndex(d, metric)
+
+
+class VideoIndex:
+    def __init__(self, dim: int, codec_str: str = "Flat", metric: int = METRIC_INNER_PRODUCT):
+        self.dim = dim
+        self.index = index_factory(dim, codec_str, metric)
+        self.video_clip_idx: List[int] = []
+        self.video_clip_to_video_ids: list = []
+        self.video_metadata = {}
+
+    def add(self, db: List[VideoFeature]):
+        for vf in db:
+            n = vf.feature.shape[0]
+            self.video_clip_idx.extend(range(n))
+            self.video_clip_to_video_ids.extend([vf.video_id] * n)
+            self.video_metadata[vf.video_id] = vf.metadata()
+            self.index.add(vf.feature)
+
+    def search(self, queries: List[VideoFeature], global_k: int) -> List[PairMatches]:
+        query_ids, query_indices = [], []
+        for q in queries:
+            query_ids.extend([q.video_id] * len(q))
+            query_indices.extend(range(len(q)))
+        query_metadatas = {q.video_id: q.metadata() for q in queries}
+        query_features = np.concatenate([q.feature for q in queries])
+        if global_k < 0:
+            logging.warning(
+                "Using local k for KNN search. Warning: this is against the VSC rules, since predictions for a "
+                "query-ref pair are not independent of other references. KNN search is provided for comparison.")
+            hits = self._knn_search(query_features, -global_k)
+        else:
+            hits = self._global_threshold_knn_search(query_features, global_k)
+        grouped = collections.defaultdict(list)
+        for i, j, score in hits:
+            qid, rid = query_ids[i], self.video_clip_to_video_ids[j]
+            grouped[qid, rid].append(PairMatch(
+                query_timestamps=query_metadatas[qid].get_timestamps(query_indices[i]),
+                ref_timestamps=self.video_metadata[rid].get_timestamps(self.video_clip_idx[j]),
+                score=score))
+        return [PairMatches(qid, rid, matches) for (qid, rid), matches in grouped.items()]
+
+    # ---- engines -----------------------------------------------------------------------------------------
+    def global_topk_device(self, query_features, global_k: int):
+        """Device tensors (query_row, db_row, score) of the global top-`global_k` frame pairs, best first; equal
+        scores keep (query row, database row) ascending -- the order of the reference's stable sort."""
+        torch = _lib.require_cuda()
+        keep_max = self.index.metric_type == METRIC_INNER_PRODUCT
+        score, row, col, _ = self.index.range_search_max_results(query_features, 2 * global_k, global_k)
+        if score.numel() == 0:
+            return row, col, score
+        order = torch.argsort(row * self.index.ntotal + col, stable=True)       # (query row, db row) ascending
+        score, row, col = score[order], row[order], col[order]
+        order = torch.sort(score, descending=keep_max, stable=True).indices[:global_k]
+        return row[order], col[order], score[order]
+
+    def _global_threshold_knn_search(self, query_features: np.ndarray, global_k: int) -> Iterable[SearchIndices]:
+        row, col, score = self.global_topk_device(query_features, global_k)
+        return list(zip(row.cpu().numpy().tolist(), col.cpu().numpy().tolist(), score.cpu().numpy()))
+
+    def _knn_search(self, query_features: np.ndarray, k: int) -> Iterable[SearchIndices]:
+        similarity, ids = self.index.search(query_features, k)
+        for i in range(ids.shape[0]):
+            for j in range(ids.shape[1]):
+                yield (i, ids[i, j], similarity[i, j])
