@@ -60,7 +60,7 @@ def test_reference_index_test(global_k):
     for r in results:
         assert r.query_id[1:] == r.ref_id[1:]
     if global_k == -1:
-        assert len(results) == 3 and all(len(r.matches) == 1 for r in results)
+        assert len(results) == 3 and all(len(r.matches) == 3 for r in results)
     else:
         assert results == []  # all 9 best distances tie at 0: the strict radius drops them (oracle agrees)
 
