@@ -107,6 +107,27 @@ int vsc_gemm_emit(const void *d_a, int64_t m, const void *d_b, int64_t n, int32_
                   int64_t col_offset, float *d_score, int32_t *d_row, int32_t *d_col, uint64_t capacity,
                   unsigned long long *d_counters, vsc_stream_t stream);
 
+/* -------------------------------------------------------------------------
+ * Stage A: SSCD ResNet-50 frame descriptors (vsc/baseline/inference_impl.py:210-239 runs the TorchScript model;
+ * architecture contract vsc/baseline/adapt_sscd_model.py:56-70).  Activations NHWC bf16; BN folded into the
+ * convolution weights [cout][k] (bf16) and biases (fp32) by the host.
+ * ------------------------------------------------------------------------- */
+/* out[m][n] (bf16, row stride ldc) = relu?(A[m][:] . W[n][:] + bias[n] + residual[m][n]); n % 32 == 0 */
+int vsc_gemm_conv(const void *d_a, int64_t m, const void *d_w, int64_t n, int32_t k, const float *d_bias,
+                  const void *d_residual, int32_t relu, void *d_out_bf16, int64_t ldc, vsc_stream_t stream);
+/* fp32 out[m][n] = A . W^T + bias[n] (projection head) */
+int vsc_gemm_linear(const void *d_a, int64_t m, const void *d_w, int64_t n, int32_t k, const float *d_bias, float *d_out,
+                    int64_t ldc, vsc_stream_t stream);
+/* 7x7/2 stem patches [n*ho*wo][192]; mode 0: uint8 NHWC pixels (normalised here), 1: float32 NCHW normalised */
+int vsc_im2col_stem(const void *d_in, int32_t mode, int32_t n, int32_t h, int32_t w, void *d_out, vsc_stream_t stream);
+/* 3x3 pad-1 patches [n*ho*wo][9*c] of an NHWC bf16 tensor, stride 1 or 2 */
+int vsc_im2col3x3(const void *d_in, int32_t n, int32_t h, int32_t w, int32_t c, int32_t stride, void *d_out,
+                  vsc_stream_t stream);
+int vsc_subsample2(const void *d_in, int32_t n, int32_t h, int32_t w, int32_t c, void *d_out, vsc_stream_t stream);
+int vsc_maxpool3x3s2(const void *d_in, int32_t n, int32_t h, int32_t w, int32_t c, void *d_out, vsc_stream_t stream);
+/* GeM pooling over hw pixels: (mean clamp(x, eps)^p)^(1/p), bf16 [n][c] out */
+int vsc_gem_pool(const void *d_in, int32_t n, int32_t hw, int32_t c, float p, float eps, void *d_out, vsc_stream_t stream);
+
 /* Number of kernel launches issued by this library since load (all entry points). */
 int64_t vsc_launch_count(void);
 

@@ -1,0 +1,82 @@
+"""GPU parity of stage A (SSCD ResNet-50 forward on the tensor-core GEMM) against a plain PyTorch fp32 model with
+the same seeded weights.  Floating-point stage: tolerance = bf16 activations through 53 convolutions ->
+cosine similarity >= 0.999 and relative L2 error <= 3e-2 per descriptor (stated here)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _cos(a, b):
+    return (a * b).sum(1) / (np.linalg.norm(a, axis=1) * np.linalg.norm(b, axis=1))
+
+
+@pytest.fixture(scope="module")
+def models():
+    import torch
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from vsc2022_b200.sscd import SSCDResNet50, TorchReference
+    ref = TorchReference(seed=0)
+    return SSCDResNet50(ref.trunk, ref.head), ref
+
+
+@pytest.mark.parametrize("hw", [(64, 64), (96, 128), (288, 288)])
+def test_descriptors_match_torch(models, hw):
+    import torch
+    from vsc2022_b200.sscd import normalize_pixels
+    ours, ref = models
+    g = torch.Generator(device="cuda"); g.manual_seed(hw[0])
+    frames = torch.randint(0, 256, (6, hw[0], hw[1], 3), generator=g, device="cuda", dtype=torch.uint8)
+    want = ref(normalize_pixels(frames)).cpu().numpy()
+    got_u8 = ours(frames).cpu().numpy()
+    got_f32 = ours(normalize_pixels(frames)).cpu().numpy()
+    for got in (got_u8, got_f32):
+        assert got.shape == (6, 512)
+        assert _cos(got, want).min() >= 0.999, _cos(got, want)
+        rel = np.linalg.norm(got - want, axis=1) / np.linalg.norm(want, axis=1)
+        assert rel.max() <= 3e-2, rel
+    np.testing.assert_allclose(got_u8, got_f32, rtol=0, atol=1e-2 * np.abs(want).max())
+
+
+def test_batching_is_transparent(models):
+    import torch
+    ours, _ = models
+    g = torch.Generator(device="cuda"); g.manual_seed(1)
+    frames = torch.randint(0, 256, (10, 64, 64, 3), generator=g, device="cuda", dtype=torch.uint8)
+    a = ours.forward(frames, batch=4).cpu().numpy()
+    b = ours.forward(frames, batch=10).cpu().numpy()
+    assert np.array_equal(a, b)
+
+
+def test_primitives_against_torch():
+    """im2col + GEMM-conv against torch.nn.functional.conv2d on grid data (exact), plus maxpool."""
+    import ctypes
+    import torch
+    import torch.nn.functional as F
+    from vsc2022_b200 import _lib
+    lib = _lib.load()
+    dev = torch.device("cuda")
+    sp = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    g = torch.Generator(device=dev); g.manual_seed(2)
+    n, h, w, c, cout = 3, 13, 17, 64, 128
+    x = (torch.randint(-8, 9, (n, h, w, c), generator=g, device=dev) / 8.0).to(torch.bfloat16)
+    wt = (torch.randint(-8, 9, (cout, c, 3, 3), generator=g, device=dev) / 8.0)
+    bias = torch.randint(-4, 5, (cout,), generator=g, device=dev).float()
+    for stride in (1, 2):
+        ho, wo = (h + 2 - 3) // stride + 1, (w + 2 - 3) // stride + 1
+        cols = torch.empty((n * ho * wo, 9 * c), dtype=torch.bfloat16, device=dev)
+        _lib.check(lib.vsc_im2col3x3(x.data_ptr(), n, h, w, c, stride, cols.data_ptr(), sp), "im2col")
+        panel = wt.permute(0, 2, 3, 1).reshape(cout, 9 * c).to(torch.bfloat16).contiguous()
+        res = (torch.randint(-8, 9, (n * ho * wo, cout), generator=g, device=dev) / 4.0).to(torch.bfloat16)
+        out = torch.empty((n * ho * wo, cout), dtype=torch.bfloat16, device=dev)
+        _lib.check(lib.vsc_gemm_conv(cols.data_ptr(), n * ho * wo, panel.data_ptr(), cout, 9 * c, bias.data_ptr(),
+                                     res.data_ptr(), 1, out.data_ptr(), cout, sp), "conv")
+        ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt, bias, stride=stride, padding=1).permute(0, 2, 3, 1).reshape(-1, cout)
+        ref = torch.relu(ref + res.float()).to(torch.bfloat16)
+        assert torch.equal(out, ref)
+    ho, wo = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
+    mp = torch.empty((n * ho * wo, c), dtype=torch.bfloat16, device=dev)
+    _lib.check(lib.vsc_maxpool3x3s2(x.data_ptr(), n, h, w, c, mp.data_ptr(), sp), "maxpool")
+    ref = F.max_pool2d(x.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).reshape(-1, c).to(torch.bfloat16)
+    assert torch.equal(mp, ref)

@@ -28,20 +28,23 @@ namespace {
 
 using vsc::kFullMask;
 
-constexpr int BM = 128, BN = 256, BK = 64;
+constexpr int BM = 128, BK = 64;  // the N tile (64 / 128 / 256) is a template parameter
 constexpr int STAGES = 4;
 constexpr int UMMA_K = 16;
 constexpr int kThreads = 192;
-constexpr uint32_t kStageBytesA = BM * BK * 2, kStageBytesB = BN * BK * 2;
-constexpr uint32_t kTmemCols = 512;  // two 256-column fp32 accumulators
+constexpr uint32_t kStageBytesA = BM * BK * 2;
 
-enum Epilogue { EPI_STORE = 0, EPI_ROWMAX = 1, EPI_EMIT = 2, EPI_ROWARGMAX = 3 };
+enum Epilogue { EPI_STORE = 0, EPI_ROWMAX = 1, EPI_EMIT = 2, EPI_ROWARGMAX = 3, EPI_CONV = 4 };
 
 struct GemmArgs {
     int64_t M, N;
     int K;  // multiple of BK
-    // STORE
+    // STORE (fp32, optional per-column bias) and CONV (bf16 out = relu?(acc + bias[col] + residual))
     float *c; int64_t ldc;
+    const float *bias;
+    const __nv_bfloat16 *residual;
+    __nv_bfloat16 *out_bf16;
+    int relu;
     // ROWMAX: order-preserving keys (vsc::float_to_key), combined with atomicMax
     uint32_t *rowmax_key;
     // ROWARGMAX: (key << 32) | (0xFFFFFFFF - column): atomicMax keeps the best score, lowest column on ties
@@ -56,9 +59,10 @@ struct GemmArgs {
     unsigned long long *counters;  // [0] entries claimed (may exceed capacity), [1] hits beyond count_thr
 };
 
+template <int BN>
 struct SharedStorage {
     alignas(1024) uint8_t a[STAGES][kStageBytesA];
-    alignas(1024) uint8_t b[STAGES][kStageBytesB];
+    alignas(1024) uint8_t b[STAGES][BN * BK * 2];
     alignas(8) uint64_t full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2];
     uint32_t tmem_base;
 };
@@ -146,7 +150,41 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs &g, float &best, i
         if (row_ok) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-                if (j < valid) g.c[row * g.ldc + col0 + j] = __uint_as_float(acc[j]);
+                if (j < valid) g.c[row * g.ldc + col0 + j] = __uint_as_float(acc[j]) + (g.bias ? g.bias[col0 + j] : 0.0f);
+        }
+    } else if (EPI == EPI_CONV) {
+        // convolution as GEMM: row = output pixel, col = output channel (NHWC).  Channel counts are multiples of
+        // 32, so a chunk is all-or-nothing and the 64 bytes a thread writes are one aligned run.
+        if (row_ok && valid >= 32) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) + g.bias[col0 + j];
+            if (g.residual) {
+                const uint4 *r4 = reinterpret_cast<const uint4 *>(g.residual + row * g.ldc + col0);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint4 r = r4[q];
+                    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        v[q * 8 + 2 * t] += __uint_as_float(w[t] << 16);
+                        v[q * 8 + 2 * t + 1] += __uint_as_float(w[t] & 0xFFFF0000u);
+                    }
+                }
+            }
+            uint4 *o4 = reinterpret_cast<uint4 *>(g.out_bf16 + row * g.ldc + col0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint32_t w[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    float lo = v[q * 8 + 2 * t], hi = v[q * 8 + 2 * t + 1];
+                    if (g.relu) { lo = fmaxf(lo, 0.0f); hi = fmaxf(hi, 0.0f); }
+                    const __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+                    w[t] = *reinterpret_cast<const uint32_t *>(&p);
+                }
+                o4[q] = make_uint4(w[0], w[1], w[2], w[3]);
+            }
         }
     } else if (EPI == EPI_ROWARGMAX) {
         int arg = -1;
@@ -227,12 +265,15 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs &g, float &best, i
     }
 }
 
-template <int EPI>
+template <int EPI, int BN>
 __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant__ CUtensorMap tma_a,
                                                            const __grid_constant__ CUtensorMap tma_b,
                                                            const GemmArgs g) {
     extern __shared__ uint8_t smem_raw[];
-    SharedStorage &sm = *reinterpret_cast<SharedStorage *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    using Storage = SharedStorage<BN>;
+    Storage &sm = *reinterpret_cast<Storage *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr uint32_t kStageBytesB = BN * BK * 2;
+    constexpr uint32_t kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;  // two fp32 accumulators of BN columns
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t m_tiles = (g.M + BM - 1) / BM, n_tiles = (g.N + BN - 1) / BN;
     const int64_t tiles = m_tiles * n_tiles;
@@ -366,7 +407,7 @@ int make_map(CUtensorMap *map, const void *ptr, int64_t rows, int k, int box_row
     return VSC_OK;
 }
 
-template <int EPI>
+template <int EPI, int BN>
 int launch(const void *a, const void *b, const GemmArgs &g, cudaStream_t stream) {
     if (g.M <= 0 || g.N <= 0) return VSC_OK;
     if (g.K <= 0 || g.K % BK != 0) { vsc::set_error("gemm: K=%d must be a positive multiple of %d", g.K, BK); return VSC_ERR_INVALID; }
@@ -378,14 +419,14 @@ int launch(const void *a, const void *b, const GemmArgs &g, cudaStream_t stream)
     if (rc != VSC_OK) return rc;
     rc = make_map(&mb, b, g.N, g.K, BN);
     if (rc != VSC_OK) return rc;
-    const size_t smem = sizeof(SharedStorage) + 1024;
-    VSC_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = sizeof(SharedStorage<BN>) + 1024;
+    VSC_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<EPI, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 148;
     VSC_CUDA_CHECK(cudaGetDevice(&dev));
     VSC_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int64_t tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
     const int grid = (int)(tiles < sms ? tiles : sms);
-    gemm_kernel<EPI><<<grid, kThreads, smem, stream>>>(ma, mb, g);
+    gemm_kernel<EPI, BN><<<grid, kThreads, smem, stream>>>(ma, mb, g);
     VSC_CUDA_CHECK(cudaGetLastError());
     vsc::count_launch();
     return VSC_OK;
@@ -413,7 +454,7 @@ extern "C" int vsc_gemm_store(const void *d_a, int64_t m, const void *d_b, int64
                               int64_t ldc, vsc_stream_t stream) {
     GemmArgs g = {};
     g.M = m; g.N = n; g.K = k; g.c = d_c; g.ldc = ldc;
-    return launch<EPI_STORE>(d_a, d_b, g, static_cast<cudaStream_t>(stream));
+    return launch<EPI_STORE, 256>(d_a, d_b, g, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int vsc_gemm_rowmax(const void *d_a, int64_t m, const void *d_b, int64_t n, int32_t k, float *d_rowmax,
@@ -426,12 +467,34 @@ extern "C" int vsc_gemm_rowmax(const void *d_a, int64_t m, const void *d_b, int6
     g.rowmax_key = reinterpret_cast<uint32_t *>(d_rowmax);
     fill_u32<<<(unsigned)((m + 255) / 256), 256, 0, stream>>>(g.rowmax_key, m, 0x007FFFFFu);  // key of -inf
     vsc::count_launch();
-    int rc = launch<EPI_ROWMAX>(d_a, d_b, g, stream);
+    int rc = launch<EPI_ROWMAX, 256>(d_a, d_b, g, stream);
     if (rc != VSC_OK) return rc;
     keys_to_float<<<(unsigned)((m + 255) / 256), 256, 0, stream>>>(g.rowmax_key, d_rowmax, m);
     VSC_CUDA_CHECK(cudaGetLastError());
     vsc::count_launch();
     return VSC_OK;
+}
+
+// Convolution as GEMM: out[m][n] (bf16, row stride ldc) = relu?(A[m][:] . W[n][:] + bias[n] + residual[m][n]).
+extern "C" int vsc_gemm_conv(const void *d_a, int64_t m, const void *d_w, int64_t n, int32_t k, const float *d_bias,
+                             const void *d_residual, int32_t relu, void *d_out_bf16, int64_t ldc,
+                             vsc_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (n % 32 != 0 || ldc % 8 != 0 || !d_bias) { vsc::set_error("vsc_gemm_conv: need n %% 32 == 0, ldc %% 8 == 0, a bias"); return VSC_ERR_INVALID; }
+    GemmArgs g = {};
+    g.M = m; g.N = n; g.K = k; g.bias = d_bias; g.residual = static_cast<const __nv_bfloat16 *>(d_residual);
+    g.relu = relu; g.out_bf16 = static_cast<__nv_bfloat16 *>(d_out_bf16); g.ldc = ldc;
+    if (n <= 64) return launch<EPI_CONV, 64>(d_a, d_w, g, stream);
+    if (n <= 128) return launch<EPI_CONV, 128>(d_a, d_w, g, stream);
+    return launch<EPI_CONV, 256>(d_a, d_w, g, stream);
+}
+
+// fp32 out[m][n] = A . W^T + bias[n]  (the SSCD projection head)
+extern "C" int vsc_gemm_linear(const void *d_a, int64_t m, const void *d_w, int64_t n, int32_t k, const float *d_bias,
+                               float *d_out, int64_t ldc, vsc_stream_t stream) {
+    GemmArgs g = {};
+    g.M = m; g.N = n; g.K = k; g.c = d_out; g.ldc = ldc; g.bias = d_bias;
+    return launch<EPI_STORE, 256>(d_a, d_w, g, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int vsc_gemm_rowargmax(const void *d_a, int64_t m, const void *d_b, int64_t n, int32_t k, float *d_score,
@@ -441,7 +504,7 @@ extern "C" int vsc_gemm_rowargmax(const void *d_a, int64_t m, const void *d_b, i
     GemmArgs g = {};
     g.M = m; g.N = n; g.K = k; g.rowbest = d_scratch;
     VSC_CUDA_CHECK(cudaMemsetAsync(d_scratch, 0, sizeof(unsigned long long) * (size_t)m, stream));
-    int rc = launch<EPI_ROWARGMAX>(d_a, d_b, g, stream);
+    int rc = launch<EPI_ROWARGMAX, 256>(d_a, d_b, g, stream);
     if (rc != VSC_OK) return rc;
     unpack_rowbest<<<(unsigned)((m + 255) / 256), 256, 0, stream>>>(d_scratch, d_score, d_col, m);
     VSC_CUDA_CHECK(cudaGetLastError());
@@ -459,5 +522,5 @@ extern "C" int vsc_gemm_emit(const void *d_a, int64_t m, const void *d_b, int64_
     g.a_norm = d_a_norm; g.b_norm = d_b_norm; g.metric_l2 = metric_l2;
     g.count_thr = count_thr; g.emit_thr = emit_thr; g.row_offset = row_offset; g.col_offset = col_offset;
     g.out_score = d_score; g.out_row = d_row; g.out_col = d_col; g.capacity = capacity; g.counters = d_counters;
-    return launch<EPI_EMIT>(d_a, d_b, g, static_cast<cudaStream_t>(stream));
+    return launch<EPI_EMIT, 256>(d_a, d_b, g, static_cast<cudaStream_t>(stream));
 }

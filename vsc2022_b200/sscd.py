@@ -1,0 +1,172 @@
+"""Stage A: SSCD frame-descriptor model (ResNet-50 trunk -> GeM pooling -> Linear(2048 -> 512), no L2 norm).
+
+The reference runs a downloaded TorchScript file (`vsc/baseline/inference_impl.py:173,229`); its architecture is
+documented in `vsc/baseline/adapt_sscd_model.py:56-70`.  Here every convolution is a tensor-core GEMM
+(`vsc_gemm_conv`: tcgen05 MMA, TMA-staged operands, folded BatchNorm bias + residual + ReLU in the epilogue,
+NHWC bf16 activations); 1x1 convolutions read the activation tensor directly, 3x3 / 7x7 go through im2col panels.
+Weights come from any torch module with the torchvision ResNet-50 layout (random init in tests and the bench:
+the SSCD checkpoint is a download the sandbox does not have).
+"""
+import ctypes
+from typing import List, Optional
+
+from . import _lib
+
+
+def _sp(torch, dev):
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+class _Conv:
+    """A convolution with BatchNorm folded in: bf16 weight panel [cout][k], fp32 bias [cout]."""
+
+    def __init__(self, torch, conv, bn, device, pad_k: Optional[int] = None):
+        w = conv.weight.detach().to(device, torch.float32)           # [cout, cin, kh, kw]
+        scale = bn.weight.detach().to(device, torch.float32) / torch.sqrt(bn.running_var.detach().to(device, torch.float32) + bn.eps)
+        bias = bn.bias.detach().to(device, torch.float32) - bn.running_mean.detach().to(device, torch.float32) * scale
+        w = w * scale[:, None, None, None]
+        cout, cin, kh, kw = w.shape
+        panel = w.permute(0, 2, 3, 1).reshape(cout, kh * kw * cin)   # k = (ky*kw + kx)*cin + c
+        if pad_k is not None and pad_k > panel.shape[1]:
+            panel = torch.cat([panel, torch.zeros((cout, pad_k - panel.shape[1]), device=device)], dim=1)
+        self.weight = panel.to(torch.bfloat16).contiguous()
+        self.bias = bias.contiguous()
+        self.cout, self.k = cout, self.weight.shape[1]
+        self.ksize, self.stride = kh, conv.stride[0]
+
+
+class SSCDResNet50:
+    def __init__(self, trunk, head, gem_p: float = 3.0, gem_eps: float = 1e-6, device=None):
+        """trunk: torchvision-style ResNet-50 (conv1, bn1, layer1..4); head: nn.Linear(2048, 512)."""
+        torch = _lib.require_cuda()
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        dev = self.device
+        self.stem = _Conv(torch, trunk.conv1, trunk.bn1, dev, pad_k=192)
+        self.blocks: List[dict] = []
+        for layer in (trunk.layer1, trunk.layer2, trunk.layer3, trunk.layer4):
+            for blk in layer:
+                self.blocks.append({
+                    "c1": _Conv(torch, blk.conv1, blk.bn1, dev), "c2": _Conv(torch, blk.conv2, blk.bn2, dev),
+                    "c3": _Conv(torch, blk.conv3, blk.bn3, dev),
+                    "down": _Conv(torch, blk.downsample[0], blk.downsample[1], dev) if blk.downsample is not None else None,
+                })
+        self.head_w = head.weight.detach().to(dev, torch.bfloat16).contiguous()   # [512][2048]
+        self.head_b = head.bias.detach().to(dev, torch.float32).contiguous()
+        self.gem_p, self.gem_eps = float(gem_p), float(gem_eps)
+        self.lib = _lib.load()
+
+    # ---- primitive launches ------------------------------------------------------------------------------------
+    def _conv(self, a, m, conv: _Conv, relu: bool, residual=None):
+        torch = _lib.require_cuda()
+        out = torch.empty((m, conv.cout), dtype=torch.bfloat16, device=self.device)
+        rc = self.lib.vsc_gemm_conv(a.data_ptr(), m, conv.weight.data_ptr(), conv.cout, conv.k, conv.bias.data_ptr(),
+                                    residual.data_ptr() if residual is not None else None, 1 if relu else 0,
+                                    out.data_ptr(), conv.cout, _sp(torch, self.device))
+        _lib.check(rc, "vsc_gemm_conv")
+        return out
+
+    def _im2col3x3(self, x, n, h, w, c, stride):
+        torch = _lib.require_cuda()
+        ho, wo = (h + 2 - 3) // stride + 1, (w + 2 - 3) // stride + 1
+        out = torch.empty((n * ho * wo, 9 * c), dtype=torch.bfloat16, device=self.device)
+        _lib.check(self.lib.vsc_im2col3x3(x.data_ptr(), n, h, w, c, stride, out.data_ptr(), _sp(torch, self.device)),
+                   "vsc_im2col3x3")
+        return out, ho, wo
+
+    # ---- forward -----------------------------------------------------------------------------------------------
+    def forward(self, frames, batch: int = 64):
+        """frames: uint8 [N, H, W, 3] pixels (normalised on the device like inference_impl.py:39-69) or float32
+        [N, 3, H, W] already normalised (what the reference model receives).  Returns float32 [N, 512] descriptors."""
+        torch = _lib.require_cuda()
+        frames = frames.to(self.device)
+        outs = [self._forward_batch(frames[i:i + batch]) for i in range(0, frames.shape[0], batch)]
+        return torch.cat(outs) if outs else torch.empty((0, self.head_w.shape[0]), device=self.device)
+
+    __call__ = forward
+
+    def _forward_batch(self, frames):
+        torch = _lib.require_cuda()
+        dev, lib = self.device, self.lib
+        with torch.cuda.device(dev):
+            if frames.dtype == torch.uint8:
+                n, h, w, _ = frames.shape
+                mode = 0
+            else:
+                n, _, h, w = frames.shape
+                mode = 1
+                frames = frames.to(torch.float32)
+            frames = frames.contiguous()
+            ho, wo = (h + 6 - 7) // 2 + 1, (w + 6 - 7) // 2 + 1
+            panel = torch.empty((n * ho * wo, 192), dtype=torch.bfloat16, device=dev)
+            _lib.check(lib.vsc_im2col_stem(frames.data_ptr(), mode, n, h, w, panel.data_ptr(), _sp(torch, dev)), "vsc_im2col_stem")
+            x = self._conv(panel, n * ho * wo, self.stem, relu=True)
+            h, w, c = ho, wo, 64
+            ho, wo = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
+            pooled = torch.empty((n * ho * wo, c), dtype=torch.bfloat16, device=dev)
+            _lib.check(lib.vsc_maxpool3x3s2(x.data_ptr(), n, h, w, c, pooled.data_ptr(), _sp(torch, dev)), "vsc_maxpool3x3s2")
+            x, h, w = pooled, ho, wo
+            for blk in self.blocks:
+                stride = blk["c2"].stride
+                identity = x
+                if blk["down"] is not None:
+                    src = x
+                    if stride == 2:
+                        h2, w2 = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+                        src = torch.empty((n * h2 * w2, c), dtype=torch.bfloat16, device=dev)
+                        _lib.check(lib.vsc_subsample2(x.data_ptr(), n, h, w, c, src.data_ptr(), _sp(torch, dev)), "vsc_subsample2")
+                        m_down = n * h2 * w2
+                    else:
+                        m_down = n * h * w
+                    identity = self._conv(src, m_down, blk["down"], relu=False)
+                y = self._conv(x, n * h * w, blk["c1"], relu=True)
+                cols, h, w = self._im2col3x3(y, n, h, w, blk["c1"].cout, stride)
+                y = self._conv(cols, n * h * w, blk["c2"], relu=True)
+                x = self._conv(y, n * h * w, blk["c3"], relu=True, residual=identity)
+                c = blk["c3"].cout
+            pooled = torch.empty((n, c), dtype=torch.bfloat16, device=dev)
+            _lib.check(lib.vsc_gem_pool(x.data_ptr(), n, h * w, c, self.gem_p, self.gem_eps, pooled.data_ptr(), _sp(torch, dev)),
+                       "vsc_gem_pool")
+            out = torch.empty((n, self.head_w.shape[0]), dtype=torch.float32, device=dev)
+            _lib.check(lib.vsc_gemm_linear(pooled.data_ptr(), n, self.head_w.data_ptr(), self.head_w.shape[0], c,
+                                           self.head_b.data_ptr(), out.data_ptr(), self.head_w.shape[0], _sp(torch, dev)),
+                       "vsc_gemm_linear")
+        return out
+
+
+class TorchReference:
+    """Plain PyTorch fp32 statement of the same model (parity oracle for this floating-point stage)."""
+
+    def __init__(self, seed: int = 0, device="cuda"):
+        import torch
+        import torchvision
+        torch.manual_seed(seed)
+        self.trunk = torchvision.models.resnet50(weights=None)
+        # give BatchNorm non-trivial statistics so the folding is actually exercised
+        for mod in self.trunk.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.running_mean.normal_(0, 0.1)
+                mod.running_var.uniform_(0.5, 1.5)
+                mod.weight.data.uniform_(0.5, 1.5)
+                mod.bias.data.normal_(0, 0.1)
+        self.head = torch.nn.Linear(2048, 512)
+        self.trunk.eval().to(device)
+        self.head.eval().to(device)
+        self.device = device
+
+    def __call__(self, x_nchw, gem_p=3.0, gem_eps=1e-6):
+        import torch
+        t = self.trunk
+        with torch.no_grad():
+            x = t.maxpool(t.relu(t.bn1(t.conv1(x_nchw))))
+            x = t.layer4(t.layer3(t.layer2(t.layer1(x))))
+            pooled = x.clamp(min=gem_eps).pow(gem_p).mean(dim=(2, 3)).pow(1.0 / gem_p)
+            return self.head(pooled)
+
+
+def normalize_pixels(frames_u8_nhwc):
+    """ToTensor + Normalize of inference_impl.py:39-69 for uint8 NHWC frames -> float32 NCHW."""
+    import torch
+    x = frames_u8_nhwc.permute(0, 3, 1, 2).float() / 255.0
+    mean = torch.tensor([0.485, 0.456, 0.406], device=x.device)[None, :, None, None]
+    std = torch.tensor([0.229, 0.224, 0.225], device=x.device)[None, :, None, None]
+    return (x - mean) / std
