@@ -37,18 +37,19 @@ class CandidateGeneration:
         self._ref_ids = [r.video_id for r in references]
         self._ref_lengths = np.array([len(r) for r in references], dtype=np.int64)
 
-    def query(self, queries: List[VideoFeature], global_k: int, limit: Optional[int] = None) -> List[CandidatePair]:
-        """`limit` (extension): keep only the best `limit` pairs -- what every caller in the reference does next."""
+    def query(self, queries: List[VideoFeature], global_k: int, limit: Optional[int] = None, group=None) -> List[CandidatePair]:
+        """`limit` (extension): keep only the best `limit` pairs -- what every caller in the reference does next.
+        `group` (extension): query-sharded search over the ranks of a torch.distributed process group."""
         if type(self.aggregation) is MaxScoreAggregation and global_k >= 0:
-            return self._query_max_fused(queries, global_k, limit)
+            return self._query_max_fused(queries, global_k, limit, group)
         matches = self.index.search(queries, global_k=global_k)
         candidates = sorted((self.aggregation.score(m) for m in matches), key=lambda c: c.score, reverse=True)
         return candidates if limit is None else candidates[:limit]
 
-    def _query_max_fused(self, queries, global_k, limit):
+    def _query_max_fused(self, queries, global_k, limit, group=None):
         torch = _lib.require_cuda()
         feats = np.concatenate([q.feature for q in queries])
-        row, col, score = self.index.global_topk_device(feats, global_k)
+        row, col, score = self.index.global_topk_device(feats, global_k, group=group)
         if score.numel() == 0:
             return []
         dev = score.device

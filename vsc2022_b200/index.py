@@ -179,7 +179,8 @@ class FlatIndex:
             I[r0:r1] = order.cpu().numpy()
         return D, I
 
-    def range_search_max_results(self, x, max_results: int, min_results: int, capacity: Optional[int] = None):
+    def range_search_max_results(self, x, max_results: int, min_results: int, capacity: Optional[int] = None,
+                                 group=None):
         """faiss.contrib.exhaustive_search.range_search_max_results over exponential query batches.
 
         Returns device tensors (score, query_row, db_row) of every result FAISS would return -- all pairs whose
@@ -194,7 +195,14 @@ class FlatIndex:
                  held score, which the next tightening can only move further, so nothing FAISS would finally
                  keep is lost, while `total` still counts every hit beyond `radius` (the emit epilogue counts
                  with one threshold and stores with the other).
+
+        Multi-GPU (`group` / an initialised default process group with world size > 1): every rank holds the same
+        queries and references and takes a contiguous slice of the rows of EVERY batch; `total` is all-reduced
+        and the new radius is the (min_results+1)-th best over all ranks' held scores (distributed.agree_radius).
+        Each rank returns ITS survivors; VideoIndex.global_topk_device gathers them.
         """
+        from . import distributed as D
+        rank, ws = D.world(group)
         torch = _lib.require_cuda()
         xq = self._to_device(x)
         xb = self.database()
@@ -215,8 +223,12 @@ class FlatIndex:
         held, total, prune = 0, 0, radius
         unbounded = True   # radius still at its initial value: every pair is a hit, emission size is known
         for b0, b1 in exponential_batches(nq):
+            if ws > 1:   # this rank's slice of the batch
+                lo, hi = D.shard_bounds(b1 - b0, rank, ws)
+                b0, b1 = b0 + lo, b0 + hi
             r0 = b0
             rows = b1 - b0
+            batch_counted = 0
             while r0 < b1:
                 rows = max(1, min(rows, b1 - r0))
                 room = hits.capacity - held
@@ -237,13 +249,18 @@ class FlatIndex:
                         hits = self._grow(hits, held, 2 * hits.capacity + nb)
                     rows = max(1, rows // 2)
                     continue
-                held, total = stored, total + counted
+                held, batch_counted = stored, batch_counted + counted
                 r0 += rows
                 rows = b1 - r0
+            total += D.global_count(batch_counted, dev, group) if ws > 1 else batch_counted
             if total > max_results:
-                radius = self._kth_best(hits.score[:held], min_results + 1, keep_max)
+                if ws > 1:
+                    radius = D.agree_radius(hits.score[:held], min_results + 1, keep_max, group)
+                else:
+                    radius = self._kth_best(hits.score[:held], min_results + 1, keep_max)
                 held = self._refilter(hits, held, radius, keep_max)
-                total, prune, unbounded = held, radius, False
+                total = D.global_count(held, dev, group) if ws > 1 else held
+                prune, unbounded = radius, False
         return hits.score[:held], hits.row[:held].long(), hits.col[:held].long(), radius
 
     @staticmethod
@@ -318,12 +335,16 @@ class VideoIndex:
         return [PairMatches(qid, rid, matches) for (qid, rid), matches in grouped.items()]
 
     # ---- engines -----------------------------------------------------------------------------------------
-    def global_topk_device(self, query_features, global_k: int):
+    def global_topk_device(self, query_features, global_k: int, group=None):
         """Device tensors (query_row, db_row, score) of the global top-`global_k` frame pairs, best first; equal
-        scores keep (query row, database row) ascending -- the order of the reference's stable sort."""
+        scores keep (query row, database row) ascending -- the order of the reference's stable sort.  With a
+        process group of several ranks the search is query-sharded and every rank gets the full result."""
         torch = _lib.require_cuda()
+        from . import distributed as D
         keep_max = self.index.metric_type == METRIC_INNER_PRODUCT
-        score, row, col, _ = self.index.range_search_max_results(query_features, 2 * global_k, global_k)
+        score, row, col, _ = self.index.range_search_max_results(query_features, 2 * global_k, global_k, group=group)
+        if D.world(group)[1] > 1:
+            score, row, col = (D.all_gather_variable(t.contiguous(), group) for t in (score, row, col))
         if score.numel() == 0:
             return row, col, score
         order = torch.argsort(row * self.index.ntotal + col, stable=True)       # (query row, db row) ascending
