@@ -1,0 +1,40 @@
+"""Worker of tests/test_multigpu_gpu.py: run under `python -m torch.distributed.run --nproc-per-node 2`."""
+import faulthandler
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+faulthandler.dump_traceback_later(120, exit=True)
+rank, ws = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+
+from oracle import synth  # noqa: E402
+from vsc2022_b200 import distributed as D, vta  # noqa: E402
+from vsc2022_b200.candidates import CandidateGeneration, MaxScoreAggregation  # noqa: E402
+from vsc2022_b200.index import VideoFeature  # noqa: E402
+
+rng = np.random.default_rng(3)
+grid = lambda n: (rng.integers(-16, 17, size=(n, 64)) / 16.0).astype(np.float32)  # noqa: E731
+q = [VideoFeature(video_id=i, timestamps=np.arange(24) * 1.0, feature=grid(24)) for i in range(60)]
+r = [VideoFeature(video_id=1000 + i, timestamps=np.arange(24) * 1.0, feature=grid(24)) for i in range(150)]
+cg = CandidateGeneration(r, MaxScoreAggregation())
+K = 1200 * len(q) // 40
+flat = lambda cs: [(c.query_id, c.ref_id, float(c.score)) for c in cs]  # noqa: E731
+sharded = flat(cg.query(q, K, group=dist.group.WORLD))     # query rows sharded, radius agreed across ranks
+single = flat(cg.query(q, K))                              # every rank alone
+assert sharded == single and len(single) > 10, "sharded search differs from single-GPU search"
+
+srng = np.random.default_rng(5)
+sims = [synth.sim_matrix(srng, 64, 64) for _ in range(37)]
+model = vta.build_vta_model("TN", tn_max_step=5, min_length=4)
+lo, hi = D.shard_bounds(len(sims), rank, ws)
+everything = D.gather_lists(model.forward_sim([(str(i), sims[i]) for i in range(lo, hi)]))
+alone = model.forward_sim([(str(i), s) for i, s in enumerate(sims)])
+assert everything == alone, "pair-sharded TN differs from single-GPU TN"
+print(f"MULTIGPU_OK rank={rank} candidates={len(single)} boxes={sum(len(b) for _, b in alone)}", flush=True)
+dist.destroy_process_group()
