@@ -132,6 +132,75 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def stage_numbers(dev, peaks):
+    """Secondary measurements of the other two stages of the path (N=1 only; device-timed, synthetic data)."""
+    import torch
+    from vsc2022_b200 import gemm
+    from vsc2022_b200.index import VideoIndex
+    out = {}
+
+    def timed(fn, n):
+        fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / n
+
+    # ---- stage B, BASELINE.json configs[2]: 40k query x 200k ref 512-d descriptors, global top-K (K = 1200/query video)
+    g = torch.Generator(device=dev)
+    g.manual_seed(3)
+    nqv, nrv, frames, d = 1250, 6250, 32, 512
+    q = torch.randn((nqv * frames, d), generator=g, device=dev).bfloat16().float()   # bf16-representable descriptors
+    r = torch.randn((nrv * frames, d), generator=g, device=dev).bfloat16().float()
+    for v in range(0, nqv, 20):                                                     # 5 % planted 16-frame copies
+        rv = (v * 7919) % nrv
+        q[v * frames + 8:v * frames + 24] = r[rv * frames + 4:rv * frames + 20]
+    oa, ob = gemm.prepare_pair(q, r)
+    flops = 2.0 * q.shape[0] * r.shape[0] * d
+    ms = timed(lambda: gemm.gemm_rowmax(oa, ob), 5)
+    out["descriptor_gemm_rowmax"] = {
+        "shape": [q.shape[0], r.shape[0], d], "ms": ms, "tflops": flops / ms / 1e9,
+        "roofline": {"bound": "tensor", "achieved": flops / ms / 1e9, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                     "frac": flops / ms / 1e9 / peaks["bf16_tflops"]}}
+    index = VideoIndex(d)
+    index.index.add_device(r)
+    K = 1200 * nqv
+    ms = timed(lambda: index.global_topk_device(q, K), 3)
+    out["descriptor_search_global_topk"] = {
+        "workload": "c3: 40k query x 200k ref x 512-d, K=1.5M, FAISS radius schedule (13 batches) + final ordering",
+        "ms": ms, "descriptors_per_s": (q.shape[0] + r.shape[0]) / ms * 1e3,
+        "gemm_equivalent_tflops": flops / ms / 1e9}
+    del q, r, oa, ob, index
+    torch.cuda.empty_cache()
+
+    # ---- stage A, BASELINE.json configs[1]: SSCD ResNet-50 on synthetic 288x288 frames (random weights: the
+    # checkpoint is a download), bf16 tensor-core GEMMs
+    from vsc2022_b200.sscd import SSCDResNet50, TorchReference
+    ref = TorchReference(seed=0, device=dev)
+    model = SSCDResNet50(ref.trunk, ref.head, device=dev)
+    n = 2048
+    frames_u8 = torch.randint(0, 256, (n, 288, 288, 3), generator=g, device=dev, dtype=torch.uint8)
+    model.forward(frames_u8[:256], batch=128)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    model.forward(frames_u8, batch=128)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    tf = n * 13.513e9 / ms / 1e9
+    out["sscd_resnet50_inference"] = {
+        "workload": "c2 slice: 2048 synthetic 288x288 uint8 frames, batch 128, bf16 (full config: 10k frames)",
+        "ms": ms, "frames_per_s": n / ms * 1e3,
+        "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                     "frac": tf / peaks["bf16_tflops"], "algorithmic_flops_per_frame": 13.513e9}}
+    return out
+
+
 def run_gpu(args, rank, local_rank, world):
     import numpy as np
     import torch
@@ -206,6 +275,10 @@ def run_gpu(args, rank, local_rank, world):
         peaks, peak_src = measured_peaks()
         algo_bytes = n * 4 * LQ * LR
         achieved = algo_bytes / (ms_max * 1e-3) / 1e9
+        stages = None
+        if world == 1 and not args.no_stages:
+            del host_sims
+            stages = stage_numbers(dev, peaks)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             rate, cores, dt, _ = cpu_reference_run(96, seed=4)
@@ -234,6 +307,7 @@ def run_gpu(args, rank, local_rank, world):
                                        "tn_dp_kernel": stage[2]},
                          "tn_topk_frac": algo_bytes / (stage[0] * 1e-3) / 1e9 / peaks["hbm_gbs"] if stage[0] > 0 else None},
             "cpu_baseline": cpu,
+            "stages": stages,
             "result_check": {"boxes_per_pair": float(np.mean(n_boxes)),
                              "pairs_on_fast_pipeline": int((status == 0).sum()),
                              "pairs_on_general_kernel": int((status == 2).sum()),
@@ -256,6 +330,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stages", action="store_true", help="skip the secondary stage A / stage B measurements")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
