@@ -66,9 +66,10 @@ int vcsl_tn_batch(const float *d_sims, const int64_t *d_off, const int32_t *d_lq
 int vsc_tn_set_profiling(int on);
 int vsc_tn_last_stage_ms(float *out4);
 
-/* Development aid: cumulative DP work counters {first-sweep layers, incremental layer steps,
- * chains found, chain nodes}; all zero unless the library was built with -DVSC_TN_COUNTERS. */
-int vsc_tn_debug_counters(unsigned long long *out4);
+/* Development aid: DP phase clocks summed over warps since the last call (reading resets them):
+ * SM cycles in {first sweep, end-node search, chain walk, zero + score, box filter, incremental sweeps},
+ * incremental layer steps, warps.  All zero unless the library was built with -DVSC_TN_COUNTERS. */
+int vsc_tn_debug_counters(unsigned long long *out8);
 
 /* -------------------------------------------------------------------------
  * Stage B: descriptor similarity on tensor cores (tcgen05 / TMEM / TMA).

@@ -28,9 +28,3 @@ for want_maxsim in (False, True):
     print(f"maxsim={want_maxsim} pairs={n_pairs} {L}x{L}: {ms:.3f} ms/step, {n_pairs / ms * 1e3:.0f} pairs/s, {gbs:.0f} GB/s algorithmic")
 bx, nb, ms_, st = res.to_host()
 print("boxes/pair mean", nb.mean(), "exact-kernel pairs", int(st.sum()))
-import ctypes
-c = (ctypes.c_ulonglong * 4)()
-_lib.load().vsc_tn_debug_counters(c)
-print("dp counters (cumulative over all calls): first-sweep layers %d, incremental steps %d, chains %d, chain nodes %d" % tuple(c))
-if c[2]:
-    print("  per chain: %.1f incremental layers, %.1f nodes" % (c[1] / c[2], c[3] / c[2]))

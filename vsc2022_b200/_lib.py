@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "csrc", "libvsc_b200.so")
+# VSC_B200_LIB: development override (e.g. a build with -DVSC_TN_COUNTERS); the product library is the in-tree one
+LIB_PATH = os.environ.get("VSC_B200_LIB") or os.path.join(_PKG, "csrc", "libvsc_b200.so")
 
 VSC_OK = 0
 

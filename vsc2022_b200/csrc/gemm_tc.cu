@@ -65,6 +65,9 @@ struct SharedStorage {
     alignas(1024) uint8_t b[STAGES][BN * BK * 2];
     alignas(8) uint64_t full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2];
     uint32_t tmem_base;
+    // CONV epilogue: per epilogue warp, a 32-row x 64-byte transpose buffer for the residual tile coming in and one
+    // for the bf16 tile going out (16-byte units, XOR-swizzled: see conv_unit)
+    alignas(16) uint4 stage_in[4][128], stage_out[4][128];
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -152,40 +155,6 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs &g, float &best, i
             for (int j = 0; j < 32; ++j)
                 if (j < valid) g.c[row * g.ldc + col0 + j] = __uint_as_float(acc[j]) + (g.bias ? g.bias[col0 + j] : 0.0f);
         }
-    } else if (EPI == EPI_CONV) {
-        // convolution as GEMM: row = output pixel, col = output channel (NHWC).  Channel counts are multiples of
-        // 32, so a chunk is all-or-nothing and the 64 bytes a thread writes are one aligned run.
-        if (row_ok && valid >= 32) {
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) + g.bias[col0 + j];
-            if (g.residual) {
-                const uint4 *r4 = reinterpret_cast<const uint4 *>(g.residual + row * g.ldc + col0);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const uint4 r = r4[q];
-                    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        v[q * 8 + 2 * t] += __uint_as_float(w[t] << 16);
-                        v[q * 8 + 2 * t + 1] += __uint_as_float(w[t] & 0xFFFF0000u);
-                    }
-                }
-            }
-            uint4 *o4 = reinterpret_cast<uint4 *>(g.out_bf16 + row * g.ldc + col0);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                uint32_t w[4];
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    float lo = v[q * 8 + 2 * t], hi = v[q * 8 + 2 * t + 1];
-                    if (g.relu) { lo = fmaxf(lo, 0.0f); hi = fmaxf(hi, 0.0f); }
-                    const __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
-                    w[t] = *reinterpret_cast<const uint32_t *>(&p);
-                }
-                o4[q] = make_uint4(w[0], w[1], w[2], w[3]);
-            }
-        }
     } else if (EPI == EPI_ROWARGMAX) {
         int arg = -1;
 #pragma unroll
@@ -263,6 +232,70 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs &g, float &best, i
             }
         }
     }
+}
+
+// CONV epilogue data path.  A thread owns one accumulator ROW (tcgen05.ld 32x32b), so direct global accesses would
+// touch 32 different 128-byte lines per warp instruction (measured: the K=64 -> N=256 expansion convolutions ran at
+// 2.3 TB/s, LSU-wavefront-bound).  Instead the 32 x 64-byte chunk is transposed through shared memory: global
+// accesses are issued with 4 lanes per row (64 contiguous bytes, 8 rows per instruction), the row-per-thread
+// accesses go to shared memory.  Unit (row, q) lives at row*4 + (q ^ ((row >> 1) & 3)): conflict-free both ways.
+__device__ __forceinline__ int conv_unit(int row, int q) { return row * 4 + (q ^ ((row >> 1) & 3)); }
+
+__device__ __forceinline__ void conv_residual_fetch(const GemmArgs &g, int64_t row0, int64_t col0, int lane, uint4 (&r)[4]) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int64_t row = row0 + it * 8 + (lane >> 2);
+        r[it] = row < g.M ? __ldg(reinterpret_cast<const uint4 *>(g.residual + row * g.ldc + col0) + (lane & 3))
+                          : make_uint4(0, 0, 0, 0);
+    }
+}
+
+__device__ __forceinline__ void conv_epilogue_chunk(const GemmArgs &g, int64_t row0, int64_t col0, int lane,
+                                                    const uint32_t (&acc)[32], const uint4 (&res)[4], uint4 *stage_in,
+                                                    uint4 *stage_out) {
+    float v[32];
+    const float4 *b4 = reinterpret_cast<const float4 *>(g.bias + col0);   // same address in every lane: one broadcast
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const float4 b = __ldg(b4 + q);
+        v[q * 4 + 0] = __uint_as_float(acc[q * 4 + 0]) + b.x; v[q * 4 + 1] = __uint_as_float(acc[q * 4 + 1]) + b.y;
+        v[q * 4 + 2] = __uint_as_float(acc[q * 4 + 2]) + b.z; v[q * 4 + 3] = __uint_as_float(acc[q * 4 + 3]) + b.w;
+    }
+    if (g.residual) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) stage_in[conv_unit(it * 8 + (lane >> 2), lane & 3)] = res[it];
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint4 r = stage_in[conv_unit(lane, q)];
+            const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                v[q * 8 + 2 * t] += __uint_as_float(w[t] << 16);
+                v[q * 8 + 2 * t + 1] += __uint_as_float(w[t] & 0xFFFF0000u);
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint32_t w[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            float lo = v[q * 8 + 2 * t], hi = v[q * 8 + 2 * t + 1];
+            if (g.relu) { lo = fmaxf(lo, 0.0f); hi = fmaxf(hi, 0.0f); }
+            const __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+            w[t] = *reinterpret_cast<const uint32_t *>(&p);
+        }
+        stage_out[conv_unit(lane, q)] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int r = it * 8 + (lane >> 2);
+        const int64_t row = row0 + r;
+        if (row < g.M) reinterpret_cast<uint4 *>(g.out_bf16 + row * g.ldc + col0)[lane & 3] = stage_out[conv_unit(r, lane & 3)];
+    }
+    __syncwarp();   // both buffers are free again
 }
 
 template <int EPI, int BN>
@@ -348,14 +381,33 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
             int64_t best_col = -1;
             mbar_wait(&sm.tmem_full[acc], acc_phase);
             tcgen05_fence_after();
+            if (EPI == EPI_CONV) {
+                // N is a multiple of 32 (checked on the host), so a chunk is all-or-nothing.  The residual of chunk
+                // c+1 is requested before chunk c is processed, so its HBM latency hides behind the TMEM read,
+                // the arithmetic and the stores of chunk c.
+                const int64_t row0 = m_blk * BM + quad * 32, colb = n_blk * BN;
+                const int chunks = (int)((g.N - colb < BN ? g.N - colb : BN) / 32);
+                uint4 res[4] = {}, res_next[4] = {};
+                if (g.residual && chunks > 0) conv_residual_fetch(g, row0, colb, lane, res);
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                const int64_t col0 = n_blk * BN + c * 32;
-                if (col0 >= g.N) break;
-                const int valid = (int)(g.N - col0 < 32 ? g.N - col0 : 32);
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + c * 32, v);
-                epilogue_chunk<EPI>(g, best, best_col, row, col0, valid, v, lane);
+                for (int c = 0; c < chunks; ++c) {
+                    if (g.residual && c + 1 < chunks) conv_residual_fetch(g, row0, colb + (c + 1) * 32, lane, res_next);
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + c * 32, v);
+                    conv_epilogue_chunk(g, row0, colb + c * 32, lane, v, res, sm.stage_in[quad], sm.stage_out[quad]);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) res[i] = res_next[i];
+                }
+            } else {
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    const int64_t col0 = n_blk * BN + c * 32;
+                    if (col0 >= g.N) break;
+                    const int valid = (int)(g.N - col0 < 32 ? g.N - col0 : 32);
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + c * 32, v);
+                    epilogue_chunk<EPI>(g, best, best_col, row, col0, valid, v, lane);
+                }
             }
             tcgen05_fence_before();
             __syncwarp();

@@ -55,10 +55,11 @@ struct RowTopK {
     }
     // After every block went through add_block (block maxima in bm[b*stride]): finish the row.
     // `row` may be any 16-byte aligned pointer to the lr columns (global memory on the device: the
-    // K hot blocks are L2 hits).  `stash`: 16 floats of per-thread scratch.  Returns false on overflow.
-    __host__ __device__ __forceinline__ bool finish(const float *row, int lr, const float *bm, float *cand_val,
-                                                    int *cand_col, int stride, float *stash, float (&val)[K],
-                                                    int (&col)[K]) const {
+    // K hot blocks are L2 hits).  `stash`: 16 floats of per-thread scratch; candidate j lives at
+    // cand_val[j*cstride] / cand_col[j*cstride].  Returns false on overflow.
+    __host__ __device__ __forceinline__ bool finish(const float *row, int lr, const float *bm, int stride,
+                                                    float *cand_val, int *cand_col, int cstride, float *stash,
+                                                    float (&val)[K], int (&col)[K]) const {
         const float4 *row4 = reinterpret_cast<const float4 *>(row);
         float4 *stash4 = reinterpret_cast<float4 *>(stash);
         const int n_chunks = lr >> 2;
@@ -102,8 +103,8 @@ struct RowTopK {
 #endif
                 hits &= hits - 1;
                 if (n_cand < kMaxCand) {
-                    cand_val[n_cand * stride] = stash[k];
-                    cand_col[n_cand * stride] = c0 * 4 + k;
+                    cand_val[n_cand * cstride] = stash[k];
+                    cand_col[n_cand * cstride] = c0 * 4 + k;
                     ++n_cand;
                 } else {
                     overflow = true;
@@ -113,8 +114,8 @@ struct RowTopK {
 #pragma unroll
         for (int i = 0; i < K; ++i) { val[i] = -INFINITY; col[i] = 0x7fffffff; }
         for (int j = 0; j < n_cand; ++j) {  // candidates arrive in ascending column order
-            float x = cand_val[j * stride];
-            int xc = cand_col[j * stride];
+            float x = cand_val[j * cstride];
+            int xc = cand_col[j * cstride];
             bool placed = false;
 #pragma unroll
             for (int i = 0; i < K; ++i) {
@@ -151,7 +152,7 @@ __host__ __device__ __forceinline__ bool select_row(const float *row, int lr, fl
         bm[b * stride] = sel.add_block(chunk, left < 4 ? left : 4);
     }
     alignas(16) float stash[16];
-    return sel.finish(row, lr, bm, cand_val, cand_col, stride, stash, val, col);
+    return sel.finish(row, lr, bm, stride, cand_val, cand_col, stride, stash, val, col);
 }
 
 }  // namespace vsc

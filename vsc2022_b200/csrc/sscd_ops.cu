@@ -15,53 +15,81 @@ namespace {
 // mode 0: uint8 NHWC pixels, normalised here ((x/255 - mean)/std, inference_impl.py:39-69); padding is zero in
 //         NORMALISED space, exactly like torchvision's Normalize followed by the conv's zero padding.
 // mode 1: float32 NCHW tensor that is already normalised (what the reference model receives).
-__global__ void __launch_bounds__(256) im2col_stem_kernel(const void *__restrict__ in, int mode, int n, int h, int w,
-                                                          int ho, int wo, __nv_bfloat16 *__restrict__ out) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per (pixel, ky, kx-group)
-    const long long total = (long long)n * ho * wo * 64;                     // 64 slots of 3 values = 192
-    if (idx >= total) return;
-    const int slot = (int)(idx & 63);
-    const long long pix = idx >> 6;
-    const int ox = (int)(pix % wo), oy = (int)((pix / wo) % ho), img = (int)(pix / ((long long)wo * ho));
-    __nv_bfloat16 v[3] = {__float2bfloat16(0.f), __float2bfloat16(0.f), __float2bfloat16(0.f)};
-    if (slot < 49) {
-        const int ky = slot / 7, kx = slot - ky * 7;
-        const int iy = oy * 2 - 3 + ky, ix = ox * 2 - 3 + kx;
-        if (iy >= 0 && iy < h && ix >= 0 && ix < w) {
-            const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+// One thread produces 16 bytes (8 consecutive K indices) of one panel row: grid.x = image row (img*ho + oy),
+// grid.y covers (ox, 24 uint4 per pixel), so the only runtime division is img = row / ho.  For uint8 input the
+// normalisation is a 3 x 256 bf16 table in shared memory built with the reference formula (two IEEE divisions per
+// entry instead of per pixel tap); the 21 taps of one (pixel, ky) are 21 contiguous input bytes.
+constexpr int kStemUnits = 24;   // 192 bf16 = 24 x 16 bytes per panel row
+template <int MODE>
+__global__ void __launch_bounds__(256) im2col_stem_kernel(const void *__restrict__ in, int n, int h, int w, int ho,
+                                                          int wo, uint4 *__restrict__ out) {
+    __shared__ uint16_t lut[3][256];
+    if (MODE == 0) {
+        const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+        for (int e = threadIdx.x; e < 768; e += blockDim.x) {
+            const int c = e >> 8, b = e & 255;
+            const __nv_bfloat16 v = __float2bfloat16_rn(((float)b / 255.0f - mean[c]) / stdv[c]);
+            lut[c][b] = *reinterpret_cast<const uint16_t *>(&v);
+        }
+        __syncthreads();
+    }
+    const int row = blockIdx.x;
+    const int img = row / ho, oy = row - img * ho;
+    const int t = blockIdx.y * blockDim.x + threadIdx.x;
+    const int ox = t / kStemUnits, j = t - ox * kStemUnits;
+    if (ox >= wo) return;
+    int ky = (j * 8) / 21, r = j * 8 - ky * 21;   // K index k = ky*21 + r, r = kx*3 + c
+    uint16_t v[8];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                float x;
-                if (mode == 0) {
-                    const uint8_t *p = static_cast<const uint8_t *>(in);
-                    x = ((float)p[(((long long)img * h + iy) * w + ix) * 3 + c] / 255.0f - mean[c]) / stdv[c];
-                } else {
-                    const float *p = static_cast<const float *>(in);
-                    x = p[(((long long)img * 3 + c) * h + iy) * w + ix];
-                }
-                v[c] = __float2bfloat16_rn(x);
+    for (int u = 0; u < 8; ++u) {
+        uint16_t x = 0;
+        const int kx = r / 3, c = r - kx * 3;
+        const int iy = oy * 2 - 3 + ky, ix = ox * 2 - 3 + kx;
+        if (ky < 7 && iy >= 0 && iy < h && ix >= 0 && ix < w) {
+            if (MODE == 0) {
+                const uint8_t *p = static_cast<const uint8_t *>(in);
+                x = lut[c][p[(((size_t)img * h + iy) * w + ix) * 3 + c]];
+            } else {
+                const float *p = static_cast<const float *>(in);
+                const __nv_bfloat16 b = __float2bfloat16_rn(p[(((size_t)img * 3 + c) * h + iy) * w + ix]);
+                x = *reinterpret_cast<const uint16_t *>(&b);
             }
         }
+        v[u] = x;
+        if (++r == 21) { r = 0; ++ky; }
     }
-    __nv_bfloat16 *o = out + pix * 192 + slot * 3;
-    o[0] = v[0]; o[1] = v[1]; o[2] = v[2];
+    out[((size_t)row * wo + ox) * kStemUnits + j] =
+        make_uint4(v[0] | ((uint32_t)v[1] << 16), v[2] | ((uint32_t)v[3] << 16), v[4] | ((uint32_t)v[5] << 16),
+                   v[6] | ((uint32_t)v[7] << 16));
 }
 
-// ---- 3x3 pad 1, stride s: panel [n*ho*wo][9*c], K index = (ky*3 + kx)*c + ch.  One thread moves 8 channels (16 B).
+// ---- 3x3 pad 1, stride s: panel [n*ho*wo][9*c], K index = (ky*3 + kx)*c + ch.  One thread moves 8 channels (16 B)
+// of all nine taps of one output pixel: the pixel is decoded once (32-bit arithmetic), the nine loads are issued
+// before the nine stores, and consecutive threads cover consecutive channels so every access is a full 16-byte
+// piece of a contiguous c*2-byte run.
 __global__ void __launch_bounds__(256) im2col3x3_kernel(const uint4 *__restrict__ in, int n, int h, int w, int c8,
-                                                        int stride, int ho, int wo, uint4 *__restrict__ out) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)n * ho * wo * 9 * c8;
+                                                        int stride, int ho, int wo, uint32_t total,
+                                                        uint4 *__restrict__ out) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;   // (pixel, channel group)
     if (idx >= total) return;
-    const int ch = (int)(idx % c8);
-    const int tap = (int)((idx / c8) % 9);
-    const long long pix = idx / ((long long)c8 * 9);
-    const int ox = (int)(pix % wo), oy = (int)((pix / wo) % ho), img = (int)(pix / ((long long)wo * ho));
-    const int ky = tap / 3, kx = tap - ky * 3;
-    const int iy = oy * stride - 1 + ky, ix = ox * stride - 1 + kx;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (iy >= 0 && iy < h && ix >= 0 && ix < w) v = in[(((long long)img * h + iy) * w + ix) * c8 + ch];
-    out[idx] = v;
+    const uint32_t pix = idx / (uint32_t)c8, ch = idx - pix * (uint32_t)c8;
+    const uint32_t t = pix / (uint32_t)wo;
+    const int ox = (int)(pix - t * (uint32_t)wo);
+    const int img = (int)(t / (uint32_t)ho), oy = (int)(t - (uint32_t)img * (uint32_t)ho);
+    const uint4 *src = in + ((size_t)img * h * w) * c8 + ch;
+    uint4 v[9];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const int iy = oy * stride - 1 + ky;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int ix = ox * stride - 1 + kx;
+            v[ky * 3 + kx] = (iy >= 0 && iy < h && ix >= 0 && ix < w) ? src[((size_t)iy * w + ix) * c8] : make_uint4(0, 0, 0, 0);
+        }
+    }
+    uint4 *dst = out + (size_t)pix * 9 * c8 + ch;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) dst[(size_t)tap * c8] = v[tap];
 }
 
 // ---- every second pixel (input of the stride-2 1x1 downsample convolution)
@@ -130,8 +158,13 @@ extern "C" int vsc_im2col_stem(const void *d_in, int32_t mode, int32_t n, int32_
                                vsc_stream_t stream) {
     const int ho = (h + 6 - 7) / 2 + 1, wo = (w + 6 - 7) / 2 + 1;
     if (n <= 0) return VSC_OK;
-    im2col_stem_kernel<<<blocks((long long)n * ho * wo * 64), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        d_in, mode, n, h, w, ho, wo, static_cast<__nv_bfloat16 *>(d_out));
+    if (mode != 0 && mode != 1) { vsc::set_error("vsc_im2col_stem: mode must be 0 (uint8 NHWC) or 1 (float32 NCHW)"); return VSC_ERR_INVALID; }
+    const dim3 grid((unsigned)((long long)n * ho), (unsigned)((wo * kStemUnits + 255) / 256));
+    if (grid.y > 65535u) { vsc::set_error("vsc_im2col_stem: frame width %d too large", w); return VSC_ERR_CAPACITY; }
+    if (mode == 0)
+        im2col_stem_kernel<0><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_in, n, h, w, ho, wo, static_cast<uint4 *>(d_out));
+    else
+        im2col_stem_kernel<1><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_in, n, h, w, ho, wo, static_cast<uint4 *>(d_out));
     VSC_CUDA_CHECK(cudaGetLastError());
     vsc::count_launch();
     return VSC_OK;
@@ -141,8 +174,10 @@ extern "C" int vsc_im2col3x3(const void *d_in, int32_t n, int32_t h, int32_t w, 
     if (c % 8 != 0 || (stride != 1 && stride != 2)) { vsc::set_error("vsc_im2col3x3: c %% 8 == 0 and stride in {1,2}"); return VSC_ERR_INVALID; }
     const int ho = (h + 2 - 3) / stride + 1, wo = (w + 2 - 3) / stride + 1;
     if (n <= 0) return VSC_OK;
-    im2col3x3_kernel<<<blocks((long long)n * ho * wo * 9 * (c / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const uint4 *>(d_in), n, h, w, c / 8, stride, ho, wo, static_cast<uint4 *>(d_out));
+    const long long total = (long long)n * ho * wo * (c / 8);
+    if (total >= (1ll << 31)) { vsc::set_error("vsc_im2col3x3: %lld work items exceed 2^31; use a smaller batch", total); return VSC_ERR_CAPACITY; }
+    im2col3x3_kernel<<<blocks(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint4 *>(d_in), n, h, w, c / 8, stride, ho, wo, (uint32_t)total, static_cast<uint4 *>(d_out));
     VSC_CUDA_CHECK(cudaGetLastError());
     vsc::count_launch();
     return VSC_OK;

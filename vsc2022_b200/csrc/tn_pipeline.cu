@@ -40,9 +40,8 @@ struct Workspace {
     uint16_t *ref_of;   // [P][N] reference frame of node
     void *rec;          // [P][N] NodeRec: {predecessor mask, zeroed-edge mask, similarity, distance}
     uint16_t *gen;      // [P][N] Kahn generation
-    uint16_t *chain;    // [P][max_lq] nodes of the chain being scored
     int rec_bytes, sim_off;  // record size and byte offset of the similarity inside it
-    uint8_t *skip;      // [P] 1 = handed to the general kernel
+    int32_t *skip;      // [P] 1 = handed to the general kernel
     int32_t *cursor;    // T1 pair counter
 };
 
@@ -52,126 +51,122 @@ struct alignas(16) NodeRec {
     float sim, dist;
 };
 static_assert(sizeof(NodeRec<uint32_t>) == 16 && sizeof(NodeRec<uint64_t>) == 32, "record layout");
+// ref_of entry: reference frame (< 2^15: the pipeline takes rows up to 512 columns) | flag "similarity >= min_sim"
+// (constraint C4, evaluated once by T1 where the similarity is in a register)
+constexpr uint16_t kRefMask = 0x7FFF, kSimOk = 0x8000;
 
 // ------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-}
-// TMA bulk copy global -> shared; completion is signalled on `bar` (complete_tx::bytes).
-__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
 // Ampere-style 16-byte async copy global -> shared (bypasses L1); one commit group per panel.
 template <int OFFSET>
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0+%2], [%1], 16;" ::"r"(dst_smem), "l"(src), "n"(OFFSET) : "memory");
-}
-__device__ __forceinline__ void cp_async16_to(void *dst, const void *src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // ------------------------------------------------------------------ T1: row top-K
-// A warp owns 32 rows (one per lane in the compute phase) and streams them through shared memory
+// A warp owns a TILE of 32 rows (one per lane in the compute phase) and streams it through shared memory
 // in 64-column panels.  The panel fill is warp-cooperative: 16 lanes x 16 B cover one 256-byte row
 // segment, so every cp.async instruction moves two fully coalesced segments into a padded panel
 // (pitch 68 words -> conflict-free LDS.128 for the thread-per-row reads); kStages panels per warp
 // are in flight.  (Measured: one cp.async.bulk per lane and panel -- 12.8 M 256-byte TMA bulk
 // copies per batch -- was TMA-issue-bound at ~27 cycles/op/SM, 2.4 TB/s; see profiles/.)
 // Pass 1 (block maxima + K best maxima) runs on the panels; at the end of a row the K hot blocks
-// are re-read straight from global memory (L2 hits) for the exact selection.
-constexpr int kT1Warps = 8;
-constexpr int kT1Threads = kT1Warps * 32;
+// are re-read straight from global memory (L2 hits) for the exact selection, whose scratch (16-float
+// stash + candidate list) is the lane's own row of the panel it has just consumed.
+// Shared memory per warp = kStages panels + block maxima for ceil(max_lr/16) blocks, so 11 warps fit one SM
+// at 300 columns (8 with the first layout): the kernel is bound by warps in flight, not by instruction issue.
+// Work unit = tile: tile t covers rows [32*(t % tpp), +32) of pair t / tpp (tpp = ceil(max_lq/32)); tiles are
+// claimed with one atomic each, TWO tiles ahead, so neither the atomic nor the pair-descriptor loads
+// sit on a warp's critical path.
+constexpr int kT1MaxWarps = 16;
+constexpr int kT1MaxThreads = kT1MaxWarps * 32;
 constexpr int kTileRows = 32;
 constexpr int kPanelCols = 64;
 constexpr int kPanelPitch = 68;
 constexpr int kStages = 2;
 constexpr int kPanelBytes = kTileRows * kPanelPitch * 4;
-constexpr int kStashPitch = 20;
+constexpr int kScratchStash = 0, kScratchVal = 16, kScratchCol = 32;   // word offsets inside the lane's panel row
+static_assert(kScratchCol + vsc::kMaxCand <= kPanelCols, "selection scratch must fit one panel row");
 
 struct Cursor {   // one panel of work
     int pair, row0, col0, lq, lr;
     const float *base;
 };
 
-struct alignas(128) T1Smem {   // per warp
-    float panel[kStages][kTileRows * kPanelPitch];
-    float bm[vsc::kMaxRowBlocks * 32];
-    float cand_val[vsc::kMaxCand * 32];
-    int cand_col[vsc::kMaxCand * 32];
-    float stash[32 * kStashPitch];   // 16 floats per lane, pitch 20 words: conflict-free STS.128
-    Cursor ring[kStages];
-};
+__host__ __device__ inline size_t t1_warp_bytes(int max_lr) {
+    const size_t blocks = (size_t)(max_lr + vsc::kBlockCols - 1) / vsc::kBlockCols;
+    const size_t b = (size_t)kStages * kPanelBytes + blocks * 32 * 4 + kStages * sizeof(Cursor);
+    return (b + 127) / 128 * 128;
+}
 
 struct T1Args {
     Batch b;
     Workspace w;
     WorkList out;
+    int tiles_per_pair, n_tiles, warp_bytes;
 };
 
-// Claim the next pair this warp can process; pairs it cannot take go to the general kernel.
-__device__ inline bool claim_pair(const T1Args &a, int lane, Cursor &c) {
-    for (;;) {
-        int p = 0;
-        if (lane == 0) p = atomicAdd(a.w.cursor, 1);
-        p = __shfl_sync(kFullMask, p, 0);
-        if (p >= a.b.n_pairs) return false;
-        const int lq = a.b.lq[p], lr = a.b.lr[p];
-        const int64_t off = a.b.off[p];
-        const bool ok = (lr & 3) == 0 && (off & 3) == 0 && lr >= a.b.topk && lr <= a.b.max_lr &&
-                        lr <= vsc::kBlockCols * vsc::kMaxRowBlocks && lq <= a.b.max_lq;
-        if (!ok) {
-            if (lane == 0) {
-                a.w.skip[p] = 1;
-                a.out.list[atomicAdd(a.out.count, 1)] = p;
-            }
-            continue;
-        }
-        if (lq <= 0) continue;  // nothing to read; T2 reports zero boxes
-        c.pair = p; c.row0 = 0; c.col0 = 0; c.lq = lq; c.lr = lr; c.base = a.b.sims + off;
-        return true;
-    }
-}
-
 template <int K>
-__global__ void __launch_bounds__(kT1Threads, 1) tn_topk_kernel(const T1Args a) {
+__global__ void __launch_bounds__(kT1MaxThreads, 1) tn_topk_kernel(const T1Args a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    T1Smem &sm = reinterpret_cast<T1Smem *>(smem_raw)[warp];
+    unsigned char *mine = smem_raw + (size_t)warp * a.warp_bytes;
+    float *panels = reinterpret_cast<float *>(mine);                       // [kStages][kTileRows * kPanelPitch]
+    float *bm = panels + kStages * kTileRows * kPanelPitch;                // [blocks][32]
+    Cursor *ring = reinterpret_cast<Cursor *>(mine + a.warp_bytes) - kStages;
 
-    Cursor ic;                       // next panel to request
-    bool more = claim_pair(a, lane, ic);
+    // ---- tile stream: `ic` = panel to request next, `nx` = descriptor of the following tile (loads in flight),
+    // `t_req` (lane 0) = id of the tile after that (atomic in flight)
+    Cursor ic, nx;
+    int t_req = 0;
+    bool more = true;
+    auto describe = [&](int t, Cursor &c) {   // issues the loads; nothing here waits for them
+        c.pair = -1; c.row0 = 0; c.col0 = 0; c.lq = 0; c.lr = 0; c.base = nullptr;
+        if (t < a.n_tiles) {
+            const int p = t / a.tiles_per_pair;
+            c.pair = p; c.row0 = (t - p * a.tiles_per_pair) * kTileRows;
+            c.lq = a.b.lq[p]; c.lr = a.b.lr[p]; c.base = a.b.sims + a.b.off[p];
+        }
+    };
+    auto advance = [&]() {   // ic <- next tile this warp can process; pairs it cannot take go to the general kernel
+        for (;;) {
+            ic = nx;
+            const int t = __shfl_sync(kFullMask, t_req, 0);
+            if (lane == 0) t_req = atomicAdd(a.w.cursor, 1);
+            describe(t, nx);
+            if (ic.pair < 0) { more = false; return; }   // tile ids only grow: nothing is left
+            const bool ok = (ic.lr & 3) == 0 && (reinterpret_cast<uintptr_t>(ic.base) & 15u) == 0 && ic.lr >= a.b.topk &&
+                            ic.lr <= a.b.max_lr && ic.lr <= vsc::kBlockCols * vsc::kMaxRowBlocks && ic.lq <= a.b.max_lq;
+            if (!ok) {
+                if (lane == 0 && ic.row0 == 0 && atomicExch(&a.w.skip[ic.pair], 1) == 0)
+                    a.out.list[atomicAdd(a.out.count, 1)] = ic.pair;
+                continue;
+            }
+            if (ic.row0 >= ic.lq) continue;   // ragged batch: this tile slot is empty (lq <= 0: T2 reports zero boxes)
+            return;
+        }
+    };
+    {
+        int t0 = 0;
+        if (lane == 0) { t0 = atomicAdd(a.w.cursor, 1); t_req = atomicAdd(a.w.cursor, 1); }
+        t0 = __shfl_sync(kFullMask, t0, 0);
+        describe(t0, nx);
+        advance();
+    }
+
     const int half = lane >> 4, ch = (lane & 15) * 4;  // fill role: row parity, column offset
-    const uint32_t panel_s = smem_u32(&sm.panel[0][0]) + (uint32_t)(half * kPanelPitch + ch) * 4u;
+    const uint32_t panel_s = smem_u32(panels) + (uint32_t)(half * kPanelPitch + ch) * 4u;
     auto issue = [&](int stage) {    // request panel `ic` into `stage`, then step `ic`
-        if (lane == 0) sm.ring[stage] = ic;
+        if (lane == 0) ring[stage] = ic;
         if (ic.col0 + ch < ic.lr) {
             const float *src = ic.base + (size_t)(ic.row0 + half) * ic.lr + ic.col0 + ch;
             const uint32_t dst = panel_s + (uint32_t)stage * kPanelBytes;
-            const int n = (ic.lq - ic.row0 - half + 1) >> 1;  // rows of this lane's parity left in the pair
+            const int n = (min(ic.lq - ic.row0, kTileRows) - half + 1) >> 1;  // rows of this lane's parity in the tile
             const size_t stride = (size_t)2 * ic.lr;
 #define VSC_COPY_ROW(I)                                                        \
             if ((I) < n) cp_async16<(I) * 2 * kPanelPitch * 4>(dst, src);        \
@@ -184,30 +179,27 @@ __global__ void __launch_bounds__(kT1Threads, 1) tn_topk_kernel(const T1Args a) 
         }
         cp_async_commit();
         ic.col0 += kPanelCols;
-        if (ic.col0 >= ic.lr) {
-            ic.col0 = 0; ic.row0 += kTileRows;
-            if (ic.row0 >= ic.lq) more = claim_pair(a, lane, ic);
-        }
+        if (ic.col0 >= ic.lr) advance();
     };
 
     unsigned issued = 0, consumed = 0;
     for (; issued < kStages - 1 && more; ++issued) issue(issued);
     vsc::RowTopK<K> sel;
     sel.reset();
-    bool pair_overflow = false;
     while (consumed < issued) {
         if (more) { issue(issued % kStages); ++issued; }
         else cp_async_commit();      // empty group keeps the wait depth constant at the tail
         const int stage = consumed % kStages;
         cp_async_wait<kStages - 1>();
         __syncwarp();                // every lane's copies for this panel have landed
-        const Cursor c = sm.ring[stage];
+        const Cursor c = ring[stage];
         const int row = c.row0 + lane;
         const bool last_panel = c.col0 + kPanelCols >= c.lr;
         bool ok = true;
         if (row < c.lq) {
             if (c.col0 == 0) sel.reset();
-            const float4 *src = reinterpret_cast<const float4 *>(&sm.panel[stage][lane * kPanelPitch]);
+            float *myrow = panels + stage * (kTileRows * kPanelPitch) + lane * kPanelPitch;
+            const float4 *src = reinterpret_cast<const float4 *>(myrow);
             const int chunks = (min(kPanelCols, c.lr - c.col0)) >> 2;
 #pragma unroll
             for (int blk = 0; blk < kPanelCols / vsc::kBlockCols; ++blk) {
@@ -217,17 +209,18 @@ __global__ void __launch_bounds__(kT1Threads, 1) tn_topk_kernel(const T1Args a) 
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     if (k < left) v[k] = src[blk * 4 + k];
-                sm.bm[(c.col0 / vsc::kBlockCols + blk) * 32 + lane] = sel.add_block(v, left < 4 ? left : 4);
+                bm[(c.col0 / vsc::kBlockCols + blk) * 32 + lane] = sel.add_block(v, left < 4 ? left : 4);
             }
             if (last_panel) {
                 float val[K]; int col[K];
-                ok = sel.finish(c.base + (size_t)row * c.lr, c.lr, sm.bm + lane, sm.cand_val + lane,
-                                sm.cand_col + lane, 32, sm.stash + lane * kStashPitch, val, col);
+                // the lane's row of this panel is consumed: it becomes the selection scratch
+                ok = sel.finish(c.base + (size_t)row * c.lr, c.lr, bm + lane, 32, myrow + kScratchVal,
+                                reinterpret_cast<int *>(myrow + kScratchCol), 1, myrow + kScratchStash, val, col);
                 const size_t node = (size_t)c.pair * a.b.max_nodes + (size_t)row * K;
                 unsigned char *rec = static_cast<unsigned char *>(a.w.rec) + node * a.w.rec_bytes;
 #pragma unroll
                 for (int i = 0; i < K; ++i) {
-                    a.w.ref_of[node + i] = (uint16_t)col[i];
+                    a.w.ref_of[node + i] = (uint16_t)col[i] | (val[i] >= a.b.min_sim ? kSimOk : (uint16_t)0);
                     // whole record in 16-byte stores: masks and distance start at zero
                     if (a.w.rec_bytes == 16) {
                         *reinterpret_cast<float4 *>(rec + i * 16) = make_float4(0.f, 0.f, val[i], 0.f);
@@ -238,27 +231,28 @@ __global__ void __launch_bounds__(kT1Threads, 1) tn_topk_kernel(const T1Args a) 
                 }
             }
         }
-        if (last_panel) {
-            pair_overflow |= __any_sync(kFullMask, !ok);
-            if (c.row0 + kTileRows >= c.lq) {  // last tile of the pair
-                if (pair_overflow && lane == 0) {
-                    a.w.skip[c.pair] = 1;
-                    a.out.list[atomicAdd(a.out.count, 1)] = c.pair;
-                }
-                pair_overflow = false;
-            }
+        if (last_panel && __any_sync(kFullMask, !ok)) {   // a row with too many tied candidates: general kernel
+            if (lane == 0 && atomicExch(&a.w.skip[c.pair], 1) == 0)
+                a.out.list[atomicAdd(a.out.count, 1)] = c.pair;
         }
         __syncwarp();  // every lane is done with `stage` before it is refilled
         ++consumed;
     }
 }
 
+// ------------------------------------------------------------------ predecessor-mask layout
+// Edge (q_src, a) -> (q_dst, b) is bit  slot = grp * GS + a  of pred[v_dst], grp = step-1-(q_dst-q_src): ascending
+// slot order == networkx predecessor insertion order (farthest source row first, then rank; oracle/tn_fast.c).
+// GS (group stride) is 8 on the fast variant (32-bit masks, (step-1)*8 <= 32), which turns the slot -> distance-
+// window index into one add and one mask; every other parameter set uses 64-bit masks with GS = K.
+
 // ------------------------------------------------------------------ T1e: edges
 // One thread per source row.  Per destination row the K*K rank combinations are screened for
 // constraint C2 with two instructions each into a hit mask; only the hits (about one per three
 // row pairs) go through C3 (no ref already linked from this row inside [r_src, r_dst]), C4
-// (destination similarity >= min_sim) and the atomic OR into the destination's predecessor mask.
-template <typename MaskT, int K>
+// (destination similarity >= min_sim: a flag T1 stored next to the reference index, so this kernel never
+// touches the node records except for the atomic OR) and the atomic OR into the destination's predecessor mask.
+template <typename MaskT, int K, int GS>
 __global__ void __launch_bounds__(256) tn_edges_kernel(const Batch b, const Workspace w) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int pair = (int)(idx / b.max_lq);
@@ -273,30 +267,38 @@ __global__ void __launch_bounds__(256) tn_edges_kernel(const Batch b, const Work
 
     int r_src[K]; uint32_t window[K];  // window[a]: refs linked from this row, relative to r_src[a]
 #pragma unroll
-    for (int x = 0; x < K; ++x) { r_src[x] = ref_of[q_src * K + x]; window[x] = 0; }
+    for (int x = 0; x < K; ++x) { r_src[x] = ref_of[q_src * K + x] & kRefMask; window[x] = 0; }
     const int q_end = min(lq, q_src + step);
     for (int q_dst = q_src + 1; q_dst < q_end; ++q_dst) {
-        const uint16_t *r_dst = ref_of + q_dst * K;
-        uint32_t hits[K];  // hits[x]: destination ranks b with 0 < r_dst[b] - r_src[x] < step (C2)
+        int r_dst[K];
+        uint32_t sim_ok = 0;
+#pragma unroll
+        for (int bb = 0; bb < K; ++bb) {
+            const uint16_t e = ref_of[q_dst * K + bb];
+            r_dst[bb] = e & kRefMask;
+            sim_ok |= (e & kSimOk) ? 1u << bb : 0u;
+        }
+        uint32_t hits[K];  // hits[x]: destination ranks b with 0 < r_dst[b] - r_src[x] < step (C2) and C4
 #pragma unroll
         for (int x = 0; x < K; ++x) hits[x] = 0;
 #pragma unroll
         for (int bb = 0; bb < K; ++bb) {
-            const int rd = r_dst[bb];
 #pragma unroll
             for (int x = 0; x < K; ++x)
-                hits[x] |= ((unsigned)(rd - r_src[x] - 1) < (unsigned)(step - 1) ? 1u : 0u) << bb;
+                hits[x] |= ((unsigned)(r_dst[bb] - r_src[x] - 1) < (unsigned)(step - 1) ? 1u : 0u) << bb;
         }
         uint32_t accepted = 0;
-        const int slot0 = (step - 1 - (q_dst - q_src)) * K;
+        const int slot0 = (step - 1 - (q_dst - q_src)) * GS;
 #pragma unroll
         for (int x = 0; x < K; ++x) {
-            uint32_t h = hits[x];
+            uint32_t h = hits[x] & sim_ok;                               // C4
             while (h) {
                 const int bb = __ffs(h) - 1; h &= h - 1;
-                const int d = (int)r_dst[bb] - r_src[x];
+                int rd = r_dst[0];
+#pragma unroll
+                for (int i = 1; i < K; ++i) rd = bb == i ? r_dst[i] : rd;   // register select, no local memory
+                const int d = rd - r_src[x];
                 if (window[x] & ((2u << d) - 1u)) continue;              // C3
-                if (!(rec[q_dst * K + bb].sim >= b.min_sim)) continue;   // C4
                 accepted |= 1u << bb;
                 const MaskT bit = (MaskT)1 << (slot0 + x);
                 if (sizeof(MaskT) == 8)
@@ -307,7 +309,9 @@ __global__ void __launch_bounds__(256) tn_edges_kernel(const Batch b, const Work
         }
         while (accepted) {  // refs linked in this step constrain the later destination rows
             const int bb = __ffs(accepted) - 1; accepted &= accepted - 1;
-            const int rd = r_dst[bb];
+            int rd = r_dst[0];
+#pragma unroll
+            for (int i = 1; i < K; ++i) rd = bb == i ? r_dst[i] : rd;
 #pragma unroll
             for (int x = 0; x < K; ++x) {
                 const int d = rd - r_src[x];
@@ -317,29 +321,45 @@ __global__ void __launch_bounds__(256) tn_edges_kernel(const Batch b, const Work
     }
 }
 
-template <typename MaskT>
+template <typename MaskT, int GS8>
 void launch_edges(const Batch &b, const Workspace &w, int grid, cudaStream_t stream) {
     switch (b.topk) {
-        case 1: tn_edges_kernel<MaskT, 1><<<grid, 256, 0, stream>>>(b, w); break;
-        case 2: tn_edges_kernel<MaskT, 2><<<grid, 256, 0, stream>>>(b, w); break;
-        case 3: tn_edges_kernel<MaskT, 3><<<grid, 256, 0, stream>>>(b, w); break;
-        case 4: tn_edges_kernel<MaskT, 4><<<grid, 256, 0, stream>>>(b, w); break;
-        case 5: tn_edges_kernel<MaskT, 5><<<grid, 256, 0, stream>>>(b, w); break;
-        case 6: tn_edges_kernel<MaskT, 6><<<grid, 256, 0, stream>>>(b, w); break;
-        case 7: tn_edges_kernel<MaskT, 7><<<grid, 256, 0, stream>>>(b, w); break;
-        default: tn_edges_kernel<MaskT, 8><<<grid, 256, 0, stream>>>(b, w); break;
+        case 1: tn_edges_kernel<MaskT, 1, GS8 ? 8 : 1><<<grid, 256, 0, stream>>>(b, w); break;
+        case 2: tn_edges_kernel<MaskT, 2, GS8 ? 8 : 2><<<grid, 256, 0, stream>>>(b, w); break;
+        case 3: tn_edges_kernel<MaskT, 3, GS8 ? 8 : 3><<<grid, 256, 0, stream>>>(b, w); break;
+        case 4: tn_edges_kernel<MaskT, 4, GS8 ? 8 : 4><<<grid, 256, 0, stream>>>(b, w); break;
+        case 5: tn_edges_kernel<MaskT, 5, GS8 ? 8 : 5><<<grid, 256, 0, stream>>>(b, w); break;
+        case 6: tn_edges_kernel<MaskT, 6, GS8 ? 8 : 6><<<grid, 256, 0, stream>>>(b, w); break;
+        case 7: tn_edges_kernel<MaskT, 7, GS8 ? 8 : 7><<<grid, 256, 0, stream>>>(b, w); break;
+        default: tn_edges_kernel<MaskT, 8, 8><<<grid, 256, 0, stream>>>(b, w); break;
     }
 }
 
 // ------------------------------------------------------------------ T2: longest-path sweeps
 // Four pairs per warp: an octet of lanes owns one pair, lane `sub` owns rank `sub` of the current
-// row layer.  Distances of the last D >= step-1 layers live in a shared-memory window, as do the
-// per-layer maxima, the best-predecessor slots and the current chain; the 16-byte node record
-// (masks, similarity, distance) is prefetched one layer ahead with a single 128-bit load.  The
-// grid is sized so that every pair of a batch is resident at once: the kernel is a chain of
-// dependent shared-memory operations, so throughput comes from pairs in flight, not from IPC.
+// row layer.  The kernel is one long dependent chain per pair (measured: 0.46 ms for a single pair,
+// ~9 cycles per instruction with the SM to itself), so everything here is about instructions on that
+// chain: (distance, Kahn generation) of the last D >= step layers sit interleaved in a shared-memory
+// window read with one 64-bit load per predecessor, the 16-byte node records are prefetched into
+// registers four layers ahead (loops unrolled by four so the rotation is free), and the chain of a
+// round is walked in shared memory by one lane, then zeroed / scored by all eight lanes of the octet.
+// The grid is sized so that every pair of a batch is resident at once.
+__device__ unsigned long long g_dp_counters[8];
+#ifdef VSC_TN_COUNTERS
+#define VSC_CLK_START() long long cyc__[8] = {}; long long t__ = clock64()
+#define VSC_CLK(i) do { const long long n__ = clock64(); cyc__[i] += n__ - t__; t__ = n__; } while (0)
+#define VSC_CLK_ADD(i, n) cyc__[i] += (n)
+#define VSC_CLK_FLUSH() do { if (lane == 0) { cyc__[7] = 1; for (int i__ = 0; i__ < 8; ++i__) atomicAdd(&g_dp_counters[i__], (unsigned long long)cyc__[i__]); } } while (0)
+#else
+#define VSC_CLK_START() do {} while (0)
+#define VSC_CLK(i) do {} while (0)
+#define VSC_CLK_ADD(i, n) do {} while (0)
+#define VSC_CLK_FLUSH() do {} while (0)
+#endif
+
 constexpr int kT2Warps = 2;  // 8 pairs per CTA: small CTAs pack the SMs so a whole batch is one wave
 constexpr int kT2Threads = kT2Warps * 32;
+constexpr int kAhead = 4;    // node-record prefetch distance in row layers
 
 // Octet reductions by xor-shuffle (distances 1, 2, 4 stay inside an aligned group of 8 lanes).
 // redux.sync with a per-octet mask compiles to a loop over the distinct masks and cost 38 % of
@@ -365,38 +385,56 @@ __host__ __device__ inline int window_depth(int step) {  // power of two >= step
     while (d < step) d <<= 1;  // > step-1, so the slot being written is never one being read
     return d;
 }
-constexpr int kRing = 4;  // row layers of node records in flight per octet (16-byte cp.async per lane and layer)
 
-__host__ __device__ inline size_t t2_pair_bytes(int max_nodes, int max_lq, int step, size_t rec_bytes = 16) {
+__host__ __device__ inline size_t t2_pair_bytes(int max_nodes, int max_lq, int step) {
     const size_t d = (size_t)window_depth(step);
-    size_t b = (size_t)kRing * 8 * rec_bytes;             // record ring
-    b += d * 8 * 4 + d * 8 * 2;                           // distance + generation windows
+    size_t b = d * 8 * 8;                                 // (distance, generation) window
     b += (size_t)max_lq * 4;                              // layer maxima
+    b += (size_t)max_lq * 2;                              // chain of the current round
     b += (size_t)max_nodes;                               // best-predecessor slots
     return (b + 15) / 16 * 16;
 }
 
+// Node records change while the kernel runs (distance, zeroed-edge mask) and the zeroed bits are set
+// with L2 atomics, so every record read goes to L2 (ld.global.cg), never through L1.
+template <typename Rec>
+__device__ __forceinline__ Rec load_rec(const Rec *p) {
+    Rec r;
+    const uint4 *s = reinterpret_cast<const uint4 *>(p);
+    uint4 *d = reinterpret_cast<uint4 *>(&r);
+    d[0] = __ldcg(s);
+    if (sizeof(Rec) == 32) d[1] = __ldcg(s + 1);
+    return r;
+}
+
 // One lane relaxes its own node against the distance window: FIRST maximal predecessor in
 // ascending slot order (networkx keeps the first maximum).
-template <typename MaskT, int K, bool FIRST>
+template <typename MaskT, int K, int GS, bool FIRST>
 __device__ __forceinline__ void relax_node(MaskT pm, MaskT zm, float w, int q, int step, int wmask,
-                                           const float *wdist, const uint16_t *wgen, float &best,
-                                           int &best_slot, int &gen) {
+                                           const float2 *win, float &best, int &best_slot, int &gen) {
     best = 0.0f; best_slot = -1; gen = 0;
+    const int base8 = (q - step + 1) * 8, wm8 = wmask * 8 + 7;
     while (pm) {
         const int sl = sizeof(MaskT) == 8 ? __ffsll((long long)pm) - 1 : __ffs((int)pm) - 1;
         pm &= pm - 1;
-        const int grp = sl / K;  // compile-time divisor
-        const int wi = ((q - (step - 1 - grp)) & wmask) * 8 + (sl - grp * K);
-        const float cand = wdist[wi] + (((zm >> sl) & 1) ? 0.0f : w);
+        int wi;
+        if (GS == 8) {
+            wi = (base8 + sl) & wm8;   // ((q - (step-1-grp)) & wmask) * 8 + rank with slot = grp*8 + rank
+        } else {
+            const int grp = sl / GS;   // compile-time divisor
+            wi = ((q - (step - 1 - grp)) & wmask) * 8 + (sl - grp * GS);
+        }
+        float cand; int pg = 0;
+        if (FIRST) { const float2 e = win[wi]; cand = e.x + w; pg = __float_as_int(e.y); }
+        else cand = win[wi].x + (((zm >> sl) & 1) ? 0.0f : w);
         if (best_slot < 0 || cand > best) { best = cand; best_slot = sl; }
-        if (FIRST) gen = max(gen, (int)wgen[wi] + 1);
+        if (FIRST) gen = max(gen, pg + 1);
     }
     if (best_slot >= 0 && !(best >= 0.0f)) { best = 0.0f; best_slot = -1; }  // networkx: negative best -> (0, v)
 }
 
-template <typename MaskT, int K>
-__global__ void __launch_bounds__(kT2Threads) tn_dp_kernel(const Batch b, const Workspace w, const WorkList out) {
+template <typename MaskT, int K, int GS>
+__global__ void __launch_bounds__(kT2Threads, 8) tn_dp_kernel(const Batch b, const Workspace w, const WorkList out) {
     // WARP-SYNCHRONOUS: the four octets of a warp run every loop together (trip count = the longest of the
     // four, shorter ones are predicated off) and all shuffles use the full mask, so the warp never splits into
     // four serially executed instruction streams.
@@ -410,19 +448,16 @@ __global__ void __launch_bounds__(kT2Threads) tn_dp_kernel(const Batch b, const 
     const int p = alive ? pair : 0;   // dead octets shadow pair 0 read-only and never store
 
     const int depth = window_depth(step), wmask = depth - 1;
-    unsigned char *mine = t2_smem + (size_t)((threadIdx.x >> 5) * 4 + oct) *
-                                        t2_pair_bytes(b.max_nodes, b.max_lq, step, sizeof(NodeRec<MaskT>));
-    NodeRec<MaskT> *ring = reinterpret_cast<NodeRec<MaskT> *>(mine);
-    float *wdist = reinterpret_cast<float *>(ring + kRing * 8);
-    uint32_t *lbest = reinterpret_cast<uint32_t *>(wdist + depth * 8);
-    uint16_t *wgen = reinterpret_cast<uint16_t *>(lbest + b.max_lq);
-    int8_t *slot = reinterpret_cast<int8_t *>(wgen + depth * 8);
-    uint16_t *chain = w.chain + (size_t)p * b.max_lq;   // global: only the chain walk touches it
+    unsigned char *mine = t2_smem + (size_t)((threadIdx.x >> 5) * 4 + oct) * t2_pair_bytes(b.max_nodes, b.max_lq, step);
+    float2 *win = reinterpret_cast<float2 *>(mine);                     // {distance, generation bits}
+    uint32_t *lbest = reinterpret_cast<uint32_t *>(win + depth * 8);    // per-layer maximum distance (float bits)
+    uint16_t *chain = reinterpret_cast<uint16_t *>(lbest + b.max_lq);   // nodes of the chain, end node first
+    int8_t *slot = reinterpret_cast<int8_t *>(chain + b.max_lq);        // best-predecessor slot per node
 
     const int lq = alive ? b.lq[p] : 0;
     const int lq_max = __reduce_max_sync(kFullMask, lq);
     const int box_cap = b.max_path + 1;
-    int32_t *boxes = b.boxes + (size_t)p * box_cap * 4;
+    int4 *boxes = reinterpret_cast<int4 *>(b.boxes) + (size_t)p * box_cap;
     const size_t nb = (size_t)p * b.max_nodes;
     using Rec = NodeRec<MaskT>;
     Rec *rec = static_cast<Rec *>(w.rec) + nb;
@@ -430,44 +465,43 @@ __global__ void __launch_bounds__(kT2Threads) tn_dp_kernel(const Batch b, const 
     uint16_t *gen = w.gen + nb;
     const bool ranked = sub < K;
 
-    for (int i = sub; i < depth * 8; i += 8) { wdist[i] = 0.0f; wgen[i] = 0; }
+    for (int i = sub; i < depth * 8; i += 8) win[i] = make_float2(0.0f, 0.0f);
     __syncwarp();
 
-    // Record ring: every rank lane keeps kRing of ITS node records in flight.
-    auto request = [&](int q, bool on) {  // one commit group per call, empty when there is nothing to load
-        if (ranked && on && q < lq) {
-            cp_async16_to(&ring[(q & (kRing - 1)) * 8 + sub], &rec[q * K + sub]);
-            if (sizeof(Rec) == 32)
-                cp_async16_to(reinterpret_cast<char *>(&ring[(q & (kRing - 1)) * 8 + sub]) + 16,
-                              reinterpret_cast<const char *>(&rec[q * K + sub]) + 16);
-        }
-        cp_async_commit();
-    };
-
+    VSC_CLK_START();
     // ---- first sweep: every layer
-    for (int i = 0; i < kRing; ++i) request(i, true);
-    for (int q = 0; q < lq_max; ++q) {
-        const bool on = q < lq;
-        const int v = q * K + sub;
-        cp_async_wait<kRing - 1>();  // this lane's record of layer q has landed (a lane only reads its own copy)
-        Rec cur = {};
-        if (ranked && on) cur = ring[(q & (kRing - 1)) * 8 + sub];
-        request(q + kRing, true);
-        float d = 0.0f; int sl = -1, g = 0;
-        if (ranked && on) {
-            relax_node<MaskT, K, true>(cur.pred, (MaskT)0, cur.sim, q, step, wmask, wdist, wgen, d, sl, g);
-            if (cur.pred) { rec[v].dist = d; gen[v] = (uint16_t)g; }  // nodes without predecessors stay (0, self, gen 0)
-            slot[v] = (int8_t)sl;
+    {
+        Rec pre[kAhead];
+#pragma unroll
+        for (int u = 0; u < kAhead; ++u) {
+            pre[u] = Rec{};
+            if (ranked && u < lq) pre[u] = load_rec(&rec[u * K + sub]);
         }
-        // window slot q & wmask held layer q-depth, which nobody reads any more
-        wdist[(q & wmask) * 8 + sub] = d;
-        wgen[(q & wmask) * 8 + sub] = (uint16_t)g;
-        const uint32_t lm = oct_max(__float_as_uint(d), kFullMask);  // dist >= +0: bits are ordered
-        if (sub == 0 && on) lbest[q] = lm;
-        __syncwarp();
+        for (int q0 = 0; q0 < lq_max; q0 += kAhead) {
+#pragma unroll
+            for (int u = 0; u < kAhead; ++u) {
+                const int q = q0 + u;
+                if (q >= lq_max) break;            // warp-uniform
+                const bool mine_on = ranked && q < lq;
+                const Rec cur = pre[u];
+                if (ranked && q + kAhead < lq) pre[u] = load_rec(&rec[(q + kAhead) * K + sub]);
+                const int v = q * K + sub;
+                float d = 0.0f; int sl = -1, g = 0;
+                if (mine_on) {
+                    relax_node<MaskT, K, GS, true>(cur.pred, (MaskT)0, cur.sim, q, step, wmask, win, d, sl, g);
+                    if (cur.pred) { rec[v].dist = d; gen[v] = (uint16_t)g; }  // nodes without predecessors stay (0, self, gen 0)
+                    slot[v] = (int8_t)sl;
+                }
+                // window slot q & wmask held layer q-depth, which nobody reads any more
+                win[(q & wmask) * 8 + sub] = make_float2(d, __int_as_float(g));
+                const uint32_t lm = oct_max(__float_as_uint(d), kFullMask);  // dist >= +0: bits are ordered
+                if (sub == 0 && q < lq) lbest[q] = lm;
+                __syncwarp();
+            }
+        }
     }
-    cp_async_wait<0>();
 
+    VSC_CLK(0);
     int n_boxes = 0;
     bool ambiguous = false;
     bool searching = alive;   // this octet still looks for chains
@@ -484,7 +518,7 @@ __global__ void __launch_bounds__(kT2Threads) tn_dp_kernel(const Batch b, const 
             if (!searching || q >= lq || lbest[q] != mk) continue;
             for (int r = 0; r < K; ++r) {
                 const int v = q * K + r;
-                if (__float_as_uint(rec[v].dist) != mk) continue;
+                if (__float_as_uint(__ldcg(&rec[v].dist)) != mk) continue;
                 const int g = gen[v];
                 if (g < bg) { bg = g; bv = v; cnt = 1; }
                 else if (g == bg) ++cnt;
@@ -496,46 +530,75 @@ __global__ void __launch_bounds__(kT2Threads) tn_dp_kernel(const Batch b, const 
         const unsigned who = __ballot_sync(kFullMask, mine_best && searching) & om;
         const int end = __shfl_sync(kFullMask, bv, who ? __ffs(who) - 1 : lane);
 
-        // ---- walk the chain back, zero its edges, score it, filter the box (one lane per octet)
-        int q_first_dst = 0, q_last = -1;
+        VSC_CLK(1);
+        // ---- walk the chain back through the best-predecessor slots (shared memory only, one lane per octet)
+        int len = 0;
         if (sub == 0 && searching) {
-            int len = 0;
             for (int v = end;;) {
                 chain[len++] = (uint16_t)v;
                 const int sl = slot[v];
                 if (sl < 0) break;
-                rec[v].zero |= (MaskT)1 << sl;  // spent edge
-                const int grp = sl / K;
-                v = (v / K - (step - 1 - grp)) * K + (sl - grp * K);
+                const int grp = sl / GS;
+                v = (v / K - (step - 1 - grp)) * K + (sl - grp * GS);
             }
-            float score = 0.0f;
-            for (int i = len - 1; i >= 0; --i) score += rec[chain[i]].sim;
+        }
+        len = __shfl_sync(kFullMask, len, oct * 8);
+        __syncwarp();   // chain[] is visible to the octet
+        // ---- all eight lanes: mark the chain's edges spent (fire-and-forget L2 atomics) and fetch the similarities;
+        // the float32 score is summed in path order (first node first) by shuffling the values through the octet.
+        VSC_CLK(2);
+        float score = 0.0f;
+        const int len_max = __reduce_max_sync(kFullMask, len);
+        for (int i0 = 0; i0 < len_max; i0 += 8) {
+            const int i = len - 1 - (i0 + sub);   // path position i0+sub counted from the first node
+            float s = 0.0f;
+            if (i >= 0) {
+                const int v = chain[i];
+                const int sl = slot[v];
+                if (sl >= 0) {
+                    if (sizeof(MaskT) == 8) atomicOr(reinterpret_cast<unsigned long long *>(&rec[v].zero), 1ull << sl);
+                    else atomicOr(reinterpret_cast<unsigned int *>(&rec[v].zero), 1u << sl);
+                }
+                s = __ldcg(&rec[v].sim);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float sk = __shfl_sync(kFullMask, s, oct * 8 + k);
+                if (i0 + k < len) score += sk;
+            }
+        }
+        VSC_CLK(3);
+        // ---- box of the chain and the filter (one lane per octet)
+        int q_first_dst = 0, q_last = -1;
+        if (sub == 0 && searching) {
             const int first = chain[len - 1], last = chain[0];
             q_first_dst = (len >= 2 ? (int)chain[len - 2] : last) / K;
             q_last = last / K;
             int q_lo = 0, q_hi = 0, r_lo = 0, r_hi = 0;
             if (score > 0.0f) {  // q and (by C2) r increase strictly along a chain
                 q_lo = first / K; q_hi = q_last;
-                r_lo = ref_of[first]; r_hi = ref_of[last];
+                r_lo = ref_of[first] & kRefMask; r_hi = ref_of[last] & kRefMask;
             }
             const double mean_extent = (double)(r_hi - r_lo + q_hi - q_lo) / 2.0;
             double worst = 0.0;
             for (int k = 0; k < n_boxes; ++k) {
-                const int32_t *g = boxes + 4 * k;
-                long long ww = (long long)min(q_hi, g[2]) - max(q_lo, g[0]) + 1;
-                long long hh = (long long)min(r_hi, g[3]) - max(r_lo, g[1]) + 1;
+                const int4 g = boxes[k];
+                long long ww = (long long)min(q_hi, g.z) - max(q_lo, g.x) + 1;
+                long long hh = (long long)min(r_hi, g.w) - max(r_lo, g.y) + 1;
                 ww = ww < 0 ? 0 : ww; hh = hh < 0 ? 0 : hh;
                 const long long inter = ww * hh;
-                const long long a1 = (long long)(q_hi - q_lo + 1) * (r_hi - r_lo + 1);
-                const long long a2 = (long long)(g[2] - g[0] + 1) * (g[3] - g[1] + 1);
-                const double iou = (double)inter / (double)(a1 + a2 - inter);
+                double iou = 0.0;   // disjoint boxes (the usual case) skip the float64 division
+                if (inter != 0) {
+                    const long long a1 = (long long)(q_hi - q_lo + 1) * (r_hi - r_lo + 1);
+                    const long long a2 = (long long)(g.z - g.x + 1) * (g.w - g.y + 1);
+                    iou = (double)inter / (double)(a1 + a2 - inter);
+                }
                 if (k == 0 || iou > worst) worst = iou;
             }
             const int shorter = min(r_hi - r_lo, q_hi - q_lo);
             if (mean_extent != 0.0 && __fdiv_rn(score, (float)mean_extent) > b.min_sim &&
                 (double)shorter > b.min_length && worst < b.max_iou) {
-                int32_t *o = boxes + 4 * n_boxes;
-                o[0] = q_lo; o[1] = r_lo; o[2] = q_hi; o[3] = r_hi;
+                boxes[n_boxes] = make_int4(q_lo, r_lo, q_hi, r_hi);
                 ++n_boxes;
             }
         }
@@ -543,6 +606,7 @@ __global__ void __launch_bounds__(kT2Threads) tn_dp_kernel(const Batch b, const 
         q_last = __shfl_sync(kFullMask, q_last, oct * 8);
         n_boxes = __shfl_sync(kFullMask, n_boxes, oct * 8);
         __syncwarp();
+        VSC_CLK(4);
         if (round == b.max_path) break;
 
         // ---- incremental sweep: layers before the first zeroed edge keep their distances, and the wave dies
@@ -552,38 +616,48 @@ __global__ void __launch_bounds__(kT2Threads) tn_dp_kernel(const Batch b, const 
         if (sweeping) {
             for (int o = 1; o < step; ++o) {  // refill the window behind the start layer
                 const int qq = q_first_dst - o;
-                if (qq >= 0) wdist[(qq & wmask) * 8 + sub] = ranked ? rec[qq * K + sub].dist : 0.0f;
+                if (qq >= 0) win[(qq & wmask) * 8 + sub].x = ranked ? __ldcg(&rec[qq * K + sub].dist) : 0.0f;
             }
         }
-        __syncwarp();
         int last_changed = INT_MIN / 2;
         int q = q_first_dst;
-        for (int i = 0; i < kRing; ++i) request(q + i, sweeping);
-        for (;;) {
-            const bool on = sweeping && q < lq && (q <= q_last || q <= last_changed + step - 1);
-            if (!__any_sync(kFullMask, on)) break;
-            const int v = q * K + sub;
-            cp_async_wait<kRing - 1>();
-            Rec cur = {};
-            if (ranked && on) cur = ring[(q & (kRing - 1)) * 8 + sub];
-            request(q + kRing, on);
-            float d = 0.0f; int sl = -1, g = 0;
-            bool changed = false;
-            if (ranked && on) {
-                relax_node<MaskT, K, false>(cur.pred, cur.zero, cur.sim, q, step, wmask, wdist, wgen, d, sl, g);
-                changed = __float_as_uint(d) != __float_as_uint(cur.dist);
-                if (changed) rec[v].dist = d;
-                slot[v] = (int8_t)sl;
-            }
-            if (on) wdist[(q & wmask) * 8 + sub] = d;
-            if (__ballot_sync(kFullMask, changed) & om) last_changed = q;
-            const uint32_t lm = oct_max(__float_as_uint(d), kFullMask);
-            if (sub == 0 && on) lbest[q] = lm;
-            if (on) ++q;
-            __syncwarp();
+        Rec pre[kAhead];
+#pragma unroll
+        for (int u = 0; u < kAhead; ++u) {
+            pre[u] = Rec{};
+            if (ranked && sweeping && q + u < lq) pre[u] = load_rec(&rec[(q + u) * K + sub]);
         }
-        cp_async_wait<0>();  // nothing may land in the ring after the next sweep re-primes it
+        __syncwarp();
+        for (bool done = false; !done;) {
+#pragma unroll
+            for (int u = 0; u < kAhead; ++u) {
+                // once `on` turns false for an octet it stays false (nothing can update last_changed), so the
+                // register rotation only has to be right while the octet is running
+                const bool on = sweeping && q < lq && (q <= q_last || q <= last_changed + step - 1);
+                if (!__any_sync(kFullMask, on)) { done = true; break; }
+                const Rec cur = pre[u];
+                if (ranked && on && q + kAhead < lq) pre[u] = load_rec(&rec[(q + kAhead) * K + sub]);
+                const int v = q * K + sub;
+                float d = 0.0f; int sl = -1, g = 0;
+                bool changed = false;
+                if (ranked && on) {
+                    relax_node<MaskT, K, GS, false>(cur.pred, cur.zero, cur.sim, q, step, wmask, win, d, sl, g);
+                    changed = __float_as_uint(d) != __float_as_uint(cur.dist);
+                    if (changed) rec[v].dist = d;
+                    slot[v] = (int8_t)sl;
+                }
+                if (on) win[(q & wmask) * 8 + sub].x = d;
+                if (__ballot_sync(kFullMask, changed) & om) last_changed = q;
+                const uint32_t lm = oct_max(__float_as_uint(d), kFullMask);
+                if (sub == 0 && on) lbest[q] = lm;
+                if (on) ++q;
+                VSC_CLK_ADD(6, 1);
+                __syncwarp();
+            }
+        }
+        VSC_CLK(5);
     }
+    VSC_CLK_FLUSH();
     if (sub == 0 && alive) {
         if (ambiguous) {
             w.skip[pair] = 1;
@@ -595,28 +669,28 @@ __global__ void __launch_bounds__(kT2Threads) tn_dp_kernel(const Batch b, const 
     }
 }
 
-template <typename MaskT, int K>
+template <typename MaskT, int K, int GS>
 cudaError_t launch_dp_k(const Batch &b, const Workspace &w, const WorkList &out, int grid, size_t smem,
                         cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(tn_dp_kernel<MaskT, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(tn_dp_kernel<MaskT, K, GS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(tn_dp_kernel<MaskT, K>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    e = cudaFuncSetAttribute(tn_dp_kernel<MaskT, K, GS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (e != cudaSuccess) return e;
-    tn_dp_kernel<MaskT, K><<<grid, kT2Threads, smem, stream>>>(b, w, out);
+    tn_dp_kernel<MaskT, K, GS><<<grid, kT2Threads, smem, stream>>>(b, w, out);
     return cudaGetLastError();
 }
-template <typename MaskT>
+template <typename MaskT, int GS8>
 cudaError_t launch_dp(const Batch &b, const Workspace &w, const WorkList &out, int grid, size_t smem,
                       cudaStream_t stream) {
     switch (b.topk) {
-        case 1: return launch_dp_k<MaskT, 1>(b, w, out, grid, smem, stream);
-        case 2: return launch_dp_k<MaskT, 2>(b, w, out, grid, smem, stream);
-        case 3: return launch_dp_k<MaskT, 3>(b, w, out, grid, smem, stream);
-        case 4: return launch_dp_k<MaskT, 4>(b, w, out, grid, smem, stream);
-        case 5: return launch_dp_k<MaskT, 5>(b, w, out, grid, smem, stream);
-        case 6: return launch_dp_k<MaskT, 6>(b, w, out, grid, smem, stream);
-        case 7: return launch_dp_k<MaskT, 7>(b, w, out, grid, smem, stream);
-        default: return launch_dp_k<MaskT, 8>(b, w, out, grid, smem, stream);
+        case 1: return launch_dp_k<MaskT, 1, GS8 ? 8 : 1>(b, w, out, grid, smem, stream);
+        case 2: return launch_dp_k<MaskT, 2, GS8 ? 8 : 2>(b, w, out, grid, smem, stream);
+        case 3: return launch_dp_k<MaskT, 3, GS8 ? 8 : 3>(b, w, out, grid, smem, stream);
+        case 4: return launch_dp_k<MaskT, 4, GS8 ? 8 : 4>(b, w, out, grid, smem, stream);
+        case 5: return launch_dp_k<MaskT, 5, GS8 ? 8 : 5>(b, w, out, grid, smem, stream);
+        case 6: return launch_dp_k<MaskT, 6, GS8 ? 8 : 6>(b, w, out, grid, smem, stream);
+        case 7: return launch_dp_k<MaskT, 7, GS8 ? 8 : 7>(b, w, out, grid, smem, stream);
+        default: return launch_dp_k<MaskT, 8, 8>(b, w, out, grid, smem, stream);
     }
 }
 
@@ -647,16 +721,21 @@ __global__ void iota_kernel(int32_t *count, int32_t *list, int n) {
     if (i == 0) *count = n;
 }
 
+// Warps per T1 CTA: as many as shared memory holds (one CTA per SM), at most kT1MaxWarps.
+int t1_warps(int max_lr) {
+    const size_t fit = (size_t)(227 * 1024) / t1_warp_bytes(max_lr);
+    return (int)(fit < (size_t)kT1MaxWarps ? fit : (size_t)kT1MaxWarps);
+}
+
 template <int K>
-int launch_topk(const T1Args &a, int grid, size_t smem, cudaStream_t stream) {
+int launch_topk(const T1Args &a, int grid, int warps, cudaStream_t stream) {
+    const size_t smem = (size_t)warps * a.warp_bytes;
     VSC_CUDA_CHECK(cudaFuncSetAttribute(tn_topk_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     VSC_CUDA_CHECK(cudaFuncSetAttribute(tn_topk_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    tn_topk_kernel<K><<<grid, kT1Threads, smem, stream>>>(a);
+    tn_topk_kernel<K><<<grid, warps * 32, smem, stream>>>(a);
     VSC_CUDA_CHECK(cudaGetLastError());
     return VSC_OK;
 }
-
-size_t t1_smem_bytes() { return sizeof(T1Smem) * kT1Warps; }
 
 }  // namespace
 
@@ -677,29 +756,30 @@ static void mark(int i, cudaStream_t stream) {
 bool pipeline_supported(const Batch &b) {
     if (b.max_lr > vsc::kBlockCols * vsc::kMaxRowBlocks || b.max_lr < b.topk) return false;
     if (b.topk < 1 || b.topk > kMaxTop) return false;
-    if ((reinterpret_cast<uintptr_t>(b.sims) & 15u) != 0) return false;
+    if ((b.step - 1) * 8 > 32 && (b.step - 1) * b.topk > 64) return false;   // predecessor mask width
+    if ((reinterpret_cast<uintptr_t>(b.sims) & 15u) != 0 || (reinterpret_cast<uintptr_t>(b.boxes) & 15u) != 0) return false;
     if (b.max_nodes > 65535) return false;
-    if (t2_pair_bytes(b.max_nodes, b.max_lq, b.step, 32) * kT2Warps * 4 > 200 * 1024) return false;
-    return t1_smem_bytes() <= 227 * 1024;
+    if (t2_pair_bytes(b.max_nodes, b.max_lq, b.step) * kT2Warps * 4 > 200 * 1024) return false;
+    if ((long long)b.n_pairs * ((b.max_lq + kTileRows - 1) / kTileRows) >= (1ll << 31) - 65536) return false;  // tile ids
+    return t1_warps(b.max_lr) >= 1;
 }
 
 int launch_pipeline(const Batch &b, const WorkList &out, cudaStream_t stream) {
-    const bool wide = (b.step - 1) * b.topk > 32;
-        const size_t P = (size_t)b.n_pairs, N = (size_t)b.max_nodes, L = (size_t)b.max_lq;
+    const bool wide = (b.step - 1) * 8 > 32;   // fast variant: 32-bit masks with a group stride of 8 slots
+    const size_t P = (size_t)b.n_pairs, N = (size_t)b.max_nodes;
     // one stream-ordered allocation, carved by alignment
     size_t sz = 0;
     auto take = [&](size_t bytes) { size_t at = sz; sz += (bytes + 255) / 256 * 256; return at; };
     const size_t rec_bytes = wide ? sizeof(NodeRec<uint64_t>) : sizeof(NodeRec<uint32_t>);
     const size_t o_rec = take(P * N * rec_bytes);
-    const size_t o_ref = take(P * N * 2), o_gen = take(P * N * 2), o_chain = take(P * L * 2);
-    const size_t o_skip = take(P), o_cursor = take(4);
+    const size_t o_ref = take(P * N * 2), o_gen = take(P * N * 2);
+    const size_t o_skip = take(P * 4), o_cursor = take(4);
     unsigned char *base = nullptr;
     VSC_CUDA_CHECK(cudaMallocAsync(&base, sz, stream));
     Workspace w;
     w.rec = base + o_rec; w.rec_bytes = (int)rec_bytes; w.sim_off = wide ? 16 : 8;
     w.ref_of = reinterpret_cast<uint16_t *>(base + o_ref); w.gen = reinterpret_cast<uint16_t *>(base + o_gen);
-    w.chain = reinterpret_cast<uint16_t *>(base + o_chain);
-    w.skip = base + o_skip; w.cursor = reinterpret_cast<int32_t *>(base + o_cursor);
+    w.skip = reinterpret_cast<int32_t *>(base + o_skip); w.cursor = reinterpret_cast<int32_t *>(base + o_cursor);
     int rc = VSC_OK;
     auto fail = [&](cudaError_t e, const char *what) {
         if (e != cudaSuccess && rc == VSC_OK) { vsc::set_error("%s: %s", what, cudaGetErrorString(e)); rc = VSC_ERR_CUDA; }
@@ -713,17 +793,20 @@ int launch_pipeline(const Batch &b, const WorkList &out, cudaStream_t stream) {
     mark(0, stream);
     if (rc == VSC_OK) {
         T1Args a; a.b = b; a.w = w; a.out = out;
-        const size_t smem = t1_smem_bytes();
-        const int grid = sms;  // persistent: one CTA of kT1Warps warps per SM
+        a.tiles_per_pair = (b.max_lq + kTileRows - 1) / kTileRows;
+        a.n_tiles = b.n_pairs * a.tiles_per_pair;
+        a.warp_bytes = (int)t1_warp_bytes(b.max_lr);
+        const int warps = t1_warps(b.max_lr);
+        const int grid = sms;  // persistent: one CTA per SM
         switch (b.topk) {
-            case 1: rc = launch_topk<1>(a, grid, smem, stream); break;
-            case 2: rc = launch_topk<2>(a, grid, smem, stream); break;
-            case 3: rc = launch_topk<3>(a, grid, smem, stream); break;
-            case 4: rc = launch_topk<4>(a, grid, smem, stream); break;
-            case 5: rc = launch_topk<5>(a, grid, smem, stream); break;
-            case 6: rc = launch_topk<6>(a, grid, smem, stream); break;
-            case 7: rc = launch_topk<7>(a, grid, smem, stream); break;
-            default: rc = launch_topk<8>(a, grid, smem, stream); break;
+            case 1: rc = launch_topk<1>(a, grid, warps, stream); break;
+            case 2: rc = launch_topk<2>(a, grid, warps, stream); break;
+            case 3: rc = launch_topk<3>(a, grid, warps, stream); break;
+            case 4: rc = launch_topk<4>(a, grid, warps, stream); break;
+            case 5: rc = launch_topk<5>(a, grid, warps, stream); break;
+            case 6: rc = launch_topk<6>(a, grid, warps, stream); break;
+            case 7: rc = launch_topk<7>(a, grid, warps, stream); break;
+            default: rc = launch_topk<8>(a, grid, warps, stream); break;
         }
         vsc::count_launch();
     }
@@ -731,8 +814,8 @@ int launch_pipeline(const Batch &b, const WorkList &out, cudaStream_t stream) {
     if (rc == VSC_OK) {
         const long long threads = (long long)b.n_pairs * b.max_lq;
         const int grid = (int)((threads + 255) / 256);
-        if (wide) launch_edges<uint64_t>(b, w, grid, stream);
-        else launch_edges<uint32_t>(b, w, grid, stream);
+        if (wide) launch_edges<uint64_t, 0>(b, w, grid, stream);
+        else launch_edges<uint32_t, 1>(b, w, grid, stream);
         fail(cudaGetLastError(), "tn_edges_kernel");
         vsc::count_launch();
     }
@@ -740,9 +823,9 @@ int launch_pipeline(const Batch &b, const WorkList &out, cudaStream_t stream) {
     if (rc == VSC_OK) {
         const int pairs_per_cta = kT2Warps * 4;
         const int grid = (b.n_pairs + pairs_per_cta - 1) / pairs_per_cta;
-        const size_t smem = t2_pair_bytes(b.max_nodes, b.max_lq, b.step, rec_bytes) * pairs_per_cta;
-        fail(wide ? launch_dp<uint64_t>(b, w, out, grid, smem, stream)
-                  : launch_dp<uint32_t>(b, w, out, grid, smem, stream), "tn_dp_kernel");
+        const size_t smem = t2_pair_bytes(b.max_nodes, b.max_lq, b.step) * pairs_per_cta;
+        fail(wide ? launch_dp<uint64_t, 0>(b, w, out, grid, smem, stream)
+                  : launch_dp<uint32_t, 1>(b, w, out, grid, smem, stream), "tn_dp_kernel");
         fail(cudaGetLastError(), "tn_dp_kernel");
         vsc::count_launch();
     }
@@ -774,10 +857,13 @@ extern "C" int vsc_tn_last_stage_ms(float *out4) {
     return VSC_OK;
 }
 
-// Development aid: DP work counters (all zero unless built with -DVSC_TN_COUNTERS).
-__device__ unsigned long long g_dp_counters[4];
-extern "C" int vsc_tn_debug_counters(unsigned long long *out4) {
-    VSC_CUDA_CHECK(cudaMemcpyFromSymbol(out4, g_dp_counters, sizeof(unsigned long long) * 4));
+// Development aid: DP phase clocks (all zero unless built with -DVSC_TN_COUNTERS), summed over warps:
+// cycles in {first sweep, end-node search, chain walk, zero + score, box filter, incremental sweeps},
+// incremental layer steps, warps.
+extern "C" int vsc_tn_debug_counters(unsigned long long *out8) {
+    VSC_CUDA_CHECK(cudaMemcpyFromSymbol(out8, g_dp_counters, sizeof(unsigned long long) * 8));
+    unsigned long long zero[8] = {};
+    VSC_CUDA_CHECK(cudaMemcpyToSymbol(g_dp_counters, zero, sizeof zero));
     return VSC_OK;
 }
 
