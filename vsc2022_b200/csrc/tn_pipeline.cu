@@ -388,9 +388,11 @@ __host__ __device__ inline int window_depth(int step) {  // power of two >= step
 
 __host__ __device__ inline size_t t2_pair_bytes(int max_nodes, int max_lq, int step) {
     const size_t d = (size_t)window_depth(step);
-    size_t b = d * 8 * 8;                                 // (distance, generation) window
+    size_t b = d * 8 * 8;                                 // (distance, generation) window of a sweep ...
+    if (b < (size_t)max_lq * 2) b = (size_t)max_lq * 2;   // ... shares its bytes with the chain of a round
+    b = (b + 15) / 16 * 16;
     b += (size_t)max_lq * 4;                              // layer maxima
-    b += (size_t)max_lq * 2;                              // chain of the current round
+    b += (size_t)max_lq;                                  // ranks that attain the layer maximum
     b += (size_t)max_nodes;                               // best-predecessor slots
     return (b + 15) / 16 * 16;
 }
@@ -449,10 +451,14 @@ __global__ void __launch_bounds__(kT2Threads, 8) tn_dp_kernel(const Batch b, con
 
     const int depth = window_depth(step), wmask = depth - 1;
     unsigned char *mine = t2_smem + (size_t)((threadIdx.x >> 5) * 4 + oct) * t2_pair_bytes(b.max_nodes, b.max_lq, step);
+    // The distance window is only alive inside a sweep (every sweep refills what it reads) and the chain only
+    // between two sweeps, so they share one region: that is what lets a whole 8000-pair batch stay resident.
+    const size_t shared_region = (max((size_t)depth * 64, (size_t)b.max_lq * 2) + 15) / 16 * 16;
     float2 *win = reinterpret_cast<float2 *>(mine);                     // {distance, generation bits}
-    uint32_t *lbest = reinterpret_cast<uint32_t *>(win + depth * 8);    // per-layer maximum distance (float bits)
-    uint16_t *chain = reinterpret_cast<uint16_t *>(lbest + b.max_lq);   // nodes of the chain, end node first
-    int8_t *slot = reinterpret_cast<int8_t *>(chain + b.max_lq);        // best-predecessor slot per node
+    uint16_t *chain = reinterpret_cast<uint16_t *>(mine);               // nodes of the chain, end node first
+    uint32_t *lbest = reinterpret_cast<uint32_t *>(mine + shared_region);  // per-layer maximum distance (float bits)
+    uint8_t *lrank = reinterpret_cast<uint8_t *>(lbest + b.max_lq);     // bit r: node (q, r) attains lbest[q]
+    int8_t *slot = reinterpret_cast<int8_t *>(lrank + b.max_lq);        // best-predecessor slot per node
 
     const int lq = alive ? b.lq[p] : 0;
     const int lq_max = __reduce_max_sync(kFullMask, lq);
@@ -470,21 +476,21 @@ __global__ void __launch_bounds__(kT2Threads, 8) tn_dp_kernel(const Batch b, con
 
     VSC_CLK_START();
     // ---- first sweep: every layer
+    // Prefetch loads are UNCONDITIONAL (row and rank clamped into the pair's own records): a predicated load
+    // makes the compiler merge old and new value with a move right behind the load, which waits for it --
+    // measured as one exposed L2 round trip per layer (740 cycles per layer with the SM to itself).
+    const int last_row = lq > 0 ? lq - 1 : 0, my_rank = ranked ? sub : K - 1;
     {
         Rec pre[kAhead];
 #pragma unroll
-        for (int u = 0; u < kAhead; ++u) {
-            pre[u] = Rec{};
-            if (ranked && u < lq) pre[u] = load_rec(&rec[u * K + sub]);
-        }
+        for (int u = 0; u < kAhead; ++u) pre[u] = load_rec(&rec[min(u, last_row) * K + my_rank]);
         for (int q0 = 0; q0 < lq_max; q0 += kAhead) {
 #pragma unroll
             for (int u = 0; u < kAhead; ++u) {
-                const int q = q0 + u;
-                if (q >= lq_max) break;            // warp-uniform
+                const int q = q0 + u;              // layers past lq_max only run predicated-off work
                 const bool mine_on = ranked && q < lq;
                 const Rec cur = pre[u];
-                if (ranked && q + kAhead < lq) pre[u] = load_rec(&rec[(q + kAhead) * K + sub]);
+                pre[u] = load_rec(&rec[min(q + kAhead, last_row) * K + my_rank]);
                 const int v = q * K + sub;
                 float d = 0.0f; int sl = -1, g = 0;
                 if (mine_on) {
@@ -494,34 +500,48 @@ __global__ void __launch_bounds__(kT2Threads, 8) tn_dp_kernel(const Batch b, con
                 }
                 // window slot q & wmask held layer q-depth, which nobody reads any more
                 win[(q & wmask) * 8 + sub] = make_float2(d, __int_as_float(g));
-                const uint32_t lm = oct_max(__float_as_uint(d), kFullMask);  // dist >= +0: bits are ordered
-                if (sub == 0 && q < lq) lbest[q] = lm;
+                const uint32_t db = __float_as_uint(d);
+                const uint32_t lm = oct_max(db, kFullMask);  // dist >= +0: bits are ordered
+                const uint32_t at_max = (__ballot_sync(kFullMask, db == lm) >> (oct * 8)) & 0xFFu;
+                if (sub == 0 && q < lq) { lbest[q] = lm; lrank[q] = (uint8_t)at_max; }
                 __syncwarp();
             }
         }
     }
-
     VSC_CLK(0);
     int n_boxes = 0;
     bool ambiguous = false;
     bool searching = alive;   // this octet still looks for chains
     for (int round = 0; round <= b.max_path; ++round) {
         if (!__any_sync(kFullMask, searching)) break;
-        // ---- end node: maximum distance; ties -> smallest Kahn generation
-        uint32_t mk = 0;
-        for (int q = sub; q < lq_max; q += 8)
-            if (q < lq) mk = max(mk, lbest[q]);
-        mk = oct_max(mk, kFullMask);
-        if (mk == 0u) searching = false;  // only zero-length paths left: networkx returns [source]
-        int bg = INT_MAX, bv = -1, cnt = 0;
+        // ---- end node: maximum distance; ties -> smallest Kahn generation.  One pass over the per-layer maxima in
+        // shared memory; the generations (global memory) are only read when more than one node attains the maximum.
+        uint32_t mine_max = 0; int q_first = -1, n_layers = 0;
         for (int q = sub; q < lq_max; q += 8) {
-            if (!searching || q >= lq || lbest[q] != mk) continue;
-            for (int r = 0; r < K; ++r) {
-                const int v = q * K + r;
-                if (__float_as_uint(__ldcg(&rec[v].dist)) != mk) continue;
-                const int g = gen[v];
-                if (g < bg) { bg = g; bv = v; cnt = 1; }
-                else if (g == bg) ++cnt;
+            if (q >= lq) break;
+            const uint32_t x = lbest[q];
+            if (x > mine_max) { mine_max = x; q_first = q; n_layers = 1; }
+            else if (x == mine_max && x != 0u) ++n_layers;
+        }
+        const uint32_t mk = oct_max(mine_max, kFullMask);
+        if (mk == 0u) searching = false;  // only zero-length paths left: networkx returns [source]
+        const bool holds_max = searching && mine_max == mk;
+        const int layers_at_max = oct_add(holds_max ? n_layers : 0, kFullMask);
+        int bg = INT_MAX, bv = -1, cnt = 0;
+        if (holds_max) {
+            const uint32_t m0 = lrank[q_first];
+            if (layers_at_max == 1 && (m0 & (m0 - 1)) == 0u) {   // a single node: no tie to break
+                bv = q_first * K + __ffs((int)m0) - 1; bg = 0; cnt = 1;
+            } else {
+                for (int q = q_first; q < lq; q += 8) {
+                    if (lbest[q] != mk) continue;
+                    for (uint32_t m = lrank[q]; m; m &= m - 1) {
+                        const int v = q * K + __ffs((int)m) - 1;
+                        const int g = gen[v];
+                        if (g < bg) { bg = g; bv = v; cnt = 1; }
+                        else if (g == bg) ++cnt;
+                    }
+                }
             }
         }
         const int g_min = oct_min(bg, kFullMask);
@@ -623,10 +643,7 @@ __global__ void __launch_bounds__(kT2Threads, 8) tn_dp_kernel(const Batch b, con
         int q = q_first_dst;
         Rec pre[kAhead];
 #pragma unroll
-        for (int u = 0; u < kAhead; ++u) {
-            pre[u] = Rec{};
-            if (ranked && sweeping && q + u < lq) pre[u] = load_rec(&rec[(q + u) * K + sub]);
-        }
+        for (int u = 0; u < kAhead; ++u) pre[u] = load_rec(&rec[min(q + u, last_row) * K + my_rank]);
         __syncwarp();
         for (bool done = false; !done;) {
 #pragma unroll
@@ -636,7 +653,7 @@ __global__ void __launch_bounds__(kT2Threads, 8) tn_dp_kernel(const Batch b, con
                 const bool on = sweeping && q < lq && (q <= q_last || q <= last_changed + step - 1);
                 if (!__any_sync(kFullMask, on)) { done = true; break; }
                 const Rec cur = pre[u];
-                if (ranked && on && q + kAhead < lq) pre[u] = load_rec(&rec[(q + kAhead) * K + sub]);
+                pre[u] = load_rec(&rec[min(q + kAhead, last_row) * K + my_rank]);
                 const int v = q * K + sub;
                 float d = 0.0f; int sl = -1, g = 0;
                 bool changed = false;
@@ -648,8 +665,10 @@ __global__ void __launch_bounds__(kT2Threads, 8) tn_dp_kernel(const Batch b, con
                 }
                 if (on) win[(q & wmask) * 8 + sub].x = d;
                 if (__ballot_sync(kFullMask, changed) & om) last_changed = q;
-                const uint32_t lm = oct_max(__float_as_uint(d), kFullMask);
-                if (sub == 0 && on) lbest[q] = lm;
+                const uint32_t db = __float_as_uint(d);
+                const uint32_t lm = oct_max(db, kFullMask);
+                const uint32_t at_max = (__ballot_sync(kFullMask, db == lm) >> (oct * 8)) & 0xFFu;
+                if (sub == 0 && on) { lbest[q] = lm; lrank[q] = (uint8_t)at_max; }
                 if (on) ++q;
                 VSC_CLK_ADD(6, 1);
                 __syncwarp();
