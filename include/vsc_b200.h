@@ -119,7 +119,9 @@ int vsc_gemm_conv(const void *d_a, int64_t m, const void *d_w, int64_t n, int32_
 /* fp32 out[m][n] = A . W^T + bias[n] (projection head) */
 int vsc_gemm_linear(const void *d_a, int64_t m, const void *d_w, int64_t n, int32_t k, const float *d_bias, float *d_out,
                     int64_t ldc, vsc_stream_t stream);
-/* 7x7/2 stem patches [n*ho*wo][192]; mode 0: uint8 NHWC pixels (normalised here), 1: float32 NCHW normalised */
+/* 7x7/2 stem patches [n*ho*wo][192]; mode 0: uint8 NHWC pixels (normalised here), 1: float32 NCHW normalised.
+ * K index = ky2*48 + kx2*12 + (dy*2+dx)*3 + c for filter tap (2*ky2+dy, 2*kx2+dx) (space-to-depth order; taps with
+ * row or column 7 are padding and must carry zero weights) */
 int vsc_im2col_stem(const void *d_in, int32_t mode, int32_t n, int32_t h, int32_t w, void *d_out, vsc_stream_t stream);
 /* 3x3 pad-1 patches [n*ho*wo][9*c] of an NHWC bf16 tensor, stride 1 or 2 */
 int vsc_im2col3x3(const void *d_in, int32_t n, int32_t h, int32_t w, int32_t c, int32_t stride, void *d_out,

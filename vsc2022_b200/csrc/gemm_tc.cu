@@ -12,10 +12,12 @@
 //   EMIT    count scores beyond `count_thr`, append (score, i, j) of those beyond `emit_thr`
 //           (strict comparisons, inner product or squared-L2 metric)
 //
-// Kernel anatomy (persistent, one CTA per SM, 192 threads):
+// Kernel anatomy (persistent, one CTA per SM, 192 threads; 320 for the convolution epilogue):
 //   warp 0      TMA producer: cp.async.bulk.tensor 2D tiles (SWIZZLE_128B) into a 4-stage ring
 //   warp 1      allocates TMEM; one lane issues tcgen05.mma (M128 x N256 x K16, cta_group::1)
 //   warps 2-5   epilogue: tcgen05.ld 32 columns at a time from one of two accumulator buffers
+//   (warps 6-9  CONV only: a second epilogue warp per TMEM lane quadrant taking every other 32-column chunk --
+//               short-K convolutions are bound by the epilogue's dependent chain, not by the MMAs)
 //               (512 TMEM columns), so the epilogue of tile t overlaps the MMAs of tile t+1
 // Tile order: m fastest, so concurrently running CTAs share the same reference tile in L2 while the
 // whole query matrix stays L2-resident; references stream from HBM once.
@@ -32,6 +34,8 @@ constexpr int BM = 128, BK = 64;  // the N tile (64 / 128 / 256) is a template p
 constexpr int STAGES = 4;
 constexpr int UMMA_K = 16;
 constexpr int kThreads = 192;
+constexpr int kThreadsConv = 320;   // 8 epilogue warps
+__host__ __device__ constexpr int epi_warps(int epi) { return epi == 4 /* EPI_CONV */ ? 8 : 4; }
 constexpr uint32_t kStageBytesA = BM * BK * 2;
 
 enum Epilogue { EPI_STORE = 0, EPI_ROWMAX = 1, EPI_EMIT = 2, EPI_ROWARGMAX = 3, EPI_CONV = 4 };
@@ -67,7 +71,7 @@ struct SharedStorage {
     uint32_t tmem_base;
     // CONV epilogue: per epilogue warp, a 32-row x 64-byte transpose buffer for the residual tile coming in and one
     // for the bf16 tile going out (16-byte units, XOR-swizzled: see conv_unit)
-    alignas(16) uint4 stage_in[4][128], stage_out[4][128];
+    alignas(16) uint4 stage_in[8][128], stage_out[8][128];
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -299,7 +303,7 @@ __device__ __forceinline__ void conv_epilogue_chunk(const GemmArgs &g, int64_t r
 }
 
 template <int EPI, int BN>
-__global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant__ CUtensorMap tma_a,
+__global__ void __launch_bounds__(EPI == 4 ? kThreadsConv : kThreads, 1) gemm_kernel(const __grid_constant__ CUtensorMap tma_a,
                                                            const __grid_constant__ CUtensorMap tma_b,
                                                            const GemmArgs g) {
     extern __shared__ uint8_t smem_raw[];
@@ -314,7 +318,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&sm.tmem_full[s], 1); mbar_init(&sm.tmem_empty[s], 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&sm.tmem_full[s], 1); mbar_init(&sm.tmem_empty[s], epi_warps(EPI)); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {  // one full warp allocates all 512 TMEM columns and publishes the base address
@@ -387,14 +391,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
                 // the arithmetic and the stores of chunk c.
                 const int64_t row0 = m_blk * BM + quad * 32, colb = n_blk * BN;
                 const int chunks = (int)((g.N - colb < BN ? g.N - colb : BN) / 32);
+                const int epi = warp - 2, first = epi >> 2;   // two warps per lane quadrant: even / odd chunks
                 uint4 res[4] = {}, res_next[4] = {};
-                if (g.residual && chunks > 0) conv_residual_fetch(g, row0, colb, lane, res);
+                if (g.residual && first < chunks) conv_residual_fetch(g, row0, colb + first * 32, lane, res);
 #pragma unroll 1
-                for (int c = 0; c < chunks; ++c) {
-                    if (g.residual && c + 1 < chunks) conv_residual_fetch(g, row0, colb + (c + 1) * 32, lane, res_next);
+                for (int c = first; c < chunks; c += 2) {
+                    if (g.residual && c + 2 < chunks) conv_residual_fetch(g, row0, colb + (c + 2) * 32, lane, res_next);
                     uint32_t v[32];
                     tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + c * 32, v);
-                    conv_epilogue_chunk(g, row0, colb + c * 32, lane, v, res, sm.stage_in[quad], sm.stage_out[quad]);
+                    conv_epilogue_chunk(g, row0, colb + c * 32, lane, v, res, sm.stage_in[epi], sm.stage_out[epi]);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) res[i] = res_next[i];
                 }
@@ -478,7 +483,7 @@ int launch(const void *a, const void *b, const GemmArgs &g, cudaStream_t stream)
     VSC_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int64_t tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
     const int grid = (int)(tiles < sms ? tiles : sms);
-    gemm_kernel<EPI, BN><<<grid, kThreads, smem, stream>>>(ma, mb, g);
+    gemm_kernel<EPI, BN><<<grid, EPI == EPI_CONV ? kThreadsConv : kThreads, smem, stream>>>(ma, mb, g);
     VSC_CUDA_CHECK(cudaGetLastError());
     vsc::count_launch();
     return VSC_OK;

@@ -11,56 +11,62 @@
 
 namespace {
 
-// ---- stem: 7x7 stride 2 pad 3 on 3 channels.  Panel row = output pixel, K index = (ky*7 + kx)*3 + c, padded 147 -> 192.
-// mode 0: uint8 NHWC pixels, normalised here ((x/255 - mean)/std, inference_impl.py:39-69); padding is zero in
-//         NORMALISED space, exactly like torchvision's Normalize followed by the conv's zero padding.
-// mode 1: float32 NCHW tensor that is already normalised (what the reference model receives).
-// One thread produces 16 bytes (8 consecutive K indices) of one panel row: grid.x = image row (img*ho + oy),
-// grid.y covers (ox, 24 uint4 per pixel), so the only runtime division is img = row / ho.  For uint8 input the
-// normalisation is a 3 x 256 bf16 table in shared memory built with the reference formula (two IEEE divisions per
-// entry instead of per pixel tap); the 21 taps of one (pixel, ky) are 21 contiguous input bytes.
-constexpr int kStemUnits = 24;   // 192 bf16 = 24 x 16 bytes per panel row
+// ---- stem: 7x7 stride 2 pad 3 on 3 channels, as a 4x4 stride-1 convolution over a 2x2 space-to-depth image.
+// Step 1 (stem_s2d_kernel): S[n][Y][X][(dy*2+dx)*3 + c] = normalised pixel (2Y+dy-3, 2X+dx-3, c), zero outside the
+//         frame (zero in NORMALISED space, exactly like torchvision's Normalize followed by the conv's padding);
+//         Y < ho+3, X < wo+3, 12 bf16 = 24 bytes per cell.
+//         mode 0: uint8 NHWC pixels, normalised here ((x/255 - mean)/std, inference_impl.py:39-69);
+//         mode 1: float32 NCHW tensor that is already normalised (what the reference model receives).
+// Step 2 (stem_panel_kernel): panel row of output pixel (oy, ox) = for ky2 = 0..3 the 96 CONTIGUOUS bytes
+//         S[n][oy+ky2][ox..ox+3][0..11]: a pure copy in 8-byte units.  K index = ky2*48 + kx2*12 + (dy*2+dx)*3 + c
+//         <-> filter tap (ky, kx) = (2*ky2+dy, 2*kx2+dx); taps with ky = 7 or kx = 7 carry zero weights.  K = 192.
+// (The first version wrote the panel element-wise from the uint8 frame: 1.3 ms per 128 frames, 8x the HBM time.)
 template <int MODE>
-__global__ void __launch_bounds__(256) im2col_stem_kernel(const void *__restrict__ in, int n, int h, int w, int ho,
-                                                          int wo, uint4 *__restrict__ out) {
-    __shared__ uint16_t lut[3][256];
-    if (MODE == 0) {
-        const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
-        for (int e = threadIdx.x; e < 768; e += blockDim.x) {
-            const int c = e >> 8, b = e & 255;
-            const __nv_bfloat16 v = __float2bfloat16_rn(((float)b / 255.0f - mean[c]) / stdv[c]);
-            lut[c][b] = *reinterpret_cast<const uint16_t *>(&v);
-        }
-        __syncthreads();
-    }
-    const int row = blockIdx.x;
-    const int img = row / ho, oy = row - img * ho;
-    const int t = blockIdx.y * blockDim.x + threadIdx.x;
-    const int ox = t / kStemUnits, j = t - ox * kStemUnits;
-    if (ox >= wo) return;
-    int ky = (j * 8) / 21, r = j * 8 - ky * 21;   // K index k = ky*21 + r, r = kx*3 + c
-    uint16_t v[8];
+__global__ void __launch_bounds__(256) stem_s2d_kernel(const void *__restrict__ in, int n, int h, int w, int yd, int xd,
+                                                       uint32_t total, uint2 *__restrict__ out) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;   // one (image, Y, X) cell
+    if (idx >= total) return;
+    const uint32_t t = idx / (uint32_t)xd;
+    const int X = (int)(idx - t * (uint32_t)xd);
+    const int img = (int)(t / (uint32_t)yd), Y = (int)(t - (uint32_t)img * (uint32_t)yd);
+    const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+    uint16_t v[12];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-        uint16_t x = 0;
-        const int kx = r / 3, c = r - kx * 3;
-        const int iy = oy * 2 - 3 + ky, ix = ox * 2 - 3 + kx;
-        if (ky < 7 && iy >= 0 && iy < h && ix >= 0 && ix < w) {
-            if (MODE == 0) {
-                const uint8_t *p = static_cast<const uint8_t *>(in);
-                x = lut[c][p[(((size_t)img * h + iy) * w + ix) * 3 + c]];
-            } else {
-                const float *p = static_cast<const float *>(in);
-                const __nv_bfloat16 b = __float2bfloat16_rn(p[(((size_t)img * 3 + c) * h + iy) * w + ix]);
-                x = *reinterpret_cast<const uint16_t *>(&b);
+    for (int dy = 0; dy < 2; ++dy) {
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+            const int iy = 2 * Y + dy - 3, ix = 2 * X + dx - 3;
+            const bool inside = iy >= 0 && iy < h && ix >= 0 && ix < w;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float x = 0.0f;
+                if (inside) {
+                    if (MODE == 0)
+                        x = ((float)static_cast<const uint8_t *>(in)[(((size_t)img * h + iy) * w + ix) * 3 + c] / 255.0f - mean[c]) / stdv[c];
+                    else
+                        x = static_cast<const float *>(in)[(((size_t)img * 3 + c) * h + iy) * w + ix];
+                }
+                const __nv_bfloat16 b = __float2bfloat16_rn(x);
+                v[(dy * 2 + dx) * 3 + c] = inside ? *reinterpret_cast<const uint16_t *>(&b) : (uint16_t)0;
             }
         }
-        v[u] = x;
-        if (++r == 21) { r = 0; ++ky; }
     }
-    out[((size_t)row * wo + ox) * kStemUnits + j] =
-        make_uint4(v[0] | ((uint32_t)v[1] << 16), v[2] | ((uint32_t)v[3] << 16), v[4] | ((uint32_t)v[5] << 16),
-                   v[6] | ((uint32_t)v[7] << 16));
+    uint2 *o = out + (size_t)idx * 3;
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+        o[q] = make_uint2(v[q * 4] | ((uint32_t)v[q * 4 + 1] << 16), v[q * 4 + 2] | ((uint32_t)v[q * 4 + 3] << 16));
+}
+
+constexpr int kStemUnits = 48;   // 192 bf16 = 48 x 8 bytes per panel row
+__global__ void __launch_bounds__(256) stem_panel_kernel(const uint2 *__restrict__ s2d, int ho, int wo, int yd, int xd,
+                                                         uint2 *__restrict__ out) {
+    const int row = blockIdx.x;                       // img*ho + oy
+    const int img = row / ho, oy = row - img * ho;
+    const int t = blockIdx.y * blockDim.x + threadIdx.x;
+    const int ox = t / kStemUnits, u = t - ox * kStemUnits;
+    if (ox >= wo) return;
+    const int ky2 = u / 12, part = u - ky2 * 12;
+    out[((size_t)row * wo + ox) * kStemUnits + u] = s2d[(((size_t)img * yd + oy + ky2) * xd + ox) * 3 + part];
 }
 
 // ---- 3x3 pad 1, stride s: panel [n*ho*wo][9*c], K index = (ky*3 + kx)*c + ch.  One thread moves 8 channels (16 B)
@@ -155,18 +161,24 @@ inline unsigned blocks(long long total) { return (unsigned)((total + 255) / 256)
 }  // namespace
 
 extern "C" int vsc_im2col_stem(const void *d_in, int32_t mode, int32_t n, int32_t h, int32_t w, void *d_out,
-                               vsc_stream_t stream) {
-    const int ho = (h + 6 - 7) / 2 + 1, wo = (w + 6 - 7) / 2 + 1;
+                               vsc_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const int ho = (h + 6 - 7) / 2 + 1, wo = (w + 6 - 7) / 2 + 1, yd = ho + 3, xd = wo + 3;
     if (n <= 0) return VSC_OK;
     if (mode != 0 && mode != 1) { vsc::set_error("vsc_im2col_stem: mode must be 0 (uint8 NHWC) or 1 (float32 NCHW)"); return VSC_ERR_INVALID; }
+    const long long cells = (long long)n * yd * xd;
     const dim3 grid((unsigned)((long long)n * ho), (unsigned)((wo * kStemUnits + 255) / 256));
-    if (grid.y > 65535u) { vsc::set_error("vsc_im2col_stem: frame width %d too large", w); return VSC_ERR_CAPACITY; }
-    if (mode == 0)
-        im2col_stem_kernel<0><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_in, n, h, w, ho, wo, static_cast<uint4 *>(d_out));
-    else
-        im2col_stem_kernel<1><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_in, n, h, w, ho, wo, static_cast<uint4 *>(d_out));
-    VSC_CUDA_CHECK(cudaGetLastError());
-    vsc::count_launch();
+    if (cells >= (1ll << 31) || grid.y > 65535u) { vsc::set_error("vsc_im2col_stem: batch of %d %dx%d frames too large", n, h, w); return VSC_ERR_CAPACITY; }
+    vsc::keep_pool_cached();
+    uint2 *s2d = nullptr;
+    VSC_CUDA_CHECK(cudaMallocAsync(&s2d, (size_t)cells * 24, stream));
+    if (mode == 0) stem_s2d_kernel<0><<<blocks(cells), 256, 0, stream>>>(d_in, n, h, w, yd, xd, (uint32_t)cells, s2d);
+    else stem_s2d_kernel<1><<<blocks(cells), 256, 0, stream>>>(d_in, n, h, w, yd, xd, (uint32_t)cells, s2d);
+    stem_panel_kernel<<<grid, 256, 0, stream>>>(s2d, ho, wo, yd, xd, static_cast<uint2 *>(d_out));
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(s2d, stream);
+    VSC_CUDA_CHECK(e);
+    vsc::count_launch(2);
     return VSC_OK;
 }
 extern "C" int vsc_im2col3x3(const void *d_in, int32_t n, int32_t h, int32_t w, int32_t c, int32_t stride, void *d_out,

@@ -645,13 +645,15 @@ __global__ void __launch_bounds__(kT2Threads, 8) tn_dp_kernel(const Batch b, con
 #pragma unroll
         for (int u = 0; u < kAhead; ++u) pre[u] = load_rec(&rec[min(q + u, last_row) * K + my_rank]);
         __syncwarp();
-        for (bool done = false; !done;) {
+        for (;;) {
+            // the exit test runs once per kAhead steps (an early exit inside the unrolled body brings back the
+            // register moves behind the prefetch loads); the few extra steps are predicated off
+            if (!__any_sync(kFullMask, sweeping && q < lq && (q <= q_last || q <= last_changed + step - 1))) break;
 #pragma unroll
             for (int u = 0; u < kAhead; ++u) {
                 // once `on` turns false for an octet it stays false (nothing can update last_changed), so the
                 // register rotation only has to be right while the octet is running
                 const bool on = sweeping && q < lq && (q <= q_last || q <= last_changed + step - 1);
-                if (!__any_sync(kFullMask, on)) { done = true; break; }
                 const Rec cur = pre[u];
                 pre[u] = load_rec(&rec[min(q + kAhead, last_row) * K + my_rank]);
                 const int v = q * K + sub;

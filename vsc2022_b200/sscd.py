@@ -20,15 +20,21 @@ def _sp(torch, dev):
 class _Conv:
     """A convolution with BatchNorm folded in: bf16 weight panel [cout][k], fp32 bias [cout]."""
 
-    def __init__(self, torch, conv, bn, device, pad_k: Optional[int] = None):
+    def __init__(self, torch, conv, bn, device, stem_s2d: bool = False):
         w = conv.weight.detach().to(device, torch.float32)           # [cout, cin, kh, kw]
         scale = bn.weight.detach().to(device, torch.float32) / torch.sqrt(bn.running_var.detach().to(device, torch.float32) + bn.eps)
         bias = bn.bias.detach().to(device, torch.float32) - bn.running_mean.detach().to(device, torch.float32) * scale
         w = w * scale[:, None, None, None]
         cout, cin, kh, kw = w.shape
-        panel = w.permute(0, 2, 3, 1).reshape(cout, kh * kw * cin)   # k = (ky*kw + kx)*cin + c
-        if pad_k is not None and pad_k > panel.shape[1]:
-            panel = torch.cat([panel, torch.zeros((cout, pad_k - panel.shape[1]), device=device)], dim=1)
+        if stem_s2d:
+            # 7x7 stride-2 filter as a 4x4 stride-1 filter over the 2x2 space-to-depth image (vsc_im2col_stem):
+            # k = ky2*48 + kx2*12 + (dy*2 + dx)*3 + c  <->  tap (2*ky2 + dy, 2*kx2 + dx); row / column 7 are zero.
+            assert (cin, kh, kw) == (3, 7, 7)
+            w8 = torch.zeros((cout, cin, 8, 8), device=device)
+            w8[:, :, :7, :7] = w
+            panel = w8.reshape(cout, cin, 4, 2, 4, 2).permute(0, 2, 4, 3, 5, 1).reshape(cout, 192)
+        else:
+            panel = w.permute(0, 2, 3, 1).reshape(cout, kh * kw * cin)   # k = (ky*kw + kx)*cin + c
         self.weight = panel.to(torch.bfloat16).contiguous()
         self.bias = bias.contiguous()
         self.cout, self.k = cout, self.weight.shape[1]
@@ -41,7 +47,7 @@ class SSCDResNet50:
         torch = _lib.require_cuda()
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         dev = self.device
-        self.stem = _Conv(torch, trunk.conv1, trunk.bn1, dev, pad_k=192)
+        self.stem = _Conv(torch, trunk.conv1, trunk.bn1, dev, stem_s2d=True)
         self.blocks: List[dict] = []
         for layer in (trunk.layer1, trunk.layer2, trunk.layer3, trunk.layer4):
             for blk in layer:
