@@ -69,9 +69,11 @@ struct SharedStorage {
     alignas(1024) uint8_t b[STAGES][BN * BK * 2];
     alignas(8) uint64_t full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2];
     uint32_t tmem_base;
-    // CONV epilogue: per epilogue warp, a 32-row x 64-byte transpose buffer for the residual tile coming in and one
-    // for the bf16 tile going out (16-byte units, XOR-swizzled: see conv_unit)
-    alignas(16) uint4 stage_in[8][128], stage_out[8][128];
+    // CONV epilogue, per epilogue warp: a 32-row x 64-byte transpose buffer (16-byte units, XOR-swizzled: see
+    // conv_unit) used first for the residual chunk coming in, then for the bf16 chunk going out; and the folded
+    // BatchNorm bias of the warp's (up to four) 32-column chunks
+    alignas(16) uint4 stage[8][128];
+    alignas(16) float bias_s[8][4 * 32];
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -255,23 +257,23 @@ __device__ __forceinline__ void conv_residual_fetch(const GemmArgs &g, int64_t r
 }
 
 __device__ __forceinline__ void conv_epilogue_chunk(const GemmArgs &g, int64_t row0, int64_t col0, int lane,
-                                                    const uint32_t (&acc)[32], const uint4 (&res)[4], uint4 *stage_in,
-                                                    uint4 *stage_out) {
+                                                    const uint32_t (&acc)[32], const uint4 (&res)[4],
+                                                    const float *bias_chunk, uint4 *stage) {
     float v[32];
-    const float4 *b4 = reinterpret_cast<const float4 *>(g.bias + col0);   // same address in every lane: one broadcast
+    const float4 *b4 = reinterpret_cast<const float4 *>(bias_chunk);   // shared memory, same address in every lane
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-        const float4 b = __ldg(b4 + q);
+        const float4 b = b4[q];
         v[q * 4 + 0] = __uint_as_float(acc[q * 4 + 0]) + b.x; v[q * 4 + 1] = __uint_as_float(acc[q * 4 + 1]) + b.y;
         v[q * 4 + 2] = __uint_as_float(acc[q * 4 + 2]) + b.z; v[q * 4 + 3] = __uint_as_float(acc[q * 4 + 3]) + b.w;
     }
     if (g.residual) {
 #pragma unroll
-        for (int it = 0; it < 4; ++it) stage_in[conv_unit(it * 8 + (lane >> 2), lane & 3)] = res[it];
+        for (int it = 0; it < 4; ++it) stage[conv_unit(it * 8 + (lane >> 2), lane & 3)] = res[it];
         __syncwarp();
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const uint4 r = stage_in[conv_unit(lane, q)];
+            const uint4 r = stage[conv_unit(lane, q)];
             const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
@@ -279,6 +281,7 @@ __device__ __forceinline__ void conv_epilogue_chunk(const GemmArgs &g, int64_t r
                 v[q * 8 + 2 * t + 1] += __uint_as_float(w[t] & 0xFFFF0000u);
             }
         }
+        __syncwarp();   // every lane has its residual row: the buffer may be overwritten
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -290,16 +293,16 @@ __device__ __forceinline__ void conv_epilogue_chunk(const GemmArgs &g, int64_t r
             const __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
             w[t] = *reinterpret_cast<const uint32_t *>(&p);
         }
-        stage_out[conv_unit(lane, q)] = make_uint4(w[0], w[1], w[2], w[3]);
+        stage[conv_unit(lane, q)] = make_uint4(w[0], w[1], w[2], w[3]);
     }
     __syncwarp();
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
         const int r = it * 8 + (lane >> 2);
         const int64_t row = row0 + r;
-        if (row < g.M) reinterpret_cast<uint4 *>(g.out_bf16 + row * g.ldc + col0)[lane & 3] = stage_out[conv_unit(r, lane & 3)];
+        if (row < g.M) reinterpret_cast<uint4 *>(g.out_bf16 + row * g.ldc + col0)[lane & 3] = stage[conv_unit(r, lane & 3)];
     }
-    __syncwarp();   // both buffers are free again
+    __syncwarp();   // the buffer is free again
 }
 
 template <int EPI, int BN>
@@ -376,6 +379,7 @@ __global__ void __launch_bounds__(EPI == 4 ? kThreadsConv : kThreads, 1) gemm_ke
     } else {
         // ===== epilogue warps: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32) =====
         const int quad = warp & 3;
+        int64_t bias_blk = -1;
         uint32_t it = 0;
         for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
@@ -394,12 +398,21 @@ __global__ void __launch_bounds__(EPI == 4 ? kThreadsConv : kThreads, 1) gemm_ke
                 const int epi = warp - 2, first = epi >> 2;   // two warps per lane quadrant: even / odd chunks
                 uint4 res[4] = {}, res_next[4] = {};
                 if (g.residual && first < chunks) conv_residual_fetch(g, row0, colb + first * 32, lane, res);
+                if (n_blk != bias_blk) {   // tiles run m-fastest: the bias columns change only every m_tiles tiles
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int c = first + 2 * j;
+                        if (c < chunks) sm.bias_s[epi][j * 32 + lane] = g.bias[colb + c * 32 + lane];
+                    }
+                    bias_blk = n_blk;
+                    __syncwarp();
+                }
 #pragma unroll 1
                 for (int c = first; c < chunks; c += 2) {
                     if (g.residual && c + 2 < chunks) conv_residual_fetch(g, row0, colb + (c + 2) * 32, lane, res_next);
                     uint32_t v[32];
                     tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + c * 32, v);
-                    conv_epilogue_chunk(g, row0, colb + c * 32, lane, v, res, sm.stage_in[epi], sm.stage_out[epi]);
+                    conv_epilogue_chunk(g, row0, colb + c * 32, lane, v, res, &sm.bias_s[epi][(c >> 1) * 32], sm.stage[epi]);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) res[i] = res_next[i];
                 }

@@ -18,7 +18,7 @@ namespace {
 //         mode 0: uint8 NHWC pixels, normalised here ((x/255 - mean)/std, inference_impl.py:39-69);
 //         mode 1: float32 NCHW tensor that is already normalised (what the reference model receives).
 // Step 2 (stem_panel_kernel): panel row of output pixel (oy, ox) = for ky2 = 0..3 the 96 CONTIGUOUS bytes
-//         S[n][oy+ky2][ox..ox+3][0..11]: a pure copy in 8-byte units.  K index = ky2*48 + kx2*12 + (dy*2+dx)*3 + c
+//         S[n][oy+ky2][ox..ox+3][0..11]: a pure copy (16-byte stores, 8-byte aligned loads).  K index = ky2*48 + kx2*12 + (dy*2+dx)*3 + c
 //         <-> filter tap (ky, kx) = (2*ky2+dy, 2*kx2+dx); taps with ky = 7 or kx = 7 carry zero weights.  K = 192.
 // (The first version wrote the panel element-wise from the uint8 frame: 1.3 ms per 128 frames, 8x the HBM time.)
 template <int MODE>
@@ -57,16 +57,18 @@ __global__ void __launch_bounds__(256) stem_s2d_kernel(const void *__restrict__ 
         o[q] = make_uint2(v[q * 4] | ((uint32_t)v[q * 4 + 1] << 16), v[q * 4 + 2] | ((uint32_t)v[q * 4 + 3] << 16));
 }
 
-constexpr int kStemUnits = 48;   // 192 bf16 = 48 x 8 bytes per panel row
+constexpr int kStemUnits = 24;   // 192 bf16 = 24 x 16 bytes per panel row
 __global__ void __launch_bounds__(256) stem_panel_kernel(const uint2 *__restrict__ s2d, int ho, int wo, int yd, int xd,
-                                                         uint2 *__restrict__ out) {
+                                                         uint4 *__restrict__ out) {
     const int row = blockIdx.x;                       // img*ho + oy
     const int img = row / ho, oy = row - img * ho;
     const int t = blockIdx.y * blockDim.x + threadIdx.x;
     const int ox = t / kStemUnits, u = t - ox * kStemUnits;
     if (ox >= wo) return;
-    const int ky2 = u / 12, part = u - ky2 * 12;
-    out[((size_t)row * wo + ox) * kStemUnits + u] = s2d[(((size_t)img * yd + oy + ky2) * xd + ox) * 3 + part];
+    const int ky2 = u / 6, part = u - ky2 * 6;        // 6 x 16 bytes per 96-byte run; cells are 8-byte aligned
+    const uint2 *src = s2d + (((size_t)img * yd + oy + ky2) * xd + ox) * 3 + part * 2;
+    const uint2 lo = src[0], hi = src[1];
+    out[((size_t)row * wo + ox) * kStemUnits + u] = make_uint4(lo.x, lo.y, hi.x, hi.y);
 }
 
 // ---- 3x3 pad 1, stride s: panel [n*ho*wo][9*c], K index = (ky*3 + kx)*c + ch.  One thread moves 8 channels (16 B)
@@ -174,7 +176,7 @@ extern "C" int vsc_im2col_stem(const void *d_in, int32_t mode, int32_t n, int32_
     VSC_CUDA_CHECK(cudaMallocAsync(&s2d, (size_t)cells * 24, stream));
     if (mode == 0) stem_s2d_kernel<0><<<blocks(cells), 256, 0, stream>>>(d_in, n, h, w, yd, xd, (uint32_t)cells, s2d);
     else stem_s2d_kernel<1><<<blocks(cells), 256, 0, stream>>>(d_in, n, h, w, yd, xd, (uint32_t)cells, s2d);
-    stem_panel_kernel<<<grid, 256, 0, stream>>>(s2d, ho, wo, yd, xd, static_cast<uint2 *>(d_out));
+    stem_panel_kernel<<<grid, 256, 0, stream>>>(s2d, ho, wo, yd, xd, static_cast<uint4 *>(d_out));
     cudaError_t e = cudaGetLastError();
     cudaFreeAsync(s2d, stream);
     VSC_CUDA_CHECK(e);
