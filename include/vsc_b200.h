@@ -116,6 +116,12 @@ int vsc_gemm_emit(const void *d_a, int64_t m, const void *d_b, int64_t n, int32_
 /* out[m][n] (bf16, row stride ldc) = relu?(A[m][:] . W[n][:] + bias[n] + residual[m][n]); n % 32 == 0 */
 int vsc_gemm_conv(const void *d_a, int64_t m, const void *d_w, int64_t n, int32_t k, const float *d_bias,
                   const void *d_residual, int32_t relu, void *d_out_bf16, int64_t ldc, vsc_stream_t stream);
+/* 3x3 / pad 1 / stride 1|2 convolution + folded-BN bias (+ residual) (+ ReLU) straight from the NHWC bf16 tensor
+ * [n][h][w][c] (implicit GEMM: TMA im2col loads, no patch matrix).  c % 64 == 0, cout % 32 == 0; weights
+ * [cout][9*c] with K index = (ky*3 + kx)*c + channel; out [n*ho*wo][cout] bf16. */
+int vsc_conv3x3(const void *d_in, int32_t n, int32_t h, int32_t w, int32_t c, int32_t stride, const void *d_w,
+                int32_t cout, const float *d_bias, const void *d_residual, int32_t relu, void *d_out_bf16,
+                vsc_stream_t stream);
 /* fp32 out[m][n] = A . W^T + bias[n] (projection head) */
 int vsc_gemm_linear(const void *d_a, int64_t m, const void *d_w, int64_t n, int32_t k, const float *d_bias, float *d_out,
                     int64_t ldc, vsc_stream_t stream);

@@ -81,6 +81,11 @@ def test_primitives_against_torch():
         assert torch.equal(cols.float(), ucols)
         pre = ucols @ panel.float().T + bias
         assert torch.equal(out, torch.relu(pre + res.float()).to(torch.bfloat16))
+        # implicit GEMM (TMA im2col loads straight from the NHWC tensor): identical result, no patch matrix
+        out2 = torch.empty_like(out)
+        _lib.check(lib.vsc_conv3x3(x.data_ptr(), n, h, w, c, stride, panel.data_ptr(), cout, bias.data_ptr(),
+                                   res.data_ptr(), 1, out2.data_ptr(), sp), "conv3x3")
+        assert torch.equal(out2, out)
         cudnn = F.conv2d(x.float().permute(0, 3, 1, 2), wt, bias, stride=stride, padding=1).permute(0, 2, 3, 1).reshape(-1, cout)
         torch.testing.assert_close(cudnn, pre, rtol=0, atol=1e-4)
     ho, wo = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1

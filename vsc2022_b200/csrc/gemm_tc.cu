@@ -61,6 +61,9 @@ struct GemmArgs {
     float *out_score; int32_t *out_row, *out_col;
     unsigned long long capacity;
     unsigned long long *counters;  // [0] entries claimed (may exceed capacity), [1] hits beyond count_thr
+    // implicit 3x3 convolution (A operand loaded by TMA in im2col mode from the NHWC activation tensor):
+    // output extent, traversal stride and 64-channel blocks per filter tap
+    int conv_ho, conv_wo, conv_stride, conv_cblocks;
 };
 
 template <int BN>
@@ -100,6 +103,16 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+// TMA im2col load: 128 consecutive output pixels (W fastest, then H, then image; padding is zero-filled by the
+// hardware) x 64 channels of filter tap (off_w, off_h), starting at base pixel (w, h, n) of the bounding box.
+__device__ __forceinline__ void tma_load_im2col(void *dst, const CUtensorMap *map, int c, int w, int h, int n,
+                                                uint16_t off_w, uint16_t off_h, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%2, %3, %4, %5}], [%6], {%7, %8};"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(c), "r"(w), "r"(h), "r"(n), "r"(smem_u32(bar)), "h"(off_w), "h"(off_h)
+        : "memory");
 }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -305,7 +318,7 @@ __device__ __forceinline__ void conv_epilogue_chunk(const GemmArgs &g, int64_t r
     __syncwarp();   // the buffer is free again
 }
 
-template <int EPI, int BN>
+template <int EPI, int BN, bool IM2COL = false>
 __global__ void __launch_bounds__(EPI == 4 ? kThreadsConv : kThreads, 1) gemm_kernel(const __grid_constant__ CUtensorMap tma_a,
                                                            const __grid_constant__ CUtensorMap tma_b,
                                                            const GemmArgs g) {
@@ -341,9 +354,21 @@ __global__ void __launch_bounds__(EPI == 4 ? kThreadsConv : kThreads, 1) gemm_ke
             int stage = 0; uint32_t phase = 0;
             for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
                 const int m_blk = (int)(t % m_tiles), n_blk = (int)(t / m_tiles);
+                int px = 0, py = 0, pn = 0, tap = 0, cb = 0;
+                if (IM2COL) {   // first output pixel of the tile -> base pixel of the 3x3 window (pad 1)
+                    const int64_t m0 = (int64_t)m_blk * BM, row = m0 / g.conv_wo;
+                    px = (int)(m0 - row * g.conv_wo) * g.conv_stride - 1;
+                    pn = (int)(row / g.conv_ho);
+                    py = (int)(row - (int64_t)pn * g.conv_ho) * g.conv_stride - 1;
+                }
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(&sm.empty[stage], phase ^ 1);
                     mbar_expect_tx(&sm.full[stage], kStageBytesA + kStageBytesB);
+                    if (IM2COL) {   // K index = (ky*3 + kx)*C + channel
+                        tma_load_im2col(sm.a[stage], &tma_a, cb * BK, px, py, pn, (uint16_t)(tap % 3), (uint16_t)(tap / 3),
+                                        &sm.full[stage]);
+                        if (++cb == g.conv_cblocks) { cb = 0; ++tap; }
+                    } else
                     tma_load_2d(sm.a[stage], &tma_a, kb * BK, m_blk * BM, &sm.full[stage]);
                     tma_load_2d(sm.b[stage], &tma_b, kb * BK, n_blk * BN, &sm.full[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -477,26 +502,57 @@ int make_map(CUtensorMap *map, const void *ptr, int64_t rows, int k, int box_row
     return VSC_OK;
 }
 
-template <int EPI, int BN>
-int launch(const void *a, const void *b, const GemmArgs &g, cudaStream_t stream) {
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                   const cuuint64_t *, const int *, const int *, cuuint32_t, cuuint32_t, const cuuint32_t *,
+                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                   CUtensorMapFloatOOBfill);
+
+// NHWC bf16 activation tensor [n][h][w][c] for a 3x3 / pad 1 / stride s convolution: one load = 128 output pixels x
+// 64 channels of one filter tap, 128-byte swizzle (the same shared-memory image as a tiled 128 x 64 box).
+// Bounding box corners (cuTensorMapEncodeIm2col): lower = -pad, upper = pad - (filter - 1).
+int make_im2col_map(CUtensorMap *map, const void *ptr, int n, int h, int w, int c, int stride) {
+    static EncodeIm2colFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeIm2colFn>(p);
+    }
+    if (!fn) { vsc::set_error("cuTensorMapEncodeIm2col entry point not available"); return VSC_ERR_CUDA; }
+    cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+    cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
+    int lower[2] = {-1, -1}, upper[2] = {-1, -1};
+    cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(ptr), dims, strides, lower, upper,
+                    (cuuint32_t)BK, (cuuint32_t)BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { vsc::set_error("cuTensorMapEncodeIm2col failed (%d)", (int)r); return VSC_ERR_CUDA; }
+    return VSC_OK;
+}
+
+template <int EPI, int BN, bool IM2COL = false>
+int launch(const void *a, const void *b, const GemmArgs &g, cudaStream_t stream, const CUtensorMap *map_a = nullptr) {
     if (g.M <= 0 || g.N <= 0) return VSC_OK;
     if (g.K <= 0 || g.K % BK != 0) { vsc::set_error("gemm: K=%d must be a positive multiple of %d", g.K, BK); return VSC_ERR_INVALID; }
     if ((reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(b) & 15)) {
         vsc::set_error("gemm: operands must be 16-byte aligned"); return VSC_ERR_INVALID;
     }
     CUtensorMap ma, mb;
-    int rc = make_map(&ma, a, g.M, g.K, BM);
+    int rc = VSC_OK;
+    if (map_a) ma = *map_a;
+    else rc = make_map(&ma, a, g.M, g.K, BM);
     if (rc != VSC_OK) return rc;
     rc = make_map(&mb, b, g.N, g.K, BN);
     if (rc != VSC_OK) return rc;
     const size_t smem = sizeof(SharedStorage<BN>) + 1024;
-    VSC_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<EPI, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VSC_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<EPI, BN, IM2COL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 148;
     VSC_CUDA_CHECK(cudaGetDevice(&dev));
     VSC_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int64_t tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
     const int grid = (int)(tiles < sms ? tiles : sms);
-    gemm_kernel<EPI, BN><<<grid, EPI == EPI_CONV ? kThreadsConv : kThreads, smem, stream>>>(ma, mb, g);
+    gemm_kernel<EPI, BN, IM2COL><<<grid, EPI == EPI_CONV ? kThreadsConv : kThreads, smem, stream>>>(ma, mb, g);
     VSC_CUDA_CHECK(cudaGetLastError());
     vsc::count_launch();
     return VSC_OK;
@@ -557,6 +613,31 @@ extern "C" int vsc_gemm_conv(const void *d_a, int64_t m, const void *d_w, int64_
     if (n <= 64) return launch<EPI_CONV, 64>(d_a, d_w, g, stream);
     if (n <= 128) return launch<EPI_CONV, 128>(d_a, d_w, g, stream);
     return launch<EPI_CONV, 256>(d_a, d_w, g, stream);
+}
+
+// 3x3 / pad 1 / stride 1|2 convolution straight from the NHWC bf16 activation tensor (implicit GEMM: no patch
+// matrix in memory).  Weights [cout][9*c] with K index = (ky*3 + kx)*c + channel; out[(n*ho + oy)*wo + ox][cout].
+extern "C" int vsc_conv3x3(const void *d_in, int32_t n, int32_t h, int32_t w, int32_t c, int32_t stride, const void *d_w,
+                           int32_t cout, const float *d_bias, const void *d_residual, int32_t relu, void *d_out_bf16,
+                           vsc_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (c % BK != 0 || cout % 32 != 0 || (stride != 1 && stride != 2) || !d_bias) {
+        vsc::set_error("vsc_conv3x3: need c %% 64 == 0, cout %% 32 == 0, stride in {1,2}, a bias"); return VSC_ERR_INVALID;
+    }
+    if (n <= 0) return VSC_OK;
+    const int ho = (h + 2 - 3) / stride + 1, wo = (w + 2 - 3) / stride + 1;
+    if ((reinterpret_cast<uintptr_t>(d_in) & 15) != 0) { vsc::set_error("vsc_conv3x3: input must be 16-byte aligned"); return VSC_ERR_INVALID; }
+    CUtensorMap ma;
+    int rc = make_im2col_map(&ma, d_in, n, h, w, c, stride);
+    if (rc != VSC_OK) return rc;
+    GemmArgs g = {};
+    g.M = (int64_t)n * ho * wo; g.N = cout; g.K = 9 * c; g.bias = d_bias;
+    g.residual = static_cast<const __nv_bfloat16 *>(d_residual); g.relu = relu;
+    g.out_bf16 = static_cast<__nv_bfloat16 *>(d_out_bf16); g.ldc = cout;
+    g.conv_ho = ho; g.conv_wo = wo; g.conv_stride = stride; g.conv_cblocks = c / BK;
+    if (cout <= 64) return launch<EPI_CONV, 64, true>(d_in, d_w, g, stream, &ma);
+    if (cout <= 128) return launch<EPI_CONV, 128, true>(d_in, d_w, g, stream, &ma);
+    return launch<EPI_CONV, 256, true>(d_in, d_w, g, stream, &ma);
 }
 
 // fp32 out[m][n] = A . W^T + bias[n]  (the SSCD projection head)
