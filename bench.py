@@ -132,6 +132,36 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def sscd_layerwise_bound(peaks, hw=288):
+    """Frames/s bound of the ResNet-50 trunk when every convolution runs at max(tensor time, HBM time): bf16 NHWC
+    activations read and written once per layer (implicit GEMM, no cross-layer fusion).  34 of the 53 convolutions
+    are HBM-bound at 288x288, so this -- not the 13.5 GFLOP/frame tensor bound -- is the ceiling of a per-layer design."""
+    t_peak, h_peak = peaks["bf16_tflops"] * 1e12, peaks["hbm_gbs"] * 1e9
+    total = [0.0]
+
+    def conv(cin, cout, k, s, hin, residual=False):
+        hout = (hin + 2 * (k // 2) - k) // s + 1
+        flops = 2.0 * cin * cout * k * k * hout * hout
+        byts = 2.0 * (cin * hin * hin + cout * hout * hout * (2 if residual else 1))
+        total[0] += max(flops / t_peak, byts / h_peak)
+        return hout
+
+    h = conv(3, 64, 7, 2, hw)
+    total[0] += 2.0 * 64 * (h * h + ((h + 1) // 2) ** 2) / h_peak   # max pool
+    h = (h + 2 - 3) // 2 + 1
+    cin = 64
+    for mid, blocks, stride in ((64, 3, 1), (128, 4, 2), (256, 6, 2), (512, 3, 2)):
+        for b in range(blocks):
+            s = stride if b == 0 else 1
+            if b == 0:
+                conv(cin, mid * 4, 1, s, h)
+            conv(cin, mid, 1, 1, h)
+            h2 = conv(mid, mid, 3, s, h)
+            conv(mid, mid * 4, 1, 1, h2, residual=True)
+            h, cin = h2, mid * 4
+    return 1.0 / total[0]
+
+
 def stage_numbers(dev, peaks):
     """Secondary measurements of the other two stages of the path (N=1 only; device-timed, synthetic data)."""
     import torch
@@ -193,11 +223,15 @@ def stage_numbers(dev, peaks):
     torch.cuda.synchronize(dev)
     ms = e0.elapsed_time(e1)
     tf = n * 13.513e9 / ms / 1e9
+    bound = sscd_layerwise_bound(peaks)
     out["sscd_resnet50_inference"] = {
         "workload": "c2 slice: 2048 synthetic 288x288 uint8 frames, batch 128, bf16 (full config: 10k frames)",
         "ms": ms, "frames_per_s": n / ms * 1e3,
         "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                     "frac": tf / peaks["bf16_tflops"], "algorithmic_flops_per_frame": 13.513e9}}
+                     "frac": tf / peaks["bf16_tflops"], "algorithmic_flops_per_frame": 13.513e9},
+        "layerwise_bound": {"frames_per_s": bound, "frac": n / ms * 1e3 / bound,
+                            "note": "sum over the 53 convolutions of max(tensor time, HBM time of its bf16 "
+                                    "activations); 34 of them are HBM-bound at 288x288"}}
     return out
 
 
@@ -320,7 +354,7 @@ def run_gpu(args, rank, local_rank, world):
 
 # dram__bytes_read.sum + dram__bytes_write.sum over the three kernels of one call, from the ncu capture
 # committed under profiles/ (profiles/r01_tn_launches.csv); None until a capture exists.
-TRAFFIC_BYTES_PER_CALL = 3.80e9  # tn_topk 2.917+0.209, tn_edges 0.196+0.055, tn_dp 0.319+0.115 GB (profiles/r01_tn_summary.md)
+TRAFFIC_BYTES_PER_CALL = 3.88e9  # tn_topk 3.014+0.213, tn_edges 0.152+0.058, tn_dp 0.326+0.116 GB (profiles/r01_tn_summary.md)
 
 
 def main():

@@ -125,15 +125,21 @@ int vsc_conv3x3(const void *d_in, int32_t n, int32_t h, int32_t w, int32_t c, in
 /* fp32 out[m][n] = A . W^T + bias[n] (projection head) */
 int vsc_gemm_linear(const void *d_a, int64_t m, const void *d_w, int64_t n, int32_t k, const float *d_bias, float *d_out,
                     int64_t ldc, vsc_stream_t stream);
-/* 7x7/2 stem patches [n*ho*wo][192]; mode 0: uint8 NHWC pixels (normalised here), 1: float32 NCHW normalised.
- * K index = ky2*48 + kx2*12 + (dy*2+dx)*3 + c for filter tap (2*ky2+dy, 2*kx2+dx) (space-to-depth order; taps with
- * row or column 7 are padding and must carry zero weights) */
-int vsc_im2col_stem(const void *d_in, int32_t mode, int32_t n, int32_t h, int32_t w, void *d_out, vsc_stream_t stream);
+/* Stem: 7x7 / stride 2 / pad 3 convolution on 3 channels + folded-BN bias + ReLU.  mode 0: uint8 NHWC pixels
+ * (normalised here), 1: float32 NCHW normalised.  Weights [64][256] with K index = ky2*64 + kx2*16 + (dy*2+dx)*3 + c
+ * for filter tap (2*ky2+dy, 2*kx2+dx) (space-to-depth order; taps with row / column 7 and channels 12..15 of a
+ * group are padding and must be zero).  Output bf16 [n][ho+3][wo+3][64]: rows < ho, columns < wo are the result. */
+int vsc_conv_stem(const void *d_in, int32_t mode, int32_t n, int32_t h, int32_t w, const void *d_w, const float *d_bias,
+                  void *d_out_bf16, vsc_stream_t stream);
+/* the GEMM half of vsc_conv_stem on a prepared space-to-depth image (pixels cells of 16 bf16, +4 cells readable) */
+int vsc_gemm_stem(const void *d_s2d, int64_t pixels, int64_t row_shift, const void *d_w, const float *d_bias,
+                  void *d_out_bf16, vsc_stream_t stream);
 /* 3x3 pad-1 patches [n*ho*wo][9*c] of an NHWC bf16 tensor, stride 1 or 2 */
 int vsc_im2col3x3(const void *d_in, int32_t n, int32_t h, int32_t w, int32_t c, int32_t stride, void *d_out,
                   vsc_stream_t stream);
 int vsc_subsample2(const void *d_in, int32_t n, int32_t h, int32_t w, int32_t c, void *d_out, vsc_stream_t stream);
-int vsc_maxpool3x3s2(const void *d_in, int32_t n, int32_t h, int32_t w, int32_t c, void *d_out, vsc_stream_t stream);
+int vsc_maxpool3x3s2(const void *d_in, int32_t n, int32_t h, int32_t w, int32_t c, int32_t row_pitch, int32_t img_rows,
+                     void *d_out, vsc_stream_t stream);
 /* GeM pooling over hw pixels: (mean clamp(x, eps)^p)^(1/p), bf16 [n][c] out */
 int vsc_gem_pool(const void *d_in, int32_t n, int32_t hw, int32_t c, float p, float eps, void *d_out, vsc_stream_t stream);
 

@@ -90,6 +90,6 @@ def test_primitives_against_torch():
         torch.testing.assert_close(cudnn, pre, rtol=0, atol=1e-4)
     ho, wo = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
     mp = torch.empty((n * ho * wo, c), dtype=torch.bfloat16, device=dev)
-    _lib.check(lib.vsc_maxpool3x3s2(x.data_ptr(), n, h, w, c, mp.data_ptr(), sp), "maxpool")
+    _lib.check(lib.vsc_maxpool3x3s2(x.data_ptr(), n, h, w, c, w, h, mp.data_ptr(), sp), "maxpool")
     ref = F.max_pool2d(x.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).reshape(-1, c).to(torch.bfloat16)
     assert torch.equal(mp, ref)

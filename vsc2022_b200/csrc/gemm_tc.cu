@@ -38,6 +38,7 @@ constexpr int kThreadsConv = 320;   // 8 epilogue warps
 __host__ __device__ constexpr int epi_warps(int epi) { return epi == 4 /* EPI_CONV */ ? 8 : 4; }
 constexpr uint32_t kStageBytesA = BM * BK * 2;
 
+enum ALoad { A_TILED = 0, A_IM2COL = 1, A_SHIFT = 2 };  // how the producer fetches the A tile of a k-block
 enum Epilogue { EPI_STORE = 0, EPI_ROWMAX = 1, EPI_EMIT = 2, EPI_ROWARGMAX = 3, EPI_CONV = 4 };
 
 struct GemmArgs {
@@ -64,6 +65,8 @@ struct GemmArgs {
     // implicit 3x3 convolution (A operand loaded by TMA in im2col mode from the NHWC activation tensor):
     // output extent, traversal stride and 64-channel blocks per filter tap
     int conv_ho, conv_wo, conv_stride, conv_cblocks;
+    // A_SHIFT (stem): k-block kb reads rows m + kb * a_row_shift of an overlapping-row view (see vsc_conv_stem)
+    int64_t a_row_shift;
 };
 
 template <int BN>
@@ -318,7 +321,7 @@ __device__ __forceinline__ void conv_epilogue_chunk(const GemmArgs &g, int64_t r
     __syncwarp();   // the buffer is free again
 }
 
-template <int EPI, int BN, bool IM2COL = false>
+template <int EPI, int BN, int ALOAD = A_TILED>
 __global__ void __launch_bounds__(EPI == 4 ? kThreadsConv : kThreads, 1) gemm_kernel(const __grid_constant__ CUtensorMap tma_a,
                                                            const __grid_constant__ CUtensorMap tma_b,
                                                            const GemmArgs g) {
@@ -355,7 +358,7 @@ __global__ void __launch_bounds__(EPI == 4 ? kThreadsConv : kThreads, 1) gemm_ke
             for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
                 const int m_blk = (int)(t % m_tiles), n_blk = (int)(t / m_tiles);
                 int px = 0, py = 0, pn = 0, tap = 0, cb = 0;
-                if (IM2COL) {   // first output pixel of the tile -> base pixel of the 3x3 window (pad 1)
+                if (ALOAD == A_IM2COL) {   // first output pixel of the tile -> base pixel of the 3x3 window (pad 1)
                     const int64_t m0 = (int64_t)m_blk * BM, row = m0 / g.conv_wo;
                     px = (int)(m0 - row * g.conv_wo) * g.conv_stride - 1;
                     pn = (int)(row / g.conv_ho);
@@ -364,7 +367,9 @@ __global__ void __launch_bounds__(EPI == 4 ? kThreadsConv : kThreads, 1) gemm_ke
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(&sm.empty[stage], phase ^ 1);
                     mbar_expect_tx(&sm.full[stage], kStageBytesA + kStageBytesB);
-                    if (IM2COL) {   // K index = (ky*3 + kx)*C + channel
+                    if (ALOAD == A_SHIFT) {
+                        tma_load_2d(sm.a[stage], &tma_a, 0, (int)((int64_t)m_blk * BM + kb * g.a_row_shift), &sm.full[stage]);
+                    } else if (ALOAD == A_IM2COL) {   // K index = (ky*3 + kx)*C + channel
                         tma_load_im2col(sm.a[stage], &tma_a, cb * BK, px, py, pn, (uint16_t)(tap % 3), (uint16_t)(tap / 3),
                                         &sm.full[stage]);
                         if (++cb == g.conv_cblocks) { cb = 0; ++tap; }
@@ -531,7 +536,7 @@ int make_im2col_map(CUtensorMap *map, const void *ptr, int n, int h, int w, int 
     return VSC_OK;
 }
 
-template <int EPI, int BN, bool IM2COL = false>
+template <int EPI, int BN, int ALOAD = A_TILED>
 int launch(const void *a, const void *b, const GemmArgs &g, cudaStream_t stream, const CUtensorMap *map_a = nullptr) {
     if (g.M <= 0 || g.N <= 0) return VSC_OK;
     if (g.K <= 0 || g.K % BK != 0) { vsc::set_error("gemm: K=%d must be a positive multiple of %d", g.K, BK); return VSC_ERR_INVALID; }
@@ -546,13 +551,13 @@ int launch(const void *a, const void *b, const GemmArgs &g, cudaStream_t stream,
     rc = make_map(&mb, b, g.N, g.K, BN);
     if (rc != VSC_OK) return rc;
     const size_t smem = sizeof(SharedStorage<BN>) + 1024;
-    VSC_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<EPI, BN, IM2COL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VSC_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<EPI, BN, ALOAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 148;
     VSC_CUDA_CHECK(cudaGetDevice(&dev));
     VSC_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int64_t tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
     const int grid = (int)(tiles < sms ? tiles : sms);
-    gemm_kernel<EPI, BN, IM2COL><<<grid, EPI == EPI_CONV ? kThreadsConv : kThreads, smem, stream>>>(ma, mb, g);
+    gemm_kernel<EPI, BN, ALOAD><<<grid, EPI == EPI_CONV ? kThreadsConv : kThreads, smem, stream>>>(ma, mb, g);
     VSC_CUDA_CHECK(cudaGetLastError());
     vsc::count_launch();
     return VSC_OK;
@@ -635,9 +640,31 @@ extern "C" int vsc_conv3x3(const void *d_in, int32_t n, int32_t h, int32_t w, in
     g.residual = static_cast<const __nv_bfloat16 *>(d_residual); g.relu = relu;
     g.out_bf16 = static_cast<__nv_bfloat16 *>(d_out_bf16); g.ldc = cout;
     g.conv_ho = ho; g.conv_wo = wo; g.conv_stride = stride; g.conv_cblocks = c / BK;
-    if (cout <= 64) return launch<EPI_CONV, 64, true>(d_in, d_w, g, stream, &ma);
-    if (cout <= 128) return launch<EPI_CONV, 128, true>(d_in, d_w, g, stream, &ma);
-    return launch<EPI_CONV, 256, true>(d_in, d_w, g, stream, &ma);
+    if (cout <= 64) return launch<EPI_CONV, 64, A_IM2COL>(d_in, d_w, g, stream, &ma);
+    if (cout <= 128) return launch<EPI_CONV, 128, A_IM2COL>(d_in, d_w, g, stream, &ma);
+    return launch<EPI_CONV, 256, A_IM2COL>(d_in, d_w, g, stream, &ma);
+}
+
+// The stem GEMM (vsc_conv_stem in sscd_ops.cu): A rows are 64-element windows that start every 16 elements of the
+// space-to-depth image, i.e. a 2D view whose row stride (32 B) is smaller than its row length (128 B).
+extern "C" int vsc_gemm_stem(const void *d_s2d, int64_t pixels, int64_t row_shift, const void *d_w, const float *d_bias,
+                             void *d_out_bf16, vsc_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { vsc::set_error("cuTensorMapEncodeTiled entry point not available"); return VSC_ERR_CUDA; }
+    CUtensorMap ma;
+    cuuint64_t dims[2] = {64, (cuuint64_t)pixels};
+    cuuint64_t strides[1] = {32};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(&ma, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(d_s2d), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { vsc::set_error("cuTensorMapEncodeTiled (overlapping stem rows) failed (%d)", (int)r); return VSC_ERR_CUDA; }
+    GemmArgs g = {};
+    g.M = pixels; g.N = 64; g.K = 256; g.bias = d_bias; g.relu = 1;
+    g.out_bf16 = static_cast<__nv_bfloat16 *>(d_out_bf16); g.ldc = 64; g.a_row_shift = row_shift;
+    return launch<EPI_CONV, 64, A_SHIFT>(d_s2d, d_w, g, stream, &ma);
 }
 
 // fp32 out[m][n] = A . W^T + bias[n]  (the SSCD projection head)

@@ -28,12 +28,14 @@ class _Conv:
         w = w * scale[:, None, None, None]
         cout, cin, kh, kw = w.shape
         if stem_s2d:
-            # 7x7 stride-2 filter as a 4x4 stride-1 filter over the 2x2 space-to-depth image (vsc_im2col_stem):
-            # k = ky2*48 + kx2*12 + (dy*2 + dx)*3 + c  <->  tap (2*ky2 + dy, 2*kx2 + dx); row / column 7 are zero.
+            # 7x7 stride-2 filter as a 4x4 stride-1 filter over the 2x2 space-to-depth image (vsc_conv_stem):
+            # k = ky2*64 + kx2*16 + (dy*2 + dx)*3 + c  <->  tap (2*ky2 + dy, 2*kx2 + dx); row / column 7 and the
+            # four padding channels of every 16-channel group are zero.
             assert (cin, kh, kw) == (3, 7, 7)
             w8 = torch.zeros((cout, cin, 8, 8), device=device)
             w8[:, :, :7, :7] = w
-            panel = w8.reshape(cout, cin, 4, 2, 4, 2).permute(0, 2, 4, 3, 5, 1).reshape(cout, 192)
+            taps = w8.reshape(cout, cin, 4, 2, 4, 2).permute(0, 2, 4, 3, 5, 1).reshape(cout, 4, 4, 12)
+            panel = torch.cat([taps, torch.zeros((cout, 4, 4, 4), device=device)], dim=3).reshape(cout, 256)
         else:
             panel = w.permute(0, 2, 3, 1).reshape(cout, kh * kw * cin)   # k = (ky*kw + kx)*cin + c
         self.weight = panel.to(torch.bfloat16).contiguous()
@@ -115,13 +117,15 @@ class SSCDResNet50:
                 frames = frames.to(torch.float32)
             frames = frames.contiguous()
             ho, wo = (h + 6 - 7) // 2 + 1, (w + 6 - 7) // 2 + 1
-            panel = torch.empty((n * ho * wo, 192), dtype=torch.bfloat16, device=dev)
-            _lib.check(lib.vsc_im2col_stem(frames.data_ptr(), mode, n, h, w, panel.data_ptr(), _sp(torch, dev)), "vsc_im2col_stem")
-            x = self._conv(panel, n * ho * wo, self.stem, relu=True)
+            # stem output lives in the padded (ho+3) x (wo+3) grid of the space-to-depth GEMM (vsc_conv_stem)
+            x = torch.empty((n * (ho + 3) * (wo + 3), 64), dtype=torch.bfloat16, device=dev)
+            _lib.check(lib.vsc_conv_stem(frames.data_ptr(), mode, n, h, w, self.stem.weight.data_ptr(),
+                                         self.stem.bias.data_ptr(), x.data_ptr(), _sp(torch, dev)), "vsc_conv_stem")
             h, w, c = ho, wo, 64
             ho, wo = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
             pooled = torch.empty((n * ho * wo, c), dtype=torch.bfloat16, device=dev)
-            _lib.check(lib.vsc_maxpool3x3s2(x.data_ptr(), n, h, w, c, pooled.data_ptr(), _sp(torch, dev)), "vsc_maxpool3x3s2")
+            _lib.check(lib.vsc_maxpool3x3s2(x.data_ptr(), n, h, w, c, w + 3, h + 3, pooled.data_ptr(), _sp(torch, dev)),
+                       "vsc_maxpool3x3s2")
             x, h, w = pooled, ho, wo
             for blk in self.blocks:
                 stride = blk["c2"].stride
