@@ -272,6 +272,17 @@ __device__ __forceinline__ void conv_residual_fetch(const GemmArgs &g, int64_t r
     }
 }
 
+// Pull the residual rows of a whole tile (this warp's chunks) from HBM into L2 one tile ahead: the register
+// prefetch above only reaches one chunk (~0.5 us) ahead, less than an HBM round trip under load.
+__device__ __forceinline__ void conv_residual_prefetch_l2(const GemmArgs &g, int64_t row0, int64_t colb, int first,
+                                                          int chunks, int lane) {
+    const int64_t row = row0 + lane;
+    if (row >= g.M) return;
+    const __nv_bfloat16 *p = g.residual + row * g.ldc + colb;
+    for (int c = first; c < chunks; c += 2)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p + c * 32));
+}
+
 __device__ __forceinline__ void conv_epilogue_chunk(const GemmArgs &g, int64_t row0, int64_t col0, int lane,
                                                     const uint32_t (&acc)[32], const uint4 (&res)[4],
                                                     const float *bias_chunk, uint4 *stage) {
@@ -426,6 +437,11 @@ __global__ void __launch_bounds__(EPI == 4 ? kThreadsConv : kThreads, 1) gemm_ke
                 const int64_t row0 = m_blk * BM + quad * 32, colb = n_blk * BN;
                 const int chunks = (int)((g.N - colb < BN ? g.N - colb : BN) / 32);
                 const int epi = warp - 2, first = epi >> 2;   // two warps per lane quadrant: even / odd chunks
+                if (g.residual && t + gridDim.x < tiles) {    // next tile of this CTA: its residual goes to L2 now
+                    const int64_t t2 = t + gridDim.x, m2 = t2 % m_tiles, n2 = t2 / m_tiles;
+                    conv_residual_prefetch_l2(g, m2 * BM + quad * 32, n2 * BN, first,
+                                              (int)((g.N - n2 * BN < BN ? g.N - n2 * BN : BN) / 32), lane);
+                }
                 uint4 res[4] = {}, res_next[4] = {};
                 if (g.residual && first < chunks) conv_residual_fetch(g, row0, colb + first * 32, lane, res);
                 if (n_blk != bias_blk) {   // tiles run m-fastest: the bias columns change only every m_tiles tiles
@@ -606,6 +622,11 @@ extern "C" int vsc_gemm_rowmax(const void *d_a, int64_t m, const void *d_b, int6
     return VSC_OK;
 }
 
+// N tile for a convolution GEMM.  (Measured: 128-column tiles for the 18x18 / 9x9 layers, which have only 1.1 - 2.2
+// rounds of 128x256 tiles on 148 SMs, were SLOWER -- 57 -> 80 us at 2304 -> 256 channels: the A tile is re-read per N
+// tile and the per-tile pipeline fill dominates.  So: the widest tile that N allows.)
+static int conv_bn(int64_t, int64_t n) { return n <= 64 ? 64 : n <= 128 ? 128 : 256; }
+
 // Convolution as GEMM: out[m][n] (bf16, row stride ldc) = relu?(A[m][:] . W[n][:] + bias[n] + residual[m][n]).
 extern "C" int vsc_gemm_conv(const void *d_a, int64_t m, const void *d_w, int64_t n, int32_t k, const float *d_bias,
                              const void *d_residual, int32_t relu, void *d_out_bf16, int64_t ldc,
@@ -615,8 +636,9 @@ extern "C" int vsc_gemm_conv(const void *d_a, int64_t m, const void *d_w, int64_
     GemmArgs g = {};
     g.M = m; g.N = n; g.K = k; g.bias = d_bias; g.residual = static_cast<const __nv_bfloat16 *>(d_residual);
     g.relu = relu; g.out_bf16 = static_cast<__nv_bfloat16 *>(d_out_bf16); g.ldc = ldc;
-    if (n <= 64) return launch<EPI_CONV, 64>(d_a, d_w, g, stream);
-    if (n <= 128) return launch<EPI_CONV, 128>(d_a, d_w, g, stream);
+    const int bn = conv_bn(m, n);
+    if (bn == 64) return launch<EPI_CONV, 64>(d_a, d_w, g, stream);
+    if (bn == 128) return launch<EPI_CONV, 128>(d_a, d_w, g, stream);
     return launch<EPI_CONV, 256>(d_a, d_w, g, stream);
 }
 
@@ -640,8 +662,9 @@ extern "C" int vsc_conv3x3(const void *d_in, int32_t n, int32_t h, int32_t w, in
     g.residual = static_cast<const __nv_bfloat16 *>(d_residual); g.relu = relu;
     g.out_bf16 = static_cast<__nv_bfloat16 *>(d_out_bf16); g.ldc = cout;
     g.conv_ho = ho; g.conv_wo = wo; g.conv_stride = stride; g.conv_cblocks = c / BK;
-    if (cout <= 64) return launch<EPI_CONV, 64, A_IM2COL>(d_in, d_w, g, stream, &ma);
-    if (cout <= 128) return launch<EPI_CONV, 128, A_IM2COL>(d_in, d_w, g, stream, &ma);
+    const int bn = conv_bn(g.M, cout);
+    if (bn == 64) return launch<EPI_CONV, 64, A_IM2COL>(d_in, d_w, g, stream, &ma);
+    if (bn == 128) return launch<EPI_CONV, 128, A_IM2COL>(d_in, d_w, g, stream, &ma);
     return launch<EPI_CONV, 256, A_IM2COL>(d_in, d_w, g, stream, &ma);
 }
 
