@@ -88,6 +88,11 @@ int vsc_prepare_operand(const float *d_x, int64_t n, int32_t d, int64_t ld, int3
                         void *d_out_bf16, int32_t *d_lo_flag, vsc_stream_t stream);
 int vsc_row_sqnorm(const float *d_x, int64_t n, int32_t d, int64_t ld, float *d_out, vsc_stream_t stream);
 
+/* *d_out = the k-th best of d_scores[0..n) (1-based; largest != 0: k-th largest, else k-th smallest) by radix selection:
+ * the radius update of faiss.contrib.exhaustive_search.apply_maxres (vsc/index.py:147-154).  d_scratch: >= 8208 bytes. */
+int vsc_kth_best(const float *d_scores, int64_t n, int64_t k, int32_t largest, float *d_out, void *d_scratch,
+                 vsc_stream_t stream);
+
 /* C[m][n] = A . B^T in fp32 (tests, per-pair similarity matrices). */
 int vsc_gemm_store(const void *d_a, int64_t m, const void *d_b, int64_t n, int32_t k, float *d_c, int64_t ldc,
                    vsc_stream_t stream);
@@ -101,7 +106,10 @@ int vsc_gemm_rowargmax(const void *d_a, int64_t m, const void *d_b, int64_t n, i
                        int64_t *d_col, unsigned long long *d_scratch, vsc_stream_t stream);
 /* FAISS range_search (index.py:147-154): counts the scores strictly beyond count_thr into
  * d_counters[1] and appends (score, row + row_offset, col + col_offset) of those strictly beyond
- * emit_thr at d_counters[0]++ (entries past `capacity` are dropped but still counted).
+ * emit_thr into slots claimed from d_counters[0] (entries past `capacity` are dropped but still claimed).  Slots are
+ * claimed per warp in blocks of 256; the unused tail of a warp's last block is filled with a score no threshold accepts
+ * (-inf for inner product, +inf for L2), so d_counters[0] counts CLAIMED slots and a strict re-filter of the scores
+ * removes the fillers.  At most 148 * 8 * 256 filler slots per call.
  * metric_l2 = 0: inner product, "beyond" = greater;  1: squared L2 = a_norm + b_norm - 2 a.b, "beyond" = smaller. */
 int vsc_gemm_emit(const void *d_a, int64_t m, const void *d_b, int64_t n, int32_t k, const float *d_a_norm,
                   const float *d_b_norm, int32_t metric_l2, float count_thr, float emit_thr, int64_t row_offset,

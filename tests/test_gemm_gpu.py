@@ -78,15 +78,20 @@ def test_emit_counts_and_entries(metric_l2):
         count_thr, emit_thr = np.float32(np.quantile(s, 0.98)), np.float32(np.quantile(s, 0.99))
         want = s > emit_thr
         n_count = int((s > count_thr).sum())
-    hits = gemm.HitBuffer(int(want.sum()) + 100, da.device)
+    # output slots are claimed per warp in blocks of 256 whose unused tail is filled with a never-accepted score
+    hits = gemm.HitBuffer(int(want.sum()) + 1184 * 256 + 100, da.device)
     gemm.gemm_emit(oa, ob, hits, float(count_thr), float(emit_thr), metric_l2=metric_l2,
                    a_norm=gemm.row_sqnorm(da) if metric_l2 else None,
                    b_norm=gemm.row_sqnorm(db) if metric_l2 else None, row_offset=10, col_offset=20)
     stored, counted = hits.read_counters()
-    assert stored == int(want.sum()) and counted == n_count
-    rows = hits.row[:stored].cpu().numpy() - 10
-    cols = hits.col[:stored].cpu().numpy() - 20
+    assert counted == n_count and int(want.sum()) <= stored <= hits.capacity
     sc = hits.score[:stored].cpu().numpy()
+    real = np.isfinite(sc)                      # fillers are -inf (inner product) / +inf (L2)
+    assert int(real.sum()) == int(want.sum())
+    assert np.all(sc[~real] == (np.inf if metric_l2 else -np.inf))
+    rows = hits.row[:stored].cpu().numpy()[real] - 10
+    cols = hits.col[:stored].cpu().numpy()[real] - 20
+    sc = sc[real]
     got = np.zeros_like(want)
     got[rows, cols] = True
     assert np.array_equal(got, want)
@@ -101,4 +106,4 @@ def test_emit_capacity_overflow_is_counted_not_written():
     hits = gemm.HitBuffer(1000, oa.panel.device)
     gemm.gemm_emit(oa, ob, hits, -1e10, -1e10)
     stored, counted = hits.read_counters()
-    assert stored == 256 * 512 and counted == 256 * 512
+    assert stored >= 256 * 512 and counted == 256 * 512   # claimed slots (incl. block fillers) / true hits

@@ -177,3 +177,20 @@ def test_c3_scale_properties():
     inside = {(a, b) for a, b in zip(i.tolist(), j.tolist())}
     beat = np.argwhere(slab > s[-1])
     assert all((int(rows[a]), int(b)) in inside for a, b in beat)
+
+
+@pytest.mark.parametrize("largest", [True, False])
+def test_kth_best_radix_select_matches_sort(largest):
+    """vsc_kth_best (the radius update of range_search_max_results) against a full sort: exact, ties included."""
+    import torch
+    from vsc2022_b200.index import FlatIndex
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    cases = [torch.randn(100_003, generator=g, device="cuda"),
+             (torch.randint(-50, 50, (70_000,), generator=g, device="cuda") / 8.0),          # heavy ties, +-0
+             torch.randn(3_000_000, generator=g, device="cuda") * 1e-3 + 0.5,
+             torch.tensor([2.5], device="cuda")]
+    for x in cases:
+        ordered = torch.sort(x, descending=largest).values
+        for k in sorted(k for k in {1, 2, x.numel() // 3 + 1, x.numel() // 2, x.numel()} if 1 <= k <= x.numel()):
+            got = FlatIndex._kth_best(x, k, largest)
+            assert got == float(ordered[k - 1]), (x.numel(), k, got, float(ordered[k - 1]))

@@ -35,7 +35,9 @@ constexpr int STAGES = 4;
 constexpr int UMMA_K = 16;
 constexpr int kThreads = 192;
 constexpr int kThreadsConv = 320;   // 8 epilogue warps
-__host__ __device__ constexpr int epi_warps(int epi) { return epi == 4 /* EPI_CONV */ ? 8 : 4; }
+// CONV and EMIT epilogues are long dependent chains per 32-column chunk (transposes / hit compaction): two warps per
+// TMEM lane quadrant, alternating chunks.  ROWMAX-type epilogues are short and keep four warps.
+__host__ __device__ constexpr int epi_warps(int epi) { return epi == 4 /* EPI_CONV */ || epi == 2 /* EPI_EMIT */ ? 8 : 4; }
 constexpr uint32_t kStageBytesA = BM * BK * 2;
 
 enum ALoad { A_TILED = 0, A_IM2COL = 1, A_SHIFT = 2 };  // how the producer fetches the A tile of a k-block
@@ -163,12 +165,30 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
            | ((uint32_t)(m >> 4) << 24); // M / 16
 }
 
+// EMIT output slots are claimed per WARP in blocks of kEmitBlock entries: one global atomic per block instead of one
+// per chunk with a hit (measured: ~3 M same-address atomics per launch cost 0.7-1.4 ms, more than the GEMM of a 2048-row
+// batch).  Unused slots of a warp's last block are filled with a score no threshold accepts (-inf / +inf), so the
+// consumer's strict re-filter drops them; counters[0] therefore counts CLAIMED slots, counters[1] true hits.
+constexpr int kEmitBlock = 256;
+struct EmitState {
+    unsigned long long pos;     // next free slot of this warp's block
+    int left;                   // free slots in the block
+    unsigned long long counted; // hits beyond count_thr seen by this warp (flushed once at the end)
+};
+__device__ __forceinline__ void emit_pad(const GemmArgs &g, EmitState &e, int lane) {   // retire the current block
+    const float never = g.metric_l2 ? INFINITY : -INFINITY;
+    for (int i = lane; i < e.left; i += 32)
+        if (e.pos + i < g.capacity) g.out_score[e.pos + i] = never;
+    e.left = 0;
+}
+
 // ---------------------------------------------------------------- epilogues (one thread = one accumulator row)
 // `valid` = number of in-range columns of this 32-column chunk (1..32): bounds are applied to the
 // bit masks, not per element.
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const GemmArgs &g, float &best, int64_t &best_col, int64_t row,
-                                               int64_t col0, int valid, const uint32_t (&acc)[32], int lane) {
+                                               int64_t col0, int valid, const uint32_t (&acc)[32], int lane,
+                                               EmitState &emit) {
     const bool row_ok = row < g.M;
     const uint32_t valid_mask = valid >= 32 ? 0xFFFFFFFFu : ((1u << valid) - 1u);
     if (EPI == EPI_STORE) {
@@ -225,7 +245,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs &g, float &best, i
         const uint32_t keep = row_ok ? valid_mask : 0u;
         hits &= keep; counted &= keep;
         if (!__any_sync(kFullMask, (hits | counted) != 0)) return;  // the common case once the radius is tight
-        // warp-aggregated claim of output slots
+        // warp-aggregated claim of output slots out of the warp's private block
         const int n_hit = __popc(hits);
         int incl = n_hit, total_cnt = __popc(counted);
 #pragma unroll
@@ -235,13 +255,19 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs &g, float &best, i
             total_cnt += __shfl_xor_sync(kFullMask, total_cnt, d);
         }
         const int total_hit = __shfl_sync(kFullMask, incl, 31);
-        unsigned long long base = 0;
-        if (lane == 0) {
-            if (total_hit) base = atomicAdd(&g.counters[0], (unsigned long long)total_hit);
-            if (total_cnt) atomicAdd(&g.counters[1], (unsigned long long)total_cnt);
+        emit.counted += (unsigned long long)total_cnt;
+        if (total_hit == 0) return;
+        if (total_hit > emit.left) {
+            emit_pad(g, emit, lane);
+            const int want = total_hit > kEmitBlock ? total_hit : kEmitBlock;
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(&g.counters[0], (unsigned long long)want);
+            emit.pos = __shfl_sync(kFullMask, base, 0);
+            emit.left = want;
         }
-        base = __shfl_sync(kFullMask, base, 0);
-        unsigned long long at = base + (unsigned long long)(incl - n_hit);
+        unsigned long long at = emit.pos + (unsigned long long)(incl - n_hit);
+        emit.pos += (unsigned long long)total_hit;
+        emit.left -= total_hit;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
             if ((hits >> j) & 1) {
@@ -333,7 +359,7 @@ __device__ __forceinline__ void conv_epilogue_chunk(const GemmArgs &g, int64_t r
 }
 
 template <int EPI, int BN, int ALOAD = A_TILED>
-__global__ void __launch_bounds__(EPI == 4 ? kThreadsConv : kThreads, 1) gemm_kernel(const __grid_constant__ CUtensorMap tma_a,
+__global__ void __launch_bounds__(epi_warps(EPI) == 8 ? kThreadsConv : kThreads, 1) gemm_kernel(const __grid_constant__ CUtensorMap tma_a,
                                                            const __grid_constant__ CUtensorMap tma_b,
                                                            const GemmArgs g) {
     extern __shared__ uint8_t smem_raw[];
@@ -421,6 +447,7 @@ __global__ void __launch_bounds__(EPI == 4 ? kThreadsConv : kThreads, 1) gemm_ke
         // ===== epilogue warps: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32) =====
         const int quad = warp & 3;
         int64_t bias_blk = -1;
+        EmitState emit = {0ull, 0, 0ull};
         uint32_t it = 0;
         for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
@@ -464,13 +491,13 @@ __global__ void __launch_bounds__(EPI == 4 ? kThreadsConv : kThreads, 1) gemm_ke
                 }
             } else {
 #pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
+                for (int c = (warp - 2) >> 2; c < BN / 32; c += epi_warps(EPI) / 4) {
                     const int64_t col0 = n_blk * BN + c * 32;
                     if (col0 >= g.N) break;
                     const int valid = (int)(g.N - col0 < 32 ? g.N - col0 : 32);
                     uint32_t v[32];
                     tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + c * 32, v);
-                    epilogue_chunk<EPI>(g, best, best_col, row, col0, valid, v, lane);
+                    epilogue_chunk<EPI>(g, best, best_col, row, col0, valid, v, lane, emit);
                 }
             }
             tcgen05_fence_before();
@@ -481,6 +508,10 @@ __global__ void __launch_bounds__(EPI == 4 ? kThreadsConv : kThreads, 1) gemm_ke
             if (EPI == EPI_ROWARGMAX && row < g.M && best_col >= 0)
                 atomicMax(&g.rowbest[row], ((unsigned long long)vsc::float_to_key(best) << 32) |
                                                (unsigned long long)(0xFFFFFFFFu - (uint32_t)best_col));
+        }
+        if (EPI == EPI_EMIT) {   // retire the warp's last block, publish its hit count
+            emit_pad(g, emit, lane);
+            if (lane == 0 && emit.counted) atomicAdd(&g.counters[1], emit.counted);
         }
     }
     tcgen05_fence_before();
@@ -573,7 +604,7 @@ int launch(const void *a, const void *b, const GemmArgs &g, cudaStream_t stream,
     VSC_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int64_t tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
     const int grid = (int)(tiles < sms ? tiles : sms);
-    gemm_kernel<EPI, BN, ALOAD><<<grid, EPI == EPI_CONV ? kThreadsConv : kThreads, smem, stream>>>(ma, mb, g);
+    gemm_kernel<EPI, BN, ALOAD><<<grid, epi_warps(EPI) == 8 ? kThreadsConv : kThreads, smem, stream>>>(ma, mb, g);
     VSC_CUDA_CHECK(cudaGetLastError());
     vsc::count_launch();
     return VSC_OK;

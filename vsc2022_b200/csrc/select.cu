@@ -1,0 +1,108 @@
+// k-th best of a score array by radix selection (sm_100a).
+//
+// Replaces the partition step of faiss.contrib.exhaustive_search.apply_maxres behind vsc/index.py:147-154
+// (`alldis.partition(len - target - 1); radius = alldis[-1 - target]`): the new radius is the k-th largest (inner
+// product) or k-th smallest (L2) of the scores held so far, k = min_results + 1.  A sort-based top-k over the 3-6 M held
+// scores cost 2-3 ms per tightening and there are five or six tightenings per 40k x 200k search; three histogram
+// passes (11 + 11 + 10 bits of the order-preserving key) read the array three times instead.  HBM-bound.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kBins = 2048;
+
+struct SelectState {          // lives in device memory between the passes
+    uint32_t prefix;          // key bits decided so far (aligned to the top)
+    uint32_t mask;            // which bits are decided
+    unsigned long long k;     // rank still to find inside the matching elements (1 = best)
+};
+
+__device__ __forceinline__ uint32_t order_key(float v, int largest) {
+    const uint32_t key = vsc::float_to_key(v);     // ascending with the value
+    return largest ? key : ~key;                   // "best" is always the largest key
+}
+
+// histogram of `bits` key bits starting at `shift` over the elements that match the decided prefix
+__global__ void __launch_bounds__(512) select_hist_kernel(const float *__restrict__ x, int64_t n, int largest, int shift,
+                                                          int bits, const SelectState *__restrict__ st,
+                                                          unsigned int *__restrict__ hist) {
+    __shared__ unsigned int h[kBins];
+    for (int i = threadIdx.x; i < kBins; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    const uint32_t prefix = st->prefix, mask = st->mask, field = (1u << bits) - 1u;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t key = order_key(x[i], largest);
+        if ((key & mask) == prefix) atomicAdd(&h[(key >> shift) & field], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kBins; i += blockDim.x)
+        if (h[i]) atomicAdd(&hist[i], h[i]);
+}
+
+// one block of 256 threads: find the bin (counting from the best = highest key downwards) that holds the remaining
+// rank.  Thread t owns bins [8t, 8t+8); an inclusive suffix sum over the threads' totals locates the owner.
+__global__ void __launch_bounds__(256) select_pick_kernel(SelectState *st, unsigned int *hist, int shift, int bits,
+                                                          int largest, int last, float *out) {
+    __shared__ unsigned long long suffix[256];
+    const int t = threadIdx.x;
+    unsigned int c[8];
+    unsigned long long mine = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { c[i] = hist[t * 8 + i]; mine += c[i]; hist[t * 8 + i] = 0; }   // leaves the histogram clear
+    suffix[t] = mine;
+    __syncthreads();
+    for (int d = 1; d < 256; d <<= 1) {   // suffix[t] = sum of the totals of threads >= t
+        const unsigned long long add = t + d < 256 ? suffix[t + d] : 0;
+        __syncthreads();
+        suffix[t] += add;
+        __syncthreads();
+    }
+    const unsigned long long k = st->k;
+    const unsigned long long above = t + 1 < 256 ? suffix[t + 1] : 0;   // elements in better bins than mine
+    __syncthreads();
+    // exactly one thread has above < k <= above + mine (k <= total matching elements by construction)
+    if (above < k && k <= above + mine) {
+        unsigned long long r = k - above;
+        int b = 7;
+        for (; b > 0; --b) {
+            if (r <= c[b]) break;
+            r -= c[b];
+        }
+        const uint32_t prefix = st->prefix | ((uint32_t)(t * 8 + b) << shift);
+        st->prefix = prefix;
+        st->mask |= ((1u << bits) - 1u) << shift;
+        st->k = r;
+        if (last) *out = vsc::key_to_float(largest ? prefix : ~prefix);
+    }
+}
+
+}  // namespace
+
+// *d_out = the k-th best (1-based; largest != 0: k-th largest, else k-th smallest) of d_scores[0..n).  NaNs are not
+// supported.  d_scratch: at least 8208 bytes of device memory (histogram + state), contents irrelevant.
+extern "C" int vsc_kth_best(const float *d_scores, int64_t n, int64_t k, int32_t largest, float *d_out, void *d_scratch,
+                            vsc_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (n <= 0 || k < 1 || k > n || !d_scores || !d_out || !d_scratch) {
+        vsc::set_error("vsc_kth_best: need 1 <= k <= n and non-null buffers (n=%lld, k=%lld)", (long long)n, (long long)k);
+        return VSC_ERR_INVALID;
+    }
+    unsigned int *hist = static_cast<unsigned int *>(d_scratch);
+    SelectState *st = reinterpret_cast<SelectState *>(hist + kBins);
+    VSC_CUDA_CHECK(cudaMemsetAsync(d_scratch, 0, sizeof(unsigned int) * kBins + sizeof(SelectState), stream));
+    const SelectState init = {0u, 0u, (unsigned long long)k};
+    VSC_CUDA_CHECK(cudaMemcpyAsync(st, &init, sizeof init, cudaMemcpyHostToDevice, stream));
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t want = (n + 511) / 512;
+    const int grid = (int)(want < (int64_t)sms * 4 ? want : (int64_t)sms * 4);
+    const int shifts[3] = {21, 10, 0}, bits[3] = {11, 11, 10};
+    for (int p = 0; p < 3; ++p) {
+        select_hist_kernel<<<grid, 512, 0, stream>>>(d_scores, n, largest, shifts[p], bits[p], st, hist);
+        select_pick_kernel<<<1, 256, 0, stream>>>(st, hist, shifts[p], bits[p], largest, p == 2, d_out);
+    }
+    VSC_CUDA_CHECK(cudaGetLastError());
+    vsc::count_launch(6);
+    return VSC_OK;
+}

@@ -190,7 +190,8 @@ class FlatIndex:
 
         Invariants ("beyond" = greater for inner product, smaller for L2):
           total  = number of results FAISS holds now (every pair seen so far beyond `radius`)
-          held   = results kept in the device buffer = every pair seen so far beyond `prune`
+          held   = slots used in the device buffer = every pair seen so far beyond `prune` (+ never-accepted
+                   filler entries of the emit epilogue's per-warp blocks, dropped by every strict re-filter)
           prune  is `radius` unless the buffer overflowed inside a batch; then it is the (min_results+1)-th best
                  held score, which the next tightening can only move further, so nothing FAISS would finally
                  keep is lost, while `total` still counts every hit beyond `radius` (the emit epilogue counts
@@ -220,7 +221,7 @@ class FlatIndex:
         if capacity is None:
             capacity = max(4 * max_results, min(32 * nb, 1 << 26)) + 65536
         hits = gemm.HitBuffer(int(capacity), dev)
-        held, total, prune = 0, 0, radius
+        held, total, prune, padded = 0, 0, radius, False
         unbounded = True   # radius still at its initial value: every pair is a hit, emission size is known
         for b0, b1 in exponential_batches(nq):
             if ws > 1:   # this rank's slice of the batch
@@ -232,8 +233,8 @@ class FlatIndex:
             while r0 < b1:
                 rows = max(1, min(rows, b1 - r0))
                 room = hits.capacity - held
-                if unbounded and prune == radius and rows * nb > room:
-                    rows = room // nb          # known emission: size the slice instead of trying
+                if unbounded and prune == radius and rows * nb > room - EMIT_PAD:
+                    rows = max(room - EMIT_PAD, 0) // nb   # known emission: size the slice instead of trying
                 if rows >= 1:
                     hits.counters[0] = held
                     hits.counters[1] = 0
@@ -261,15 +262,26 @@ class FlatIndex:
                 held = self._refilter(hits, held, radius, keep_max)
                 total = D.global_count(held, dev, group) if ws > 1 else held
                 prune, unbounded = radius, False
+                padded = False
+            else:
+                padded = True
+        if padded:   # drop the never-accepted fillers of the emit epilogue's per-warp blocks (see gemm_tc.cu)
+            held = self._refilter(hits, held, prune, keep_max)
         return hits.score[:held], hits.row[:held].long(), hits.col[:held].long(), radius
 
     @staticmethod
     def _kth_best(scores, k: int, keep_max: bool) -> float:
-        """The k-th best stored score (k-th largest for IP, k-th smallest for L2) as a Python float."""
-        import torch
-        if keep_max:
-            return float(torch.topk(scores, k, largest=True, sorted=True).values[-1])
-        return float(torch.topk(scores, k, largest=False, sorted=True).values[-1])
+        """The k-th best stored score (k-th largest for IP, k-th smallest for L2) as a Python float: radix selection
+        on the device (vsc_kth_best), one 4-byte read back -- the host needs the radius for the next launch."""
+        import ctypes
+        torch = _lib.require_cuda()
+        scores = scores.contiguous()
+        out = torch.empty(1, dtype=torch.float32, device=scores.device)
+        scratch = torch.empty(2080, dtype=torch.int32, device=scores.device)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(scores.device).cuda_stream)
+        _lib.check(_lib.load().vsc_kth_best(scores.data_ptr(), scores.numel(), int(k), 1 if keep_max else 0,
+                                            out.data_ptr(), scratch.data_ptr(), stream), "vsc_kth_best")
+        return float(out)
 
     @staticmethod
     def _refilter(hits, held: int, radius: float, keep_max: bool) -> int:
@@ -287,6 +299,10 @@ class FlatIndex:
         new = gemm.HitBuffer(capacity, hits.score.device)
         new.score[:held], new.row[:held], new.col[:held] = hits.score[:held], hits.row[:held], hits.col[:held]
         return new
+
+
+# upper bound of the filler slots one emit launch can add (every warp of the grid retires one partly used block)
+EMIT_PAD = 148 * 8 * 256
 
 
 def index_factory(d: int, description: str = "Flat", metric: int = METRIC_L2) -> FlatIndex:
