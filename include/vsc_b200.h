@@ -93,6 +93,12 @@ int vsc_row_sqnorm(const float *d_x, int64_t n, int32_t d, int64_t ld, float *d_
 int vsc_kth_best(const float *d_scores, int64_t n, int64_t k, int32_t largest, float *d_out, void *d_scratch,
                  vsc_stream_t stream);
 
+/* The re-filter of apply_maxres: copy the entries of (score, row, col)[0..n) strictly beyond `radius` to the output
+ * arrays (unspecified order, no overlap with the inputs); *d_count receives how many. */
+int vsc_compact_hits(const float *d_score, const int32_t *d_row, const int32_t *d_col, int64_t n, float radius,
+                     int32_t keep_max, float *d_score_out, int32_t *d_row_out, int32_t *d_col_out,
+                     unsigned long long *d_count, vsc_stream_t stream);
+
 /* C[m][n] = A . B^T in fp32 (tests, per-pair similarity matrices). */
 int vsc_gemm_store(const void *d_a, int64_t m, const void *d_b, int64_t n, int32_t k, float *d_c, int64_t ldc,
                    vsc_stream_t stream);

@@ -175,6 +175,8 @@ struct EmitState {
     int left;                   // free slots in the block
     unsigned long long counted; // hits beyond count_thr seen by this warp (flushed once at the end)
 };
+// squared L2 distance from the norms and the inner product; one expression for every place that needs the value
+__device__ __forceinline__ float l2_score(float an, float bn, float ip) { return __fmaf_rn(-2.0f, ip, __fadd_rn(an, bn)); }
 __device__ __forceinline__ void emit_pad(const GemmArgs &g, EmitState &e, int lane) {   // retire the current block
     const float never = g.metric_l2 ? INFINITY : -INFINITY;
     for (int i = lane; i < e.left; i += 32)
@@ -188,7 +190,7 @@ __device__ __forceinline__ void emit_pad(const GemmArgs &g, EmitState &e, int la
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const GemmArgs &g, float &best, int64_t &best_col, int64_t row,
                                                int64_t col0, int valid, const uint32_t (&acc)[32], int lane,
-                                               EmitState &emit) {
+                                               EmitState &emit, uint32_t taddr) {
     const bool row_ok = row < g.M;
     const uint32_t valid_mask = valid >= 32 ? 0xFFFFFFFFu : ((1u << valid) - 1u);
     if (EPI == EPI_STORE) {
@@ -220,6 +222,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs &g, float &best, i
         float s[32];
         const float emit_thr = g.emit_thr, count_thr = g.count_thr;
         const bool two = emit_thr != count_thr;  // uniform: the common case has one threshold
+        float an = 0.0f;
         if (!g.metric_l2) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -233,11 +236,11 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs &g, float &best, i
                 for (int j = 0; j < 32; ++j) counted |= (s[j] > count_thr ? 1u : 0u) << j;
             }
         } else {
-            const float an = row_ok ? g.a_norm[row] : 0.0f;
+            an = row_ok ? g.a_norm[row] : 0.0f;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 const float bn = j < valid ? g.b_norm[col0 + j] : 0.0f;
-                s[j] = an + bn - 2.0f * __uint_as_float(acc[j]);
+                s[j] = l2_score(an, bn, __uint_as_float(acc[j]));
                 hits |= (s[j] < emit_thr ? 1u : 0u) << j;
                 counted |= (s[j] < count_thr ? 1u : 0u) << j;
             }
@@ -268,6 +271,29 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs &g, float &best, i
         unsigned long long at = emit.pos + (unsigned long long)(incl - n_hit);
         emit.pos += (unsigned long long)total_hit;
         emit.left -= total_hit;
+        if (total_hit <= 8) {
+            // a handful of hits in the chunk (the usual case once the radius is tight): walk the hit COLUMNS
+            // (warp-uniform) and fetch each one again from tensor memory instead of running the 32-way predicated
+            // store sequence below (~250 instructions per chunk with a single hit)
+            uint32_t cols = __reduce_or_sync(kFullMask, hits);
+            while (cols) {
+                const int j = __ffs(cols) - 1;
+                cols &= cols - 1;
+                uint32_t raw;
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(raw) : "r"(taddr + (uint32_t)j));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if ((hits >> j) & 1) {
+                    const float v = g.metric_l2 ? l2_score(an, g.b_norm[col0 + j], __uint_as_float(raw)) : __uint_as_float(raw);
+                    if (at < g.capacity) {
+                        g.out_score[at] = v;
+                        g.out_row[at] = (int32_t)(row + g.row_offset);
+                        g.out_col[at] = (int32_t)(col0 + j + g.col_offset);
+                    }
+                    ++at;
+                }
+            }
+            return;
+        }
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
             if ((hits >> j) & 1) {
@@ -496,8 +522,9 @@ __global__ void __launch_bounds__(epi_warps(EPI) == 8 ? kThreadsConv : kThreads,
                     if (col0 >= g.N) break;
                     const int valid = (int)(g.N - col0 < 32 ? g.N - col0 : 32);
                     uint32_t v[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + c * 32, v);
-                    epilogue_chunk<EPI>(g, best, best_col, row, col0, valid, v, lane, emit);
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + c * 32;
+                    tmem_ld32(taddr, v);
+                    epilogue_chunk<EPI>(g, best, best_col, row, col0, valid, v, lane, emit, taddr);
                 }
             }
             tcgen05_fence_before();

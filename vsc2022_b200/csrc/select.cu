@@ -76,7 +76,62 @@ __global__ void __launch_bounds__(256) select_pick_kernel(SelectState *st, unsig
     }
 }
 
+// Unordered stream compaction of the survivors: keep entries strictly beyond `radius`.  One atomic per 256 entries.
+__global__ void __launch_bounds__(256) compact_kernel(const float *__restrict__ s_in, const int32_t *__restrict__ r_in,
+                                                      const int32_t *__restrict__ c_in, int64_t n, float radius,
+                                                      int keep_max, float *__restrict__ s_out, int32_t *__restrict__ r_out,
+                                                      int32_t *__restrict__ c_out, unsigned long long *__restrict__ count) {
+    __shared__ unsigned int warp_total[8];
+    __shared__ unsigned long long block_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t i0 = (int64_t)blockIdx.x * 256; i0 < n; i0 += (int64_t)gridDim.x * 256) {
+        const int64_t i = i0 + threadIdx.x;
+        float sc = 0.0f;
+        bool keep = false;
+        if (i < n) {
+            sc = s_in[i];
+            keep = keep_max ? sc > radius : sc < radius;
+        }
+        const unsigned int vote = __ballot_sync(vsc::kFullMask, keep);
+        if (lane == 0) warp_total[warp] = __popc(vote);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned int t = 0;
+            for (int w = 0; w < 8; ++w) t += warp_total[w];
+            block_base = t ? atomicAdd(count, (unsigned long long)t) : 0ull;
+        }
+        __syncthreads();
+        if (keep) {
+            unsigned long long at = block_base + __popc(vote & ((1u << lane) - 1u));
+            for (int w = 0; w < warp; ++w) at += warp_total[w];
+            s_out[at] = sc; r_out[at] = r_in[i]; c_out[at] = c_in[i];
+        }
+        __syncthreads();   // warp_total / block_base are rewritten by the next round
+    }
+}
+
 }  // namespace
+
+// Copies the entries of (score, row, col)[0..n) whose score is strictly beyond `radius` (greater for keep_max != 0,
+// smaller otherwise) to the output arrays in unspecified order; *d_count (zeroed here) receives how many.  The
+// re-filter of faiss.contrib.exhaustive_search.apply_maxres.  In and out must not overlap.
+extern "C" int vsc_compact_hits(const float *d_score, const int32_t *d_row, const int32_t *d_col, int64_t n, float radius,
+                                int32_t keep_max, float *d_score_out, int32_t *d_row_out, int32_t *d_col_out,
+                                unsigned long long *d_count, vsc_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    VSC_CUDA_CHECK(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), stream));
+    if (n <= 0) return VSC_OK;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t want = (n + 255) / 256;
+    const int grid = (int)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
+    compact_kernel<<<grid, 256, 0, stream>>>(d_score, d_row, d_col, n, radius, keep_max, d_score_out, d_row_out,
+                                             d_col_out, d_count);
+    VSC_CUDA_CHECK(cudaGetLastError());
+    vsc::count_launch();
+    return VSC_OK;
+}
 
 // *d_out = the k-th best (1-based; largest != 0: k-th largest, else k-th smallest) of d_scores[0..n).  NaNs are not
 // supported.  d_scratch: at least 8208 bytes of device memory (histogram + state), contents irrelevant.

@@ -285,14 +285,24 @@ class FlatIndex:
 
     @staticmethod
     def _refilter(hits, held: int, radius: float, keep_max: bool) -> int:
-        import torch
-        sc = hits.score[:held]
-        keep = sc > radius if keep_max else sc < radius
-        n = int(keep.sum())
-        hits.score[:n] = sc[keep]
-        hits.row[:n] = hits.row[:held][keep]
-        hits.col[:n] = hits.col[:held][keep]
-        return n
+        """Keep the held entries strictly beyond `radius`: one compaction kernel into the buffer's twin arrays
+        (order is irrelevant: the final ordering sorts), then the arrays swap roles."""
+        import ctypes
+        torch = _lib.require_cuda()
+        if held == 0:
+            return 0
+        dev = hits.score.device
+        if getattr(hits, "twin", None) is None:
+            hits.twin = (torch.empty_like(hits.score), torch.empty_like(hits.row), torch.empty_like(hits.col))
+            hits.kept = torch.zeros(1, dtype=torch.int64, device=dev)
+        s2, r2, c2 = hits.twin
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(_lib.load().vsc_compact_hits(hits.score.data_ptr(), hits.row.data_ptr(), hits.col.data_ptr(), int(held),
+                                                float(radius), 1 if keep_max else 0, s2.data_ptr(), r2.data_ptr(),
+                                                c2.data_ptr(), hits.kept.data_ptr(), stream), "vsc_compact_hits")
+        hits.twin = (hits.score, hits.row, hits.col)
+        hits.score, hits.row, hits.col = s2, r2, c2
+        return int(hits.kept)
 
     @staticmethod
     def _grow(hits, held, capacity):
