@@ -314,6 +314,16 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs &g, float &best, i
 // accesses are issued with 4 lanes per row (64 contiguous bytes, 8 rows per instruction), the row-per-thread
 // accesses go to shared memory.  Unit (row, q) lives at row*4 + (q ^ ((row >> 1) & 3)): conflict-free both ways.
 __device__ __forceinline__ int conv_unit(int row, int q) { return row * 4 + (q ^ ((row >> 1) & 3)); }
+// explicit shared-space accesses: through a generic pointer these compile to LD.E / ST.E, which take the generic
+// address path and wait on the long scoreboard like global loads
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4 &v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
 
 __device__ __forceinline__ void conv_residual_fetch(const GemmArgs &g, int64_t row0, int64_t col0, int lane, uint4 (&r)[4]) {
 #pragma unroll
@@ -337,22 +347,24 @@ __device__ __forceinline__ void conv_residual_prefetch_l2(const GemmArgs &g, int
 
 __device__ __forceinline__ void conv_epilogue_chunk(const GemmArgs &g, int64_t row0, int64_t col0, int lane,
                                                     const uint32_t (&acc)[32], const uint4 (&res)[4],
-                                                    const float *bias_chunk, uint4 *stage) {
+                                                    const float *bias_chunk, uint4 *stage_ptr) {
     float v[32];
-    const float4 *b4 = reinterpret_cast<const float4 *>(bias_chunk);   // shared memory, same address in every lane
+    const uint32_t stage = smem_u32(stage_ptr), bias_s = smem_u32(bias_chunk);
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-        const float4 b = b4[q];
-        v[q * 4 + 0] = __uint_as_float(acc[q * 4 + 0]) + b.x; v[q * 4 + 1] = __uint_as_float(acc[q * 4 + 1]) + b.y;
-        v[q * 4 + 2] = __uint_as_float(acc[q * 4 + 2]) + b.z; v[q * 4 + 3] = __uint_as_float(acc[q * 4 + 3]) + b.w;
+        const uint4 bq = lds128(bias_s + q * 16);   // same address in every lane: broadcast
+        v[q * 4 + 0] = __uint_as_float(acc[q * 4 + 0]) + __uint_as_float(bq.x);
+        v[q * 4 + 1] = __uint_as_float(acc[q * 4 + 1]) + __uint_as_float(bq.y);
+        v[q * 4 + 2] = __uint_as_float(acc[q * 4 + 2]) + __uint_as_float(bq.z);
+        v[q * 4 + 3] = __uint_as_float(acc[q * 4 + 3]) + __uint_as_float(bq.w);
     }
     if (g.residual) {
 #pragma unroll
-        for (int it = 0; it < 4; ++it) stage[conv_unit(it * 8 + (lane >> 2), lane & 3)] = res[it];
+        for (int it = 0; it < 4; ++it) sts128(stage + conv_unit(it * 8 + (lane >> 2), lane & 3) * 16, res[it]);
         __syncwarp();
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const uint4 r = stage[conv_unit(lane, q)];
+            const uint4 r = lds128(stage + conv_unit(lane, q) * 16);
             const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
@@ -367,19 +379,20 @@ __device__ __forceinline__ void conv_epilogue_chunk(const GemmArgs &g, int64_t r
         uint32_t w[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-            float lo = v[q * 8 + 2 * t], hi = v[q * 8 + 2 * t + 1];
-            if (g.relu) { lo = fmaxf(lo, 0.0f); hi = fmaxf(hi, 0.0f); }
-            const __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+            // ReLU after the rounding (identical result: rounding keeps the sign), on the packed pair
+            __nv_bfloat162 p = __floats2bfloat162_rn(v[q * 8 + 2 * t], v[q * 8 + 2 * t + 1]);
+            if (g.relu) p = __hmax2(p, __floats2bfloat162_rn(0.0f, 0.0f));
             w[t] = *reinterpret_cast<const uint32_t *>(&p);
         }
-        stage[conv_unit(lane, q)] = make_uint4(w[0], w[1], w[2], w[3]);
+        sts128(stage + conv_unit(lane, q) * 16, make_uint4(w[0], w[1], w[2], w[3]));
     }
     __syncwarp();
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
         const int r = it * 8 + (lane >> 2);
         const int64_t row = row0 + r;
-        if (row < g.M) reinterpret_cast<uint4 *>(g.out_bf16 + row * g.ldc + col0)[lane & 3] = stage[conv_unit(r, lane & 3)];
+        const uint4 o = lds128(stage + conv_unit(r, lane & 3) * 16);
+        if (row < g.M) reinterpret_cast<uint4 *>(g.out_bf16 + row * g.ldc + col0)[lane & 3] = o;
     }
     __syncwarp();   // the buffer is free again
 }
@@ -495,8 +508,6 @@ __global__ void __launch_bounds__(epi_warps(EPI) == 8 ? kThreadsConv : kThreads,
                     conv_residual_prefetch_l2(g, m2 * BM + quad * 32, n2 * BN, first,
                                               (int)((g.N - n2 * BN < BN ? g.N - n2 * BN : BN) / 32), lane);
                 }
-                uint4 res[4] = {}, res_next[4] = {};
-                if (g.residual && first < chunks) conv_residual_fetch(g, row0, colb + first * 32, lane, res);
                 if (n_blk != bias_blk) {   // tiles run m-fastest: the bias columns change only every m_tiles tiles
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -506,14 +517,28 @@ __global__ void __launch_bounds__(epi_warps(EPI) == 8 ? kThreadsConv : kThreads,
                     bias_blk = n_blk;
                     __syncwarp();
                 }
+                // This warp's chunks are c = first + 2j.  Residuals ping-pong between two register sets, each
+                // requested one chunk ahead; no register set is ever copied (a copy behind the load waits for it and
+                // exposes one memory round trip per chunk -- measured on the first version of this loop).
+                const int n_mine = chunks > first ? (chunks - first + 1) / 2 : 0;
+                const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
+                uint4 res_a[4] = {}, res_b[4] = {};
+                if (g.residual && n_mine > 0) conv_residual_fetch(g, row0, colb + first * 32, lane, res_a);
 #pragma unroll 1
-                for (int c = first; c < chunks; c += 2) {
-                    if (g.residual && c + 2 < chunks) conv_residual_fetch(g, row0, colb + (c + 2) * 32, lane, res_next);
-                    uint32_t v[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + c * 32, v);
-                    conv_epilogue_chunk(g, row0, colb + c * 32, lane, v, res, &sm.bias_s[epi][(c >> 1) * 32], sm.stage[epi]);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) res[i] = res_next[i];
+                for (int j = 0; j < n_mine; j += 2) {
+                    const int c0 = first + 2 * j, c1 = c0 + 2;
+                    if (g.residual && j + 1 < n_mine) conv_residual_fetch(g, row0, colb + c1 * 32, lane, res_b);
+                    {
+                        uint32_t v[32];
+                        tmem_ld32(tacc + c0 * 32, v);
+                        conv_epilogue_chunk(g, row0, colb + c0 * 32, lane, v, res_a, &sm.bias_s[epi][j * 32], sm.stage[epi]);
+                    }
+                    if (g.residual && j + 2 < n_mine) conv_residual_fetch(g, row0, colb + (c1 + 2) * 32, lane, res_a);
+                    if (j + 1 < n_mine) {
+                        uint32_t v[32];
+                        tmem_ld32(tacc + c1 * 32, v);
+                        conv_epilogue_chunk(g, row0, colb + c1 * 32, lane, v, res_b, &sm.bias_s[epi][(j + 1) * 32], sm.stage[epi]);
+                    }
                 }
             } else {
 #pragma unroll 1
