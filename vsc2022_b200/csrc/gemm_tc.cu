@@ -33,11 +33,13 @@ using vsc::kFullMask;
 constexpr int BM = 128, BK = 64;  // the N tile (64 / 128 / 256) is a template parameter
 constexpr int STAGES = 4;
 constexpr int UMMA_K = 16;
-constexpr int kThreads = 192;
-constexpr int kThreadsConv = 320;   // 8 epilogue warps
+#ifndef VSC_CONV_EPI_WARPS
+#define VSC_CONV_EPI_WARPS 8   // 12 (three per lane quadrant, 448 threads) measured: no gain, `down` GEMMs slower
+#endif
 // CONV and EMIT epilogues are long dependent chains per 32-column chunk (transposes / hit compaction): two warps per
 // TMEM lane quadrant, alternating chunks.  ROWMAX-type epilogues are short and keep four warps.
-__host__ __device__ constexpr int epi_warps(int epi) { return epi == 4 /* EPI_CONV */ || epi == 2 /* EPI_EMIT */ ? 8 : 4; }
+__host__ __device__ constexpr int epi_warps(int epi) { return epi == 4 /* EPI_CONV */ ? VSC_CONV_EPI_WARPS : epi == 2 /* EPI_EMIT */ ? 8 : 4; }
+__host__ __device__ constexpr int cta_threads(int epi) { return 64 + 32 * epi_warps(epi); }   // producer + MMA + epilogue warps
 constexpr uint32_t kStageBytesA = BM * BK * 2;
 
 enum ALoad { A_TILED = 0, A_IM2COL = 1, A_SHIFT = 2 };  // how the producer fetches the A tile of a k-block
@@ -80,8 +82,8 @@ struct SharedStorage {
     // CONV epilogue, per epilogue warp: a 32-row x 64-byte transpose buffer (16-byte units, XOR-swizzled: see
     // conv_unit) used first for the residual chunk coming in, then for the bf16 chunk going out; and the folded
     // BatchNorm bias of the warp's (up to four) 32-column chunks
-    alignas(16) uint4 stage[8][128];
-    alignas(16) float bias_s[8][4 * 32];
+    alignas(16) uint4 stage[12][128];
+    alignas(16) float bias_s[12][4 * 32];
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -341,7 +343,7 @@ __device__ __forceinline__ void conv_residual_prefetch_l2(const GemmArgs &g, int
     const int64_t row = row0 + lane;
     if (row >= g.M) return;
     const __nv_bfloat16 *p = g.residual + row * g.ldc + colb;
-    for (int c = first; c < chunks; c += 2)
+    for (int c = first; c < chunks; c += epi_warps(4) / 4)
         asm volatile("prefetch.global.L2 [%0];" ::"l"(p + c * 32));
 }
 
@@ -398,7 +400,7 @@ __device__ __forceinline__ void conv_epilogue_chunk(const GemmArgs &g, int64_t r
 }
 
 template <int EPI, int BN, int ALOAD = A_TILED>
-__global__ void __launch_bounds__(epi_warps(EPI) == 8 ? kThreadsConv : kThreads, 1) gemm_kernel(const __grid_constant__ CUtensorMap tma_a,
+__global__ void __launch_bounds__(cta_threads(EPI), 1) gemm_kernel(const __grid_constant__ CUtensorMap tma_a,
                                                            const __grid_constant__ CUtensorMap tma_b,
                                                            const GemmArgs g) {
     extern __shared__ uint8_t smem_raw[];
@@ -502,7 +504,8 @@ __global__ void __launch_bounds__(epi_warps(EPI) == 8 ? kThreadsConv : kThreads,
                 // the arithmetic and the stores of chunk c.
                 const int64_t row0 = m_blk * BM + quad * 32, colb = n_blk * BN;
                 const int chunks = (int)((g.N - colb < BN ? g.N - colb : BN) / 32);
-                const int epi = warp - 2, first = epi >> 2;   // two warps per lane quadrant: even / odd chunks
+                constexpr int kPer = epi_warps(EPI_CONV) / 4;   // warps per lane quadrant, interleaved over the chunks
+                const int epi = warp - 2, first = epi >> 2;
                 if (g.residual && t + gridDim.x < tiles) {    // next tile of this CTA: its residual goes to L2 now
                     const int64_t t2 = t + gridDim.x, m2 = t2 % m_tiles, n2 = t2 / m_tiles;
                     conv_residual_prefetch_l2(g, m2 * BM + quad * 32, n2 * BN, first,
@@ -511,29 +514,29 @@ __global__ void __launch_bounds__(epi_warps(EPI) == 8 ? kThreadsConv : kThreads,
                 if (n_blk != bias_blk) {   // tiles run m-fastest: the bias columns change only every m_tiles tiles
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const int c = first + 2 * j;
+                        const int c = first + kPer * j;
                         if (c < chunks) sm.bias_s[epi][j * 32 + lane] = g.bias[colb + c * 32 + lane];
                     }
                     bias_blk = n_blk;
                     __syncwarp();
                 }
-                // This warp's chunks are c = first + 2j.  Residuals ping-pong between two register sets, each
+                // This warp's chunks are c = first + kPer * j.  Residuals ping-pong between two register sets, each
                 // requested one chunk ahead; no register set is ever copied (a copy behind the load waits for it and
                 // exposes one memory round trip per chunk -- measured on the first version of this loop).
-                const int n_mine = chunks > first ? (chunks - first + 1) / 2 : 0;
+                const int n_mine = chunks > first ? (chunks - first + kPer - 1) / kPer : 0;
                 const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
                 uint4 res_a[4] = {}, res_b[4] = {};
                 if (g.residual && n_mine > 0) conv_residual_fetch(g, row0, colb + first * 32, lane, res_a);
 #pragma unroll 1
                 for (int j = 0; j < n_mine; j += 2) {
-                    const int c0 = first + 2 * j, c1 = c0 + 2;
+                    const int c0 = first + kPer * j, c1 = c0 + kPer;
                     if (g.residual && j + 1 < n_mine) conv_residual_fetch(g, row0, colb + c1 * 32, lane, res_b);
                     {
                         uint32_t v[32];
                         tmem_ld32(tacc + c0 * 32, v);
                         conv_epilogue_chunk(g, row0, colb + c0 * 32, lane, v, res_a, &sm.bias_s[epi][j * 32], sm.stage[epi]);
                     }
-                    if (g.residual && j + 2 < n_mine) conv_residual_fetch(g, row0, colb + (c1 + 2) * 32, lane, res_a);
+                    if (g.residual && j + 2 < n_mine) conv_residual_fetch(g, row0, colb + (c1 + kPer) * 32, lane, res_a);
                     if (j + 1 < n_mine) {
                         uint32_t v[32];
                         tmem_ld32(tacc + c1 * 32, v);
@@ -656,7 +659,7 @@ int launch(const void *a, const void *b, const GemmArgs &g, cudaStream_t stream,
     VSC_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int64_t tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
     const int grid = (int)(tiles < sms ? tiles : sms);
-    gemm_kernel<EPI, BN, ALOAD><<<grid, epi_warps(EPI) == 8 ? kThreadsConv : kThreads, smem, stream>>>(ma, mb, g);
+    gemm_kernel<EPI, BN, ALOAD><<<grid, cta_threads(EPI), smem, stream>>>(ma, mb, g);
     VSC_CUDA_CHECK(cudaGetLastError());
     vsc::count_launch();
     return VSC_OK;
