@@ -353,7 +353,7 @@ def run_gpu(args, rank, local_rank, world):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum over the three kernels of one call, from the ncu capture
-# committed under profiles/ (profiles/r01_tn_launches.csv); None until a capture exists.
+# committed under profiles/ (profiles/r01_tn_launches_final.csv, per-launch table r01_tn_launches_final.txt).
 TRAFFIC_BYTES_PER_CALL = 3.88e9  # tn_topk 3.014+0.213, tn_edges 0.152+0.058, tn_dp 0.326+0.116 GB (profiles/r01_tn_summary.md)
 
 
