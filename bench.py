@@ -232,6 +232,43 @@ def stage_numbers(dev, peaks):
         "layerwise_bound": {"frames_per_s": bound, "frac": n / ms * 1e3 / bound,
                             "note": "sum over the 53 convolutions of max(tensor time, HBM time of its bf16 "
                                     "activations); 34 of them are HBM-bound at 288x288"}}
+    del frames_u8
+    torch.cuda.empty_cache()
+
+    # ---- BASELINE.json configs[4] at single-GPU test size: frames -> SSCD -> score-norm search -> TN localization
+    # through the reference-shaped host API (numpy VideoFeatures between the stages, like the reference's .npz files)
+    from vsc2022_b200 import inference_impl, sscd_baseline
+    from vsc2022_b200.score_normalization import score_normalize
+    import numpy as np
+    nq, nr, nn, fr = 50, 400, 50, 40
+    ts = np.stack([np.arange(fr) * 1.0, np.arange(fr) * 1.0 + 1.0], axis=1)
+    make = lambda prefix, count: [(f"{prefix}{i:06d}", ts, torch.randint(0, 256, (fr, 288, 288, 3), generator=g, device=dev,
+                                                                       dtype=torch.uint8)) for i in range(count)]
+    refs_v, queries_v, noise_v = make("R", nr), make("Q", nq), make("N", nn)
+    for i in range(0, nq, 2):                      # every second query carries a 20-frame copy of a reference
+        queries_v[i][2][8:28] = refs_v[(i * 37) % nr][2][4:24]
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    feats = [inference_impl.infer_videos(v, model, batch_size=128, device=dev) for v in (queries_v, refs_v, noise_v)]
+    torch.cuda.synchronize(dev)
+    t1 = time.perf_counter()
+    sn_q, sn_r = score_normalize(feats[0], feats[1], feats[2], beta=1.2)
+    cands = sscd_baseline.search(sn_q, sn_r)
+    torch.cuda.synchronize(dev)
+    t2 = time.perf_counter()
+    matches = sscd_baseline.localize_and_verify(sn_q, sn_r, cands, score_normalization=True)
+    torch.cuda.synchronize(dev)
+    t3 = time.perf_counter()
+    planted = {(f"Q{i:06d}", f"R{(i * 37) % nr:06d}") for i in range(0, nq, 2)}
+    found = {(m.query_id, m.ref_id) for m in matches}
+    n_frames = (nq + nr + nn) * fr
+    out["pipeline_frames_to_matches"] = {
+        "workload": f"c5 at 1-GPU test size: {nq} query + {nr} ref + {nn} noise videos x {fr} frames of 288x288 -> SSCD -> "
+                    "score-norm + global top-K candidates -> TN localization (host API, numpy features between stages)",
+        "seconds": {"descriptors": t1 - t0, "score_norm_and_search": t2 - t1, "localize": t3 - t2, "total": t3 - t0},
+        "frames_per_s_descriptors": n_frames / (t1 - t0), "frames_per_s_total": n_frames / (t3 - t0),
+        "candidates": len(cands), "pairs_localized": min(len(cands), 5 * nq), "matches": len(matches),
+        "planted_pairs_found": len(planted & found), "planted_pairs": len(planted)}
     return out
 
 
