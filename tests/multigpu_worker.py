@@ -36,5 +36,19 @@ lo, hi = D.shard_bounds(len(sims), rank, ws)
 everything = D.gather_lists(model.forward_sim([(str(i), sims[i]) for i in range(lo, hi)]))
 alone = model.forward_sim([(str(i), s) for i, s in enumerate(sims)])
 assert everything == alone, "pair-sharded TN differs from single-GPU TN"
+# stage A: videos sharded i % world, descriptors all-gathered (NCCL) == every video inferred on one GPU
+from vsc2022_b200 import inference_impl  # noqa: E402
+from vsc2022_b200.sscd import SSCDResNet50, TorchReference  # noqa: E402
+ref = TorchReference(seed=1, device=f"cuda:{rank}")
+sscd = SSCDResNet50(ref.trunk, ref.head)
+vrng = np.random.default_rng(9)
+videos = [(f"R{i:06d}", np.arange(n) * 1.0, vrng.integers(0, 256, size=(n, 64, 64, 3), dtype=np.uint8))
+          for i, n in enumerate([5, 9, 3, 12, 7])]
+dev = torch.device("cuda", rank)
+mine = inference_impl.infer_videos([v for _, v in inference_impl.select_videos(videos, rank, ws)], sscd, batch_size=16, device=dev)
+gathered = D.all_gather_video_features(mine, len(videos), device=dev)
+alone_feats = inference_impl.infer_videos(videos, sscd, batch_size=16, device=dev)
+assert all(a.video_id == b.video_id and np.array_equal(a.feature, b.feature) for a, b in zip(gathered, alone_feats)), \
+    "all-gathered descriptors differ from single-GPU inference"
 print(f"MULTIGPU_OK rank={rank} candidates={len(single)} boxes={sum(len(b) for _, b in alone)}", flush=True)
 dist.destroy_process_group()

@@ -37,6 +37,16 @@ def _worker(rank, ws, port, results):
         out["tmax"] = D.max_over_ranks(1.0 + rank, "cpu")
         out["union"] = torch.cat([scores[a:b][: 300 + 100 * r] for r, (a, b) in
                                   enumerate(D.shard_bounds(1000, r, ws) for r in range(ws))]).numpy()
+        # stage A sharding (video i on rank i % ws) followed by the all-gather of the descriptors
+        from vsc2022_b200 import inference_impl
+        from vsc2022_b200.index import VideoFeature
+        vrng = np.random.default_rng(11)
+        videos = [VideoFeature(video_id=f"R{i:06d}", timestamps=np.arange(n) * 1.0,
+                               feature=vrng.normal(size=(n, 8)).astype(np.float32)) for i, n in enumerate([3, 5, 1, 4, 2])]
+        mine_v = [v for _, v in inference_impl.select_videos(videos, rank, ws)]
+        everyone = D.all_gather_video_features(mine_v, len(videos), device="cpu")
+        out["videos_ok"] = all(a.video_id == b.video_id and np.array_equal(a.feature, b.feature) and
+                               np.array_equal(a.timestamps, b.timestamps) for a, b in zip(everyone, videos))
         results[rank] = out
     finally:
         dist.destroy_process_group()
@@ -56,6 +66,7 @@ def test_world_size_2_gloo():
     assert r0["radius_l2"] == r1["radius_l2"] == float(np.sort(union)[49])
     assert r0["count"] == r1["count"] == 300 + 400
     assert r0["tmax"] == r1["tmax"] == 2.0
+    assert r0["videos_ok"] and r1["videos_ok"]
 
 
 def test_shard_bounds_cover_everything_in_order():

@@ -84,3 +84,52 @@ def max_over_ranks(value: float, device, group=None) -> float:
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return float(t.item())
+
+
+def all_gather_rows(t: torch.Tensor, group=None) -> List[torch.Tensor]:
+    """All-gather 2-D tensors [n_r, d] with different n_r; returns the per-rank tensors in rank order."""
+    rank, ws = world(group)
+    if ws == 1:
+        return [t]
+    d = t.shape[1]
+    flat = all_gather_variable(t.reshape(-1).contiguous(), group)
+    n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+    counts = [torch.zeros_like(n) for _ in range(ws)]
+    dist.all_gather(counts, n, group=group)
+    out, at = [], 0
+    for c in counts:
+        rows = int(c.item())
+        out.append(flat[at:at + rows * d].reshape(rows, d))
+        at += rows * d
+    return out
+
+
+def all_gather_video_features(local, n_videos: int, device=None, group=None):
+    """Stage A runs video i on rank i % world_size (inference_impl.select_videos, the reference's VideoDataset rule);
+    the search stage wants every rank to hold ALL reference descriptors (BASELINE.json configs[4]: "ref descriptors
+    NCCL all-gathered over NVLink").  `local`: this rank's VideoFeatures in its own order.  Returns the VideoFeatures of
+    all n_videos videos in global video order on every rank: ids and timestamps travel as small objects, the
+    descriptor rows in one all-gather of device tensors."""
+    import numpy as np
+    from .index import VideoFeature
+    rank, ws = world(group)
+    if ws == 1:
+        return list(local)
+    dim = local[0].feature.shape[1] if local else 0
+    dims = [None] * ws
+    dist.all_gather_object(dims, dim, group=group)
+    dim = max(dims)
+    dtype = np.result_type(*[v.feature.dtype for v in local]) if local else np.float32
+    rows = np.concatenate([v.feature for v in local]) if local else np.zeros((0, dim), dtype)
+    dev = device if device is not None else ("cuda" if dist.get_backend(group) == "nccl" else "cpu")
+    parts = all_gather_rows(torch.from_numpy(np.ascontiguousarray(rows, dtype=np.float32)).to(dev), group)
+    meta = [None] * ws
+    dist.all_gather_object(meta, [(v.video_id, v.timestamps, len(v)) for v in local], group=group)
+    out = [None] * n_videos
+    for r in range(ws):
+        feats, at = parts[r].cpu().numpy(), 0
+        for slot, (vid, ts, n) in zip(range(r, n_videos, ws), meta[r]):
+            out[slot] = VideoFeature(video_id=vid, timestamps=ts, feature=feats[at:at + n].astype(dtype, copy=False))
+            at += n
+    assert all(v is not None for v in out), "every video must be owned by exactly one rank"
+    return out
