@@ -88,7 +88,10 @@ constexpr int kT1MaxThreads = kT1MaxWarps * 32;
 constexpr int kTileRows = 32;
 constexpr int kPanelCols = 64;
 constexpr int kPanelPitch = 68;
-constexpr int kStages = 2;
+#ifndef VSC_T1_STAGES
+#define VSC_T1_STAGES 2
+#endif
+constexpr int kStages = VSC_T1_STAGES;
 constexpr int kPanelBytes = kTileRows * kPanelPitch * 4;
 constexpr int kScratchStash = 0, kScratchVal = 16, kScratchCol = 32;   // word offsets inside the lane's panel row
 static_assert(kScratchCol + vsc::kMaxCand <= kPanelCols, "selection scratch must fit one panel row");
@@ -357,9 +360,17 @@ __device__ unsigned long long g_dp_counters[8];
 #define VSC_CLK_FLUSH() do {} while (0)
 #endif
 
-constexpr int kT2Warps = 2;  // 8 pairs per CTA: small CTAs pack the SMs so a whole batch is one wave
+#ifndef VSC_T2_WARPS
+#define VSC_T2_WARPS 1
+#endif
+// 4 pairs per CTA: small CTAs pack the SMs so a whole batch is one wave (measured at 8000 pairs: 1 warp 0.485 ms,
+// 2 warps 0.493 ms, 4 warps 0.74 ms = two waves)
+constexpr int kT2Warps = VSC_T2_WARPS;
 constexpr int kT2Threads = kT2Warps * 32;
-constexpr int kAhead = 4;    // node-record prefetch distance in row layers
+#ifndef VSC_DP_AHEAD
+#define VSC_DP_AHEAD 6
+#endif
+constexpr int kAhead = VSC_DP_AHEAD;    // node-record prefetch distance in row layers (2: 0.554 ms, 4: 0.505, 6: 0.493, 8: 0.493, 12: 0.494)
 
 // Octet reductions by xor-shuffle (distances 1, 2, 4 stay inside an aligned group of 8 lanes).
 // redux.sync with a per-octet mask compiles to a loop over the distinct masks and cost 38 % of
@@ -436,7 +447,7 @@ __device__ __forceinline__ void relax_node(MaskT pm, MaskT zm, float w, int q, i
 }
 
 template <typename MaskT, int K, int GS>
-__global__ void __launch_bounds__(kT2Threads, 8) tn_dp_kernel(const Batch b, const Workspace w, const WorkList out) {
+__global__ void __launch_bounds__(kT2Threads, 16 / kT2Warps) tn_dp_kernel(const Batch b, const Workspace w, const WorkList out) {
     // WARP-SYNCHRONOUS: the four octets of a warp run every loop together (trip count = the longest of the
     // four, shorter ones are predicated off) and all shuffles use the full mask, so the warp never splits into
     // four serially executed instruction streams.
