@@ -21,7 +21,7 @@ def models():
     return SSCDResNet50(ref.trunk, ref.head), ref
 
 
-@pytest.mark.parametrize("hw", [(64, 64), (96, 128), (288, 288)])
+@pytest.mark.parametrize("hw", [(64, 64), (96, 128), (75, 101), (288, 288)])
 def test_descriptors_match_torch(models, hw):
     import torch
     from vsc2022_b200.sscd import normalize_pixels
