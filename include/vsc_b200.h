@@ -136,6 +136,11 @@ int vsc_gemm_conv(const void *d_a, int64_t m, const void *d_w, int64_t n, int32_
 int vsc_conv3x3(const void *d_in, int32_t n, int32_t h, int32_t w, int32_t c, int32_t stride, const void *d_w,
                 int32_t cout, const float *d_bias, const void *d_residual, int32_t relu, void *d_out_bf16,
                 vsc_stream_t stream);
+/* 1x1 / stride 1|2 convolution (the ResNet downsample branch) through the same TMA im2col path: stride 2 reads every
+ * second pixel of every second row without a subsampled copy.  Weights [cout][c]. */
+int vsc_conv1x1(const void *d_in, int32_t n, int32_t h, int32_t w, int32_t c, int32_t stride, const void *d_w,
+                int32_t cout, const float *d_bias, const void *d_residual, int32_t relu, void *d_out_bf16,
+                vsc_stream_t stream);
 /* fp32 out[m][n] = A . W^T + bias[n] (projection head) */
 int vsc_gemm_linear(const void *d_a, int64_t m, const void *d_w, int64_t n, int32_t k, const float *d_bias, float *d_out,
                     int64_t ldc, vsc_stream_t stream);

@@ -88,6 +88,18 @@ def test_primitives_against_torch():
         assert torch.equal(out2, out)
         cudnn = F.conv2d(x.float().permute(0, 3, 1, 2), wt, bias, stride=stride, padding=1).permute(0, 2, 3, 1).reshape(-1, cout)
         torch.testing.assert_close(cudnn, pre, rtol=0, atol=1e-4)
+    # strided 1x1 (downsample branch) through the TMA traversal stride == GEMM on the explicitly subsampled tensor
+    w1 = (torch.randint(-8, 9, (cout, c), generator=g, device=dev) / 8.0).to(torch.bfloat16).contiguous()
+    h2, w2 = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    sub = x[:, ::2, ::2, :].contiguous().reshape(n * h2 * w2, c)
+    want1 = torch.empty((n * h2 * w2, cout), dtype=torch.bfloat16, device=dev)
+    _lib.check(lib.vsc_gemm_conv(sub.data_ptr(), n * h2 * w2, w1.data_ptr(), cout, c, bias.data_ptr(), None, 0,
+                                 want1.data_ptr(), cout, sp), "conv")
+    got1 = torch.empty_like(want1)
+    _lib.check(lib.vsc_conv1x1(x.data_ptr(), n, h, w, c, 2, w1.data_ptr(), cout, bias.data_ptr(), None, 0, got1.data_ptr(), sp),
+               "conv1x1")
+    assert torch.equal(got1, want1)
+    assert torch.equal(got1.float(), (sub.float() @ w1.float().T + bias).to(torch.bfloat16).float())
     ho, wo = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
     mp = torch.empty((n * ho * wo, c), dtype=torch.bfloat16, device=dev)
     _lib.check(lib.vsc_maxpool3x3s2(x.data_ptr(), n, h, w, c, w, h, mp.data_ptr(), sp), "maxpool")

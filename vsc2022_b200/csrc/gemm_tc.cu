@@ -68,7 +68,7 @@ struct GemmArgs {
     unsigned long long *counters;  // [0] entries claimed (may exceed capacity), [1] hits beyond count_thr
     // implicit 3x3 convolution (A operand loaded by TMA in im2col mode from the NHWC activation tensor):
     // output extent, traversal stride and 64-channel blocks per filter tap
-    int conv_ho, conv_wo, conv_stride, conv_cblocks;
+    int conv_ho, conv_wo, conv_stride, conv_cblocks, conv_ksize, conv_pad;
     // A_SHIFT (stem): k-block kb reads rows m + kb * a_row_shift of an overlapping-row view (see vsc_conv_stem)
     int64_t a_row_shift;
 };
@@ -436,19 +436,19 @@ __global__ void __launch_bounds__(cta_threads(EPI), 1) gemm_kernel(const __grid_
             for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
                 const int m_blk = (int)(t % m_tiles), n_blk = (int)(t / m_tiles);
                 int px = 0, py = 0, pn = 0, tap = 0, cb = 0;
-                if (ALOAD == A_IM2COL) {   // first output pixel of the tile -> base pixel of the 3x3 window (pad 1)
+                if (ALOAD == A_IM2COL) {   // first output pixel of the tile -> base pixel of its filter window
                     const int64_t m0 = (int64_t)m_blk * BM, row = m0 / g.conv_wo;
-                    px = (int)(m0 - row * g.conv_wo) * g.conv_stride - 1;
+                    px = (int)(m0 - row * g.conv_wo) * g.conv_stride - g.conv_pad;
                     pn = (int)(row / g.conv_ho);
-                    py = (int)(row - (int64_t)pn * g.conv_ho) * g.conv_stride - 1;
+                    py = (int)(row - (int64_t)pn * g.conv_ho) * g.conv_stride - g.conv_pad;
                 }
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(&sm.empty[stage], phase ^ 1);
                     mbar_expect_tx(&sm.full[stage], kStageBytesA + kStageBytesB);
                     if (ALOAD == A_SHIFT) {
                         tma_load_2d(sm.a[stage], &tma_a, 0, (int)((int64_t)m_blk * BM + kb * g.a_row_shift), &sm.full[stage]);
-                    } else if (ALOAD == A_IM2COL) {   // K index = (ky*3 + kx)*C + channel
-                        tma_load_im2col(sm.a[stage], &tma_a, cb * BK, px, py, pn, (uint16_t)(tap % 3), (uint16_t)(tap / 3),
+                    } else if (ALOAD == A_IM2COL) {   // K index = (ky*ksize + kx)*C + channel
+                        tma_load_im2col(sm.a[stage], &tma_a, cb * BK, px, py, pn, (uint16_t)(tap % g.conv_ksize), (uint16_t)(tap / g.conv_ksize),
                                         &sm.full[stage]);
                         if (++cb == g.conv_cblocks) { cb = 0; ++tap; }
                     } else
@@ -614,10 +614,10 @@ typedef CUresult (*EncodeIm2colFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_
                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                    CUtensorMapFloatOOBfill);
 
-// NHWC bf16 activation tensor [n][h][w][c] for a 3x3 / pad 1 / stride s convolution: one load = 128 output pixels x
+// NHWC bf16 activation tensor [n][h][w][c] for a k x k / pad p / stride s convolution: one load = 128 output pixels x
 // 64 channels of one filter tap, 128-byte swizzle (the same shared-memory image as a tiled 128 x 64 box).
 // Bounding box corners (cuTensorMapEncodeIm2col): lower = -pad, upper = pad - (filter - 1).
-int make_im2col_map(CUtensorMap *map, const void *ptr, int n, int h, int w, int c, int stride) {
+int make_im2col_map(CUtensorMap *map, const void *ptr, int n, int h, int w, int c, int stride, int ksize, int pad) {
     static EncodeIm2colFn fn = nullptr;
     if (!fn) {
         void *p = nullptr;
@@ -629,7 +629,7 @@ int make_im2col_map(CUtensorMap *map, const void *ptr, int n, int h, int w, int 
     if (!fn) { vsc::set_error("cuTensorMapEncodeIm2col entry point not available"); return VSC_ERR_CUDA; }
     cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
     cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
-    int lower[2] = {-1, -1}, upper[2] = {-1, -1};
+    int lower[2] = {-pad, -pad}, upper[2] = {pad - (ksize - 1), pad - (ksize - 1)};
     cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(ptr), dims, strides, lower, upper,
                     (cuuint32_t)BK, (cuuint32_t)BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -728,30 +728,45 @@ extern "C" int vsc_gemm_conv(const void *d_a, int64_t m, const void *d_w, int64_
     return launch<EPI_CONV, 256>(d_a, d_w, g, stream);
 }
 
-// 3x3 / pad 1 / stride 1|2 convolution straight from the NHWC bf16 activation tensor (implicit GEMM: no patch
-// matrix in memory).  Weights [cout][9*c] with K index = (ky*3 + kx)*c + channel; out[(n*ho + oy)*wo + ox][cout].
-extern "C" int vsc_conv3x3(const void *d_in, int32_t n, int32_t h, int32_t w, int32_t c, int32_t stride, const void *d_w,
-                           int32_t cout, const float *d_bias, const void *d_residual, int32_t relu, void *d_out_bf16,
-                           vsc_stream_t stream_) {
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+// k x k convolution (3x3 / pad 1 or 1x1 / pad 0, stride 1|2) straight from the NHWC bf16 activation tensor (implicit
+// GEMM: no patch matrix and, for the strided 1x1 downsample, no subsampled copy in memory).
+static int conv_implicit(const char *who, const void *d_in, int n, int h, int w, int c, int ksize, int pad, int stride,
+                         const void *d_w, int cout, const float *d_bias, const void *d_residual, int relu,
+                         void *d_out_bf16, cudaStream_t stream) {
     if (c % BK != 0 || cout % 32 != 0 || (stride != 1 && stride != 2) || !d_bias) {
-        vsc::set_error("vsc_conv3x3: need c %% 64 == 0, cout %% 32 == 0, stride in {1,2}, a bias"); return VSC_ERR_INVALID;
+        vsc::set_error("%s: need c %% 64 == 0, cout %% 32 == 0, stride in {1,2}, a bias", who); return VSC_ERR_INVALID;
     }
     if (n <= 0) return VSC_OK;
-    const int ho = (h + 2 - 3) / stride + 1, wo = (w + 2 - 3) / stride + 1;
-    if ((reinterpret_cast<uintptr_t>(d_in) & 15) != 0) { vsc::set_error("vsc_conv3x3: input must be 16-byte aligned"); return VSC_ERR_INVALID; }
+    const int ho = (h + 2 * pad - ksize) / stride + 1, wo = (w + 2 * pad - ksize) / stride + 1;
+    if ((reinterpret_cast<uintptr_t>(d_in) & 15) != 0) { vsc::set_error("%s: input must be 16-byte aligned", who); return VSC_ERR_INVALID; }
     CUtensorMap ma;
-    int rc = make_im2col_map(&ma, d_in, n, h, w, c, stride);
+    int rc = make_im2col_map(&ma, d_in, n, h, w, c, stride, ksize, pad);
     if (rc != VSC_OK) return rc;
     GemmArgs g = {};
-    g.M = (int64_t)n * ho * wo; g.N = cout; g.K = 9 * c; g.bias = d_bias;
+    g.M = (int64_t)n * ho * wo; g.N = cout; g.K = ksize * ksize * c; g.bias = d_bias;
     g.residual = static_cast<const __nv_bfloat16 *>(d_residual); g.relu = relu;
     g.out_bf16 = static_cast<__nv_bfloat16 *>(d_out_bf16); g.ldc = cout;
-    g.conv_ho = ho; g.conv_wo = wo; g.conv_stride = stride; g.conv_cblocks = c / BK;
+    g.conv_ho = ho; g.conv_wo = wo; g.conv_stride = stride; g.conv_cblocks = c / BK; g.conv_ksize = ksize; g.conv_pad = pad;
     const int bn = conv_bn(g.M, cout);
     if (bn == 64) return launch<EPI_CONV, 64, A_IM2COL>(d_in, d_w, g, stream, &ma);
     if (bn == 128) return launch<EPI_CONV, 128, A_IM2COL>(d_in, d_w, g, stream, &ma);
     return launch<EPI_CONV, 256, A_IM2COL>(d_in, d_w, g, stream, &ma);
+}
+
+// 3x3 / pad 1: weights [cout][9*c] with K index = (ky*3 + kx)*c + channel; out[(n*ho + oy)*wo + ox][cout].
+extern "C" int vsc_conv3x3(const void *d_in, int32_t n, int32_t h, int32_t w, int32_t c, int32_t stride, const void *d_w,
+                           int32_t cout, const float *d_bias, const void *d_residual, int32_t relu, void *d_out_bf16,
+                           vsc_stream_t stream) {
+    return conv_implicit("vsc_conv3x3", d_in, n, h, w, c, 3, 1, stride, d_w, cout, d_bias, d_residual, relu, d_out_bf16,
+                         static_cast<cudaStream_t>(stream));
+}
+// 1x1 / stride 1|2 (the ResNet downsample branch): weights [cout][c]; stride 2 reads every second pixel of every
+// second row through the tensor map's traversal strides.
+extern "C" int vsc_conv1x1(const void *d_in, int32_t n, int32_t h, int32_t w, int32_t c, int32_t stride, const void *d_w,
+                           int32_t cout, const float *d_bias, const void *d_residual, int32_t relu, void *d_out_bf16,
+                           vsc_stream_t stream) {
+    return conv_implicit("vsc_conv1x1", d_in, n, h, w, c, 1, 0, stride, d_w, cout, d_bias, d_residual, relu, d_out_bf16,
+                         static_cast<cudaStream_t>(stream));
 }
 
 // The stem GEMM (vsc_conv_stem in sscd_ops.cu): A rows are 64-element windows that start every 16 elements of the

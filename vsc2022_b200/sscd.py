@@ -131,15 +131,15 @@ class SSCDResNet50:
                 stride = blk["c2"].stride
                 identity = x
                 if blk["down"] is not None:
-                    src = x
-                    if stride == 2:
+                    if stride == 2:   # strided 1x1: the TMA traversal stride skips the pixels, no subsampled copy
+                        down = blk["down"]
                         h2, w2 = (h - 1) // 2 + 1, (w - 1) // 2 + 1
-                        src = torch.empty((n * h2 * w2, c), dtype=torch.bfloat16, device=dev)
-                        _lib.check(lib.vsc_subsample2(x.data_ptr(), n, h, w, c, src.data_ptr(), _sp(torch, dev)), "vsc_subsample2")
-                        m_down = n * h2 * w2
+                        identity = torch.empty((n * h2 * w2, down.cout), dtype=torch.bfloat16, device=dev)
+                        _lib.check(lib.vsc_conv1x1(x.data_ptr(), n, h, w, c, 2, down.weight.data_ptr(), down.cout,
+                                                   down.bias.data_ptr(), None, 0, identity.data_ptr(), _sp(torch, dev)),
+                                   "vsc_conv1x1")
                     else:
-                        m_down = n * h * w
-                    identity = self._conv(src, m_down, blk["down"], relu=False)
+                        identity = self._conv(x, n * h * w, blk["down"], relu=False)
                 y = self._conv(x, n * h * w, blk["c1"], relu=True)
                 y, h, w = self._conv3x3(y, n, h, w, blk["c1"].cout, blk["c2"], relu=True)
                 x = self._conv(y, n * h * w, blk["c3"], relu=True, residual=identity)
