@@ -327,13 +327,41 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     return v;
 }
 
-__device__ __forceinline__ void conv_residual_fetch(const GemmArgs &g, int64_t row0, int64_t col0, int lane, uint4 (&r)[4]) {
+// Everything of the CONV epilogue's addressing that does not change from chunk to chunk: the shared-memory byte
+// addresses of the two access patterns of the transpose buffer (lane-invariant: computed once per kernel) and, per tile,
+// the byte offsets of this lane's four (row, 16-byte segment) pieces in the residual / output matrices.  The first
+// version recomputed all of it per chunk: ~690 integer instructions in the kernel, more than its floating-point work.
+struct ConvCtx {
+    uint32_t own[4];       // smem address of unit (lane, q): the row-per-thread pattern
+    uint32_t tr[4];        // smem address of unit (it*8 + lane/4, lane%4): the 4-lanes-per-row pattern
+    uint32_t bias;         // smem address of this warp's bias block
+    int64_t piece[4];      // byte offset of (row0 + it*8 + lane/4, column colb + (lane%4)*8) in a [M][ldc] bf16 matrix
+    uint32_t row_ok;       // bit it: that row is < M
+};
+__device__ __forceinline__ void conv_ctx_init(ConvCtx &cx, uint4 *stage, const float *bias_s, int lane) {
+    const uint32_t base = smem_u32(stage);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        cx.own[q] = base + conv_unit(lane, q) * 16;
+        cx.tr[q] = base + conv_unit(q * 8 + (lane >> 2), lane & 3) * 16;
+    }
+    cx.bias = smem_u32(bias_s);
+}
+__device__ __forceinline__ void conv_ctx_tile(ConvCtx &cx, const GemmArgs &g, int64_t row0, int64_t colb, int lane) {
+    cx.row_ok = 0;
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
         const int64_t row = row0 + it * 8 + (lane >> 2);
-        r[it] = row < g.M ? __ldg(reinterpret_cast<const uint4 *>(g.residual + row * g.ldc + col0) + (lane & 3))
-                          : make_uint4(0, 0, 0, 0);
+        cx.piece[it] = (row * g.ldc + colb + (lane & 3) * 8) * 2;
+        cx.row_ok |= (row < g.M ? 1u : 0u) << it;
     }
+}
+// chunk c of the tile starts c * 64 bytes into every piece
+__device__ __forceinline__ void conv_residual_fetch(const GemmArgs &g, const ConvCtx &cx, int c, uint4 (&r)[4]) {
+    const char *base = reinterpret_cast<const char *>(g.residual) + c * 64;
+#pragma unroll
+    for (int it = 0; it < 4; ++it)
+        r[it] = (cx.row_ok >> it) & 1 ? __ldg(reinterpret_cast<const uint4 *>(base + cx.piece[it])) : make_uint4(0, 0, 0, 0);
 }
 
 // Pull the residual rows of a whole tile (this warp's chunks) from HBM into L2 one tile ahead: the register
@@ -347,11 +375,10 @@ __device__ __forceinline__ void conv_residual_prefetch_l2(const GemmArgs &g, int
         asm volatile("prefetch.global.L2 [%0];" ::"l"(p + c * 32));
 }
 
-__device__ __forceinline__ void conv_epilogue_chunk(const GemmArgs &g, int64_t row0, int64_t col0, int lane,
-                                                    const uint32_t (&acc)[32], const uint4 (&res)[4],
-                                                    const float *bias_chunk, uint4 *stage_ptr) {
+__device__ __forceinline__ void conv_epilogue_chunk(const GemmArgs &g, const ConvCtx &cx, int c, int j,
+                                                    const uint32_t (&acc)[32], const uint4 (&res)[4]) {
     float v[32];
-    const uint32_t stage = smem_u32(stage_ptr), bias_s = smem_u32(bias_chunk);
+    const uint32_t bias_s = cx.bias + j * 128;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         const uint4 bq = lds128(bias_s + q * 16);   // same address in every lane: broadcast
@@ -362,11 +389,11 @@ __device__ __forceinline__ void conv_epilogue_chunk(const GemmArgs &g, int64_t r
     }
     if (g.residual) {
 #pragma unroll
-        for (int it = 0; it < 4; ++it) sts128(stage + conv_unit(it * 8 + (lane >> 2), lane & 3) * 16, res[it]);
+        for (int it = 0; it < 4; ++it) sts128(cx.tr[it], res[it]);
         __syncwarp();
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const uint4 r = lds128(stage + conv_unit(lane, q) * 16);
+            const uint4 r = lds128(cx.own[q]);
             const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
@@ -386,15 +413,14 @@ __device__ __forceinline__ void conv_epilogue_chunk(const GemmArgs &g, int64_t r
             if (g.relu) p = __hmax2(p, __floats2bfloat162_rn(0.0f, 0.0f));
             w[t] = *reinterpret_cast<const uint32_t *>(&p);
         }
-        sts128(stage + conv_unit(lane, q) * 16, make_uint4(w[0], w[1], w[2], w[3]));
+        sts128(cx.own[q], make_uint4(w[0], w[1], w[2], w[3]));
     }
     __syncwarp();
+    char *out = reinterpret_cast<char *>(g.out_bf16) + c * 64;
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
-        const int r = it * 8 + (lane >> 2);
-        const int64_t row = row0 + r;
-        const uint4 o = lds128(stage + conv_unit(r, lane & 3) * 16);
-        if (row < g.M) reinterpret_cast<uint4 *>(g.out_bf16 + row * g.ldc + col0)[lane & 3] = o;
+        const uint4 o = lds128(cx.tr[it]);
+        if ((cx.row_ok >> it) & 1) *reinterpret_cast<uint4 *>(out + cx.piece[it]) = o;
     }
     __syncwarp();   // the buffer is free again
 }
@@ -489,6 +515,8 @@ __global__ void __launch_bounds__(cta_threads(EPI), 1) gemm_kernel(const __grid_
         const int quad = warp & 3;
         int64_t bias_blk = -1;
         EmitState emit = {0ull, 0, 0ull};
+        ConvCtx cx;
+        if (EPI == EPI_CONV) conv_ctx_init(cx, sm.stage[warp - 2], sm.bias_s[warp - 2], lane);
         uint32_t it = 0;
         for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
@@ -525,22 +553,23 @@ __global__ void __launch_bounds__(cta_threads(EPI), 1) gemm_kernel(const __grid_
                 // exposes one memory round trip per chunk -- measured on the first version of this loop).
                 const int n_mine = chunks > first ? (chunks - first + kPer - 1) / kPer : 0;
                 const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
+                conv_ctx_tile(cx, g, row0, colb, lane);
                 uint4 res_a[4] = {}, res_b[4] = {};
-                if (g.residual && n_mine > 0) conv_residual_fetch(g, row0, colb + first * 32, lane, res_a);
+                if (g.residual && n_mine > 0) conv_residual_fetch(g, cx, first, res_a);
 #pragma unroll 1
                 for (int j = 0; j < n_mine; j += 2) {
                     const int c0 = first + kPer * j, c1 = c0 + kPer;
-                    if (g.residual && j + 1 < n_mine) conv_residual_fetch(g, row0, colb + c1 * 32, lane, res_b);
+                    if (g.residual && j + 1 < n_mine) conv_residual_fetch(g, cx, c1, res_b);
                     {
                         uint32_t v[32];
                         tmem_ld32(tacc + c0 * 32, v);
-                        conv_epilogue_chunk(g, row0, colb + c0 * 32, lane, v, res_a, &sm.bias_s[epi][j * 32], sm.stage[epi]);
+                        conv_epilogue_chunk(g, cx, c0, j, v, res_a);
                     }
-                    if (g.residual && j + 2 < n_mine) conv_residual_fetch(g, row0, colb + (c1 + kPer) * 32, lane, res_a);
+                    if (g.residual && j + 2 < n_mine) conv_residual_fetch(g, cx, c1 + kPer, res_a);
                     if (j + 1 < n_mine) {
                         uint32_t v[32];
                         tmem_ld32(tacc + c1 * 32, v);
-                        conv_epilogue_chunk(g, row0, colb + c1 * 32, lane, v, res_b, &sm.bias_s[epi][(j + 1) * 32], sm.stage[epi]);
+                        conv_epilogue_chunk(g, cx, c1, j + 1, v, res_b);
                     }
                 }
             } else {
