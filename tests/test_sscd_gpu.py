@@ -105,3 +105,22 @@ def test_primitives_against_torch():
     _lib.check(lib.vsc_maxpool3x3s2(x.data_ptr(), n, h, w, c, w, h, mp.data_ptr(), sp), "maxpool")
     ref = F.max_pool2d(x.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).reshape(-1, c).to(torch.bfloat16)
     assert torch.equal(mp, ref)
+
+
+def test_descriptors_match_cpu_golden():
+    """tests/golden/sscd_reference.npz (oracle/make_golden_sscd.py): the fp32 PyTorch model evaluated on the CPU."""
+    import os
+    import torch
+    from vsc2022_b200.sscd import SSCDResNet50, TorchReference
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sscd_reference.npz"))
+    ref = TorchReference(seed=int(g["seed"]))
+    probe = np.array([float(ref.trunk.conv1.weight.detach().double().sum()), float(ref.head.weight.detach().double().sum()),
+                      float(ref.trunk.layer4[2].bn3.running_mean.double().sum())])
+    np.testing.assert_allclose(probe, g["weight_probe"], rtol=1e-9, err_msg="seeded weights differ from the fixture's")
+    ours = SSCDResNet50(ref.trunk, ref.head)
+    for tag in ("a", "b"):
+        got = ours(torch.from_numpy(g[f"frames_{tag}"]).cuda()).cpu().numpy()
+        want = g[f"desc_{tag}"]
+        assert _cos(got, want).min() >= 0.999, _cos(got, want)
+        rel = np.linalg.norm(got - want, axis=1) / np.linalg.norm(want, axis=1)
+        assert rel.max() <= 3e-2, rel
