@@ -87,6 +87,35 @@ def test_library_exports_every_declared_symbol():
     assert lib.vsc_abi_version() >= 1
 
 
+def test_ctypes_prototypes_agree_with_the_header():
+    """Every prototype of include/vsc_b200.h against the ctypes declaration in _lib.py: same number of parameters,
+    pointers bound as pointers, 64-bit integers as 64-bit, floats as floats (an ABI drift crashes instead of failing)."""
+    import ctypes
+    from vsc2022_b200 import _lib
+    header = open(os.path.join(REPO, "include", "vsc_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
+    protos = re.findall(r"\b(?:int|int64_t|const char \*)\s*\*?\s*((?:vsc|vcsl)_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", header, flags=re.S)
+    assert len(protos) == len(_lib.EXPORTS), (len(protos), len(_lib.EXPORTS))
+    for name, params in protos:
+        params = " ".join(params.split())
+        args = [] if params in ("", "void") else [a.strip() for a in params.split(",")]
+        _, argtypes = _lib.EXPORTS[name]
+        assert len(args) == len(argtypes), f"{name}: header has {len(args)} parameters, ctypes {len(argtypes)}"
+        for a, t in zip(args, argtypes):
+            if "*" in a or a.startswith("vsc_stream_t"):
+                assert t in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(t, "contents") or issubclass(t, ctypes._Pointer), (name, a, t)
+            elif a.startswith(("int64_t", "uint64_t")):
+                assert t in (ctypes.c_int64, ctypes.c_uint64), (name, a, t)
+            elif a.startswith(("int32_t", "int ", "uint32_t")):
+                assert t in (ctypes.c_int32, ctypes.c_int, ctypes.c_uint32), (name, a, t)
+            elif a.startswith("float"):
+                assert t is ctypes.c_float, (name, a, t)
+            elif a.startswith("double"):
+                assert t is ctypes.c_double, (name, a, t)
+            else:
+                raise AssertionError(f"{name}: unrecognised parameter type {a!r}")
+
+
 def test_product_fails_loudly_without_gpu():
     import torch
     if torch.cuda.is_available():
