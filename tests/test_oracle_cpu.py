@@ -123,3 +123,17 @@ def test_product_fails_loudly_without_gpu():
     from vsc2022_b200 import _lib, vta
     with pytest.raises(_lib.EngineError):
         vta.build_vta_model("TN").forward_sim([("a", np.zeros((4, 4), np.float32))])
+
+
+def test_header_is_plain_c(tmp_path):
+    """The drop-in boundary is a C ABI: include/vsc_b200.h must compile as C99 (no C++ or torch types)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "use_header.c"
+    src.write_text('#include "vsc_b200.h"\nint main(void) { vsc_tn_params p; (void)p; return 0; }\n')
+    out = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I", os.path.join(REPO, "include"),
+                          str(src)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
