@@ -60,6 +60,29 @@ int vcsl_tn_batch(const float *d_sims, const int64_t *d_off, const int32_t *d_lq
                   float *d_box_maxsim, int32_t *d_status, int32_t force_exact_order,
                   vsc_stream_t stream);
 
+/* Stage C straight from frame descriptors: the batch form of VCSLLocalization.localize_all's
+ *     sims = [(key, np.matmul(q.feature, r.feature.T) + similarity_bias) ...]; model.forward_sim(sims)
+ * (vsc/baseline/localization.py:33-36,49-54,57-58).  d_q_panel / d_r_panel are K-major bf16 panels of ALL query /
+ * reference frames (vsc_prepare_operand: k = kpad, or 3*kpad for the split panels); pair p multiplies panel rows
+ * [d_q_start[p], +d_lq[p]) by [d_r_start[p], +d_lr[p]).
+ *
+ * vsc_pair_similarity writes the matrices (row-major lq x lr at element offset d_off[p]).
+ * vcsl_tn_batch_from_features aligns them: when every pair has tn_top_k <= lr <= 512 (min_lr / max_lr, host values)
+ * each 128-row accumulator tile is consumed out of tensor memory by the row top-K and the matrices are written only if
+ * d_sims_out is given (then d_off is required) or MaxSim scores are requested (d_box_maxsim != NULL; scratch memory
+ * when d_sims_out is NULL).  Other shapes compute the matrices first and run vcsl_tn_batch on them.  Outputs as
+ * vcsl_tn_batch. */
+int vsc_pair_similarity(const void *d_q_panel, int64_t q_rows, const void *d_r_panel, int64_t r_rows, int32_t k,
+                        const int32_t *d_q_start, const int32_t *d_lq, const int32_t *d_r_start, const int32_t *d_lr,
+                        int32_t n_pairs, int32_t max_lq, int32_t max_lr, float bias, float *d_sims, const int64_t *d_off,
+                        vsc_stream_t stream);
+int vcsl_tn_batch_from_features(const void *d_q_panel, int64_t q_rows, const void *d_r_panel, int64_t r_rows, int32_t k,
+                                const int32_t *d_q_start, const int32_t *d_lq, const int32_t *d_r_start,
+                                const int32_t *d_lr, int32_t n_pairs, int32_t max_lq, int32_t max_lr, int32_t min_lr,
+                                float similarity_bias, const vsc_tn_params *params, float *d_sims_out,
+                                const int64_t *d_off, int32_t *d_boxes, int32_t *d_n_boxes, float *d_box_maxsim,
+                                int32_t *d_status, int32_t force_exact_order, vsc_stream_t stream);
+
 /* Per-stage device timing of the TN fast pipeline (CUDA events recorded on the caller's stream
  * around each stage).  vsc_tn_last_stage_ms fills {row top-K, edges, sweeps, MaxSim} in ms for the
  * most recent vcsl_tn_batch call; synchronise the stream first. */

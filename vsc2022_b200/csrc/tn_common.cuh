@@ -23,6 +23,11 @@ struct Batch {
     float *box_maxsim;   // [n_pairs][max_path+1] or null
     int32_t *status;     // [n_pairs] or null: which kernel produced the result
     int max_nodes, max_lq, max_lr;
+    // Optional node records of the fast pipeline (Workspace layout, node (q, rank) at [pair * max_nodes + q * topk + rank]).
+    // When set, the general kernel reads its row top-K from them instead of scanning a similarity matrix.
+    const uint16_t *node_ref;
+    const void *node_rec;
+    int node_rec_bytes, node_sim_off;
 };
 
 // A device-side work list: count[0] entries in list[].  in == nullptr means "all pairs".
@@ -30,6 +35,41 @@ struct WorkList {
     int32_t *count;
     int32_t *list;
 };
+
+// ------------------------------------------------------------------ workspace of the fast pipeline
+// Written by the row top-K stage (tn_topk_kernel for similarity matrices in memory, pair_topk_kernel when the
+// similarities come straight out of tensor memory), read by the graph stage.
+struct Workspace {
+    uint16_t *ref_of;   // [P][N] reference frame of node | kSimOk
+    void *rec;          // [P][N] NodeRec: {predecessor mask, zeroed-edge mask, similarity, distance}
+    uint16_t *gen;      // [P][N] Kahn generation
+    int rec_bytes, sim_off;  // record size and byte offset of the similarity inside it
+    int32_t *skip;      // [P] 1 = handed to the general kernel
+    int32_t *cursor;    // T1 tile counter
+};
+
+template <typename MaskT>
+struct alignas(16) NodeRec {
+    MaskT pred, zero;
+    float sim, dist;
+};
+static_assert(sizeof(NodeRec<uint32_t>) == 16 && sizeof(NodeRec<uint64_t>) == 32, "record layout");
+// ref_of entry: reference frame (< 2^15: the pipeline takes rows up to 512 columns) | flag "similarity >= min_sim"
+// (constraint C4, evaluated once by the top-K stage where the similarity is in a register)
+constexpr uint16_t kRefMask = 0x7FFF, kSimOk = 0x8000;
+
+// Descriptor panels of a batch whose similarities are computed on the fly (pair_gemm.cu): pair p multiplies rows
+// [q_start[p], +lq[p]) of the query panel by rows [r_start[p], +lr[p]) of the reference panel and adds `bias`.
+struct PairOperands {
+    const void *q_panel, *r_panel;   // bf16 [rows][k], K-major (vsc_prepare_operand)
+    int64_t q_rows, r_rows;
+    int k;
+    const int32_t *q_start, *r_start;
+    float bias;
+};
+int launch_pair_topk(const PairOperands &op, const Batch &b, const Workspace &w, const WorkList &out, float *sims,
+                     const int64_t *off, int64_t pair_stride, cudaStream_t stream);
+bool pair_topk_supported(const Batch &b);
 
 // General kernel (tn_fused.cu): any shape / alignment.  exact_order=false breaks end-node ties by
 // Kahn generation and appends unresolved pairs to `out`; exact_order=true computes full Kahn
@@ -39,8 +79,13 @@ int launch_fused(const Batch &b, bool exact_order, const WorkList *in, const Wor
 
 // Fast pipeline (tn_pipeline.cu): aligned rows (lr % 4 == 0, 16-byte aligned start, lr <= 512,
 // lr >= topk).  Pairs it cannot finish are appended to `out`.
-int launch_pipeline(const Batch &b, const WorkList &out, cudaStream_t stream);
+int launch_pipeline(const Batch &b, const Workspace &w, const WorkList &out, cudaStream_t stream);
 bool pipeline_supported(const Batch &b);
+// Same pipeline with the row top-K taken straight from descriptor panels (pair_gemm.cu) instead of matrices in memory.
+int launch_pipeline_from_features(const PairOperands &op, const Batch &b, const Workspace &w, const WorkList &out,
+                                  cudaStream_t stream);
+bool graph_supported(const Batch &b);
+int workspace_alloc(const Batch &b, Workspace *w, void **base_out, cudaStream_t stream);
 
 }  // namespace tn
 }  // namespace vsc

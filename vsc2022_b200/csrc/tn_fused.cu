@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(kThreads) tn_kernel(const TnArgs args) {
         const int n = lq * top;
         const int step = a.step;
         const int n_slots = (step - 1) * top;
-        const float *__restrict__ sims = a.sims + a.off[pair];
+        const float *__restrict__ sims = a.sims ? a.sims + a.off[pair] : nullptr;
         const int box_cap = a.max_path + 1;
 
         __syncthreads();  // previous pair fully retired before smem is reused
@@ -242,7 +242,17 @@ __global__ void __launch_bounds__(kThreads) tn_kernel(const TnArgs args) {
         if (tid == 0) { s.sc->n_boxes = 0; s.sc->ambiguous = 0; }
         __syncthreads();
 
-        // ---- phase 1: row top-k (each warp streams whole rows, coalesced)
+        // ---- phase 1: row top-k (each warp streams whole rows, coalesced); or the node records the fast pipeline
+        // already holds for this pair (from-features path: there may be no similarity matrix in memory at all)
+        if (a.node_ref) {
+            for (int i = tid; i < n; i += kThreads) {
+                const int q = i / top, r = i - q * top;
+                const size_t gi = (size_t)pair * a.max_nodes + (size_t)q * a.topk + r;
+                s.ref_of[i] = a.node_ref[gi] & vsc::tn::kRefMask;
+                s.sim_of[i] = *reinterpret_cast<const float *>(static_cast<const unsigned char *>(a.node_rec) +
+                                                              gi * a.node_rec_bytes + a.node_sim_off);
+            }
+        } else
         for (int q = warp; q < lq; q += kWarps) {
             uint32_t key; int col;
             warp_row_topk(sims + (size_t)q * lr, lr, top, lane, key, col);
@@ -424,7 +434,7 @@ __global__ void __launch_bounds__(kThreads) tn_kernel(const TnArgs args) {
         }
         for (int i = tid; i < nb * 4; i += kThreads)
             a.boxes[(size_t)pair * box_cap * 4 + i] = s.sc->boxes[i];
-        if (a.box_maxsim) {
+        if (a.box_maxsim && sims) {
             for (int k = 0; k < nb; ++k) {
                 const int32_t *g = s.sc->boxes + 4 * k;
                 const int h = g[2] - g[0], w = g[3] - g[1];

@@ -34,26 +34,10 @@ using vsc::tn::Batch;
 using vsc::tn::WorkList;
 using vsc::tn::kMaxBoxes;
 using vsc::tn::kMaxTop;
-
-// ------------------------------------------------------------------ workspace
-struct Workspace {
-    uint16_t *ref_of;   // [P][N] reference frame of node
-    void *rec;          // [P][N] NodeRec: {predecessor mask, zeroed-edge mask, similarity, distance}
-    uint16_t *gen;      // [P][N] Kahn generation
-    int rec_bytes, sim_off;  // record size and byte offset of the similarity inside it
-    int32_t *skip;      // [P] 1 = handed to the general kernel
-    int32_t *cursor;    // T1 pair counter
-};
-
-template <typename MaskT>
-struct alignas(16) NodeRec {
-    MaskT pred, zero;
-    float sim, dist;
-};
-static_assert(sizeof(NodeRec<uint32_t>) == 16 && sizeof(NodeRec<uint64_t>) == 32, "record layout");
-// ref_of entry: reference frame (< 2^15: the pipeline takes rows up to 512 columns) | flag "similarity >= min_sim"
-// (constraint C4, evaluated once by T1 where the similarity is in a register)
-constexpr uint16_t kRefMask = 0x7FFF, kSimOk = 0x8000;
+using vsc::tn::Workspace;
+using vsc::tn::NodeRec;
+using vsc::tn::kRefMask;
+using vsc::tn::kSimOk;
 
 // ------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -785,21 +769,28 @@ static void mark(int i, cudaStream_t stream) {
     if (i == 4) g_ev_valid = true;
 }
 
-bool pipeline_supported(const Batch &b) {
-    if (b.max_lr > vsc::kBlockCols * vsc::kMaxRowBlocks || b.max_lr < b.topk) return false;
+// what the graph stage (edges + sweeps) needs, whatever produced the node records
+bool graph_supported(const Batch &b) {
     if (b.topk < 1 || b.topk > kMaxTop) return false;
     if ((b.step - 1) * 8 > 32 && (b.step - 1) * b.topk > 64) return false;   // predecessor mask width
-    if ((reinterpret_cast<uintptr_t>(b.sims) & 15u) != 0 || (reinterpret_cast<uintptr_t>(b.boxes) & 15u) != 0) return false;
-    if (b.max_nodes > 65535) return false;
+    if ((reinterpret_cast<uintptr_t>(b.boxes) & 15u) != 0) return false;
+    if (b.max_nodes > 65535 || b.max_lr > kRefMask) return false;
     if (t2_pair_bytes(b.max_nodes, b.max_lq, b.step) * kT2Warps * 4 > 200 * 1024) return false;
+    return true;
+}
+
+bool pipeline_supported(const Batch &b) {
+    if (!graph_supported(b)) return false;
+    if (b.max_lr > vsc::kBlockCols * vsc::kMaxRowBlocks || b.max_lr < b.topk) return false;
+    if ((reinterpret_cast<uintptr_t>(b.sims) & 15u) != 0) return false;
     if ((long long)b.n_pairs * ((b.max_lq + kTileRows - 1) / kTileRows) >= (1ll << 31) - 65536) return false;  // tile ids
     return t1_warps(b.max_lr) >= 1;
 }
 
-int launch_pipeline(const Batch &b, const WorkList &out, cudaStream_t stream) {
+// One stream-ordered allocation holding the node records, carved by alignment; flags and counters zeroed.
+int workspace_alloc(const Batch &b, Workspace *w, void **base_out, cudaStream_t stream) {
     const bool wide = (b.step - 1) * 8 > 32;   // fast variant: 32-bit masks with a group stride of 8 slots
     const size_t P = (size_t)b.n_pairs, N = (size_t)b.max_nodes;
-    // one stream-ordered allocation, carved by alignment
     size_t sz = 0;
     auto take = [&](size_t bytes) { size_t at = sz; sz += (bytes + 255) / 256 * 256; return at; };
     const size_t rec_bytes = wide ? sizeof(NodeRec<uint64_t>) : sizeof(NodeRec<uint32_t>);
@@ -808,42 +799,49 @@ int launch_pipeline(const Batch &b, const WorkList &out, cudaStream_t stream) {
     const size_t o_skip = take(P * 4), o_cursor = take(4);
     unsigned char *base = nullptr;
     VSC_CUDA_CHECK(cudaMallocAsync(&base, sz, stream));
-    Workspace w;
-    w.rec = base + o_rec; w.rec_bytes = (int)rec_bytes; w.sim_off = wide ? 16 : 8;
-    w.ref_of = reinterpret_cast<uint16_t *>(base + o_ref); w.gen = reinterpret_cast<uint16_t *>(base + o_gen);
-    w.skip = reinterpret_cast<int32_t *>(base + o_skip); w.cursor = reinterpret_cast<int32_t *>(base + o_cursor);
+    *base_out = base;
+    w->rec = base + o_rec; w->rec_bytes = (int)rec_bytes; w->sim_off = wide ? 16 : 8;
+    w->ref_of = reinterpret_cast<uint16_t *>(base + o_ref); w->gen = reinterpret_cast<uint16_t *>(base + o_gen);
+    w->skip = reinterpret_cast<int32_t *>(base + o_skip); w->cursor = reinterpret_cast<int32_t *>(base + o_cursor);
+    VSC_CUDA_CHECK(cudaMemsetAsync(w->gen, 0, P * N * 2, stream));
+    VSC_CUDA_CHECK(cudaMemsetAsync(w->skip, 0, (o_cursor - o_skip) + 4, stream));
+    return VSC_OK;
+}
+
+// T1: row top-K of similarity matrices resident in memory
+static int launch_row_topk(const Batch &b, const Workspace &w, const WorkList &out, cudaStream_t stream) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    T1Args a; a.b = b; a.w = w; a.out = out;
+    a.tiles_per_pair = (b.max_lq + kTileRows - 1) / kTileRows;
+    a.n_tiles = b.n_pairs * a.tiles_per_pair;
+    a.warp_bytes = (int)t1_warp_bytes(b.max_lr);
+    const int warps = t1_warps(b.max_lr);
+    const int grid = sms;  // persistent: one CTA per SM
+    int rc;
+    switch (b.topk) {
+        case 1: rc = launch_topk<1>(a, grid, warps, stream); break;
+        case 2: rc = launch_topk<2>(a, grid, warps, stream); break;
+        case 3: rc = launch_topk<3>(a, grid, warps, stream); break;
+        case 4: rc = launch_topk<4>(a, grid, warps, stream); break;
+        case 5: rc = launch_topk<5>(a, grid, warps, stream); break;
+        case 6: rc = launch_topk<6>(a, grid, warps, stream); break;
+        case 7: rc = launch_topk<7>(a, grid, warps, stream); break;
+        default: rc = launch_topk<8>(a, grid, warps, stream); break;
+    }
+    vsc::count_launch();
+    return rc;
+}
+
+// edges + longest-path sweeps (+ MaxSim when the similarity matrices are in memory) on the node records of `w`
+static int launch_graph(const Batch &b, const Workspace &w, const WorkList &out, cudaStream_t stream) {
+    const bool wide = (b.step - 1) * 8 > 32;
     int rc = VSC_OK;
     auto fail = [&](cudaError_t e, const char *what) {
         if (e != cudaSuccess && rc == VSC_OK) { vsc::set_error("%s: %s", what, cudaGetErrorString(e)); rc = VSC_ERR_CUDA; }
     };
-    fail(cudaMemsetAsync(w.gen, 0, P * N * 2, stream), "memset generations");
-    fail(cudaMemsetAsync(w.skip, 0, (o_cursor - o_skip) + 4, stream), "memset flags");
-
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    mark(0, stream);
-    if (rc == VSC_OK) {
-        T1Args a; a.b = b; a.w = w; a.out = out;
-        a.tiles_per_pair = (b.max_lq + kTileRows - 1) / kTileRows;
-        a.n_tiles = b.n_pairs * a.tiles_per_pair;
-        a.warp_bytes = (int)t1_warp_bytes(b.max_lr);
-        const int warps = t1_warps(b.max_lr);
-        const int grid = sms;  // persistent: one CTA per SM
-        switch (b.topk) {
-            case 1: rc = launch_topk<1>(a, grid, warps, stream); break;
-            case 2: rc = launch_topk<2>(a, grid, warps, stream); break;
-            case 3: rc = launch_topk<3>(a, grid, warps, stream); break;
-            case 4: rc = launch_topk<4>(a, grid, warps, stream); break;
-            case 5: rc = launch_topk<5>(a, grid, warps, stream); break;
-            case 6: rc = launch_topk<6>(a, grid, warps, stream); break;
-            case 7: rc = launch_topk<7>(a, grid, warps, stream); break;
-            default: rc = launch_topk<8>(a, grid, warps, stream); break;
-        }
-        vsc::count_launch();
-    }
-    mark(1, stream);
-    if (rc == VSC_OK) {
+    {
         const long long threads = (long long)b.n_pairs * b.max_lq;
         const int grid = (int)((threads + 255) / 256);
         if (wide) launch_edges<uint64_t, 0>(b, w, grid, stream);
@@ -862,13 +860,29 @@ int launch_pipeline(const Batch &b, const WorkList &out, cudaStream_t stream) {
         vsc::count_launch();
     }
     mark(3, stream);
-    if (rc == VSC_OK && b.box_maxsim) {
+    if (rc == VSC_OK && b.box_maxsim && b.sims) {
         tn_maxsim_kernel<<<(b.n_pairs + 3) / 4, 128, 0, stream>>>(b, w);
         fail(cudaGetLastError(), "tn_maxsim_kernel");
         vsc::count_launch();
     }
     mark(4, stream);
-    cudaFreeAsync(base, stream);
+    return rc;
+}
+
+int launch_pipeline(const Batch &b, const Workspace &w, const WorkList &out, cudaStream_t stream) {
+    mark(0, stream);
+    int rc = launch_row_topk(b, w, out, stream);
+    mark(1, stream);
+    if (rc == VSC_OK) rc = launch_graph(b, w, out, stream);
+    return rc;
+}
+
+int launch_pipeline_from_features(const PairOperands &op, const Batch &b, const Workspace &w, const WorkList &out,
+                                  cudaStream_t stream) {
+    mark(0, stream);
+    int rc = launch_pair_topk(op, b, w, out, const_cast<float *>(b.sims), b.off, 0, stream);
+    mark(1, stream);
+    if (rc == VSC_OK) rc = launch_graph(b, w, out, stream);
     return rc;
 }
 
@@ -899,62 +913,156 @@ extern "C" int vsc_tn_debug_counters(unsigned long long *out8) {
     return VSC_OK;
 }
 
-extern "C" int vcsl_tn_batch(const float *d_sims, const int64_t *d_off, const int32_t *d_lq,
-                             const int32_t *d_lr, int32_t n_pairs, int32_t max_lq, int32_t max_lr,
-                             const vsc_tn_params *p, int32_t *d_boxes, int32_t *d_n_boxes,
-                             float *d_box_maxsim, int32_t *d_status, int32_t force_exact_order,
-                             vsc_stream_t stream_) {
-    using namespace vsc::tn;
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    if (!p || n_pairs < 0) { vsc::set_error("vcsl_tn_batch: bad arguments"); return VSC_ERR_INVALID; }
-    if (n_pairs == 0) return VSC_OK;
-    vsc::keep_pool_cached();
-    if (!d_sims || !d_off || !d_lq || !d_lr || !d_boxes || !d_n_boxes) {
-        vsc::set_error("vcsl_tn_batch: null device pointer"); return VSC_ERR_INVALID;
-    }
+namespace {
+
+__global__ void strided_offsets_kernel(int64_t *off, int n, int64_t stride) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) off[i] = (int64_t)i * stride;
+}
+
+int check_params(const vsc_tn_params *p, int32_t n_pairs, int32_t max_lq, int32_t max_lr, const char *who) {
+    if (!p || n_pairs < 0) { vsc::set_error("%s: bad arguments", who); return VSC_ERR_INVALID; }
     if (p->tn_top_k < 1 || p->tn_top_k > kMaxTop || p->tn_max_step < 1 || p->tn_max_step > 31 ||
         (p->tn_max_step - 1) * p->tn_top_k > 64 || p->max_path < 0 || p->max_path + 1 > kMaxBoxes) {
-        vsc::set_error("vcsl_tn_batch: unsupported parameters (need tn_top_k<=%d, "
-                       "(tn_max_step-1)*tn_top_k<=64, max_path<%d)", kMaxTop, kMaxBoxes);
+        vsc::set_error("%s: unsupported parameters (need tn_top_k<=%d, "
+                       "(tn_max_step-1)*tn_top_k<=64, max_path<%d)", who, kMaxTop, kMaxBoxes);
         return VSC_ERR_INVALID;
     }
     if (max_lr > 65535 || max_lq < 0 || max_lr < 0) {
-        vsc::set_error("vcsl_tn_batch: max_lr %d out of range (<= 65535)", max_lr);
+        vsc::set_error("%s: max_lr %d out of range (<= 65535)", who, max_lr);
         return VSC_ERR_INVALID;
     }
-    Batch b;
-    b.sims = d_sims; b.off = d_off; b.lq = d_lq; b.lr = d_lr; b.n_pairs = n_pairs;
+    return VSC_OK;
+}
+
+void fill_batch(vsc::tn::Batch &b, const vsc_tn_params *p, int32_t max_lq, int32_t max_lr) {
     b.step = p->tn_max_step; b.topk = p->tn_top_k; b.max_path = p->max_path;
     b.min_sim = p->min_sim; b.min_length = p->min_length; b.max_iou = p->max_iou;
-    b.boxes = d_boxes; b.n_boxes = d_n_boxes; b.box_maxsim = d_box_maxsim; b.status = d_status;
     b.max_lq = max_lq > 0 ? max_lq : 1;
     b.max_lr = max_lr;
     b.max_nodes = b.max_lq * (p->tn_top_k < max_lr ? p->tn_top_k : (max_lr > 0 ? max_lr : 1));
+}
+
+// The whole alignment of a batch.  `op` != null: the similarities come from descriptor panels (b.sims is then either
+// null or the buffer the matrices are to be written to); `features_direct`: the row top-K may run straight out of
+// tensor memory (every pair has at least topk columns).
+int run_tn(vsc::tn::Batch b, const vsc::tn::PairOperands *op, bool features_direct, int force_exact_order,
+           cudaStream_t stream) {
+    using namespace vsc::tn;
     if (b.max_nodes > 65535) {
         vsc::set_error("vcsl_tn_batch: %d graph nodes exceed the 16-bit node index", b.max_nodes);
         return VSC_ERR_CAPACITY;
     }
     // two device-side work lists: [count, ids...]
     int32_t *lists = nullptr;
-    const size_t list_len = (size_t)n_pairs + 1;
+    const size_t list_len = (size_t)b.n_pairs + 1;
     VSC_CUDA_CHECK(cudaMallocAsync(&lists, sizeof(int32_t) * 2 * list_len, stream));
     WorkList A{lists, lists + 1}, B{lists + list_len, lists + list_len + 1};
     int rc = VSC_OK;
+    void *ws_base = nullptr;
     cudaError_t e = cudaMemsetAsync(lists, 0, sizeof(int32_t), stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(lists + list_len, 0, sizeof(int32_t), stream);
     if (e != cudaSuccess) { vsc::set_error("memset: %s", cudaGetErrorString(e)); rc = VSC_ERR_CUDA; }
     if (rc == VSC_OK) {
+        Workspace w;
         if (force_exact_order) {
-            iota_kernel<<<(n_pairs + 255) / 256, 256, 0, stream>>>(B.count, B.list, n_pairs);
+            iota_kernel<<<(b.n_pairs + 255) / 256, 256, 0, stream>>>(B.count, B.list, b.n_pairs);
             vsc::count_launch();
+        } else if (op && features_direct && graph_supported(b) && pair_topk_supported(b)) {
+            rc = workspace_alloc(b, &w, &ws_base, stream);
+            if (rc == VSC_OK) rc = launch_pipeline_from_features(*op, b, w, A, stream);
+            if (rc == VSC_OK) {   // pairs handed back read their node records instead of a similarity matrix
+                Batch bn = b;
+                bn.node_ref = w.ref_of; bn.node_rec = w.rec; bn.node_rec_bytes = w.rec_bytes; bn.node_sim_off = w.sim_off;
+                rc = launch_fused(bn, false, &A, &B, 2, stream);
+                if (rc == VSC_OK) rc = launch_fused(bn, true, &B, nullptr, 1, stream);
+            }
+            if (ws_base) cudaFreeAsync(ws_base, stream);
+            cudaFreeAsync(lists, stream);
+            return rc;
         } else if (pipeline_supported(b)) {
-            rc = launch_pipeline(b, A, stream);
+            rc = workspace_alloc(b, &w, &ws_base, stream);
+            if (rc == VSC_OK) rc = launch_pipeline(b, w, A, stream);
             if (rc == VSC_OK) rc = launch_fused(b, false, &A, &B, 2, stream);
         } else {
             rc = launch_fused(b, false, nullptr, &B, 2, stream);
         }
     }
     if (rc == VSC_OK) rc = launch_fused(b, true, &B, nullptr, 1, stream);
+    if (ws_base) cudaFreeAsync(ws_base, stream);
     cudaFreeAsync(lists, stream);
+    return rc;
+}
+
+}  // namespace
+
+extern "C" int vcsl_tn_batch(const float *d_sims, const int64_t *d_off, const int32_t *d_lq,
+                             const int32_t *d_lr, int32_t n_pairs, int32_t max_lq, int32_t max_lr,
+                             const vsc_tn_params *p, int32_t *d_boxes, int32_t *d_n_boxes,
+                             float *d_box_maxsim, int32_t *d_status, int32_t force_exact_order,
+                             vsc_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    int rc = check_params(p, n_pairs, max_lq, max_lr, "vcsl_tn_batch");
+    if (rc != VSC_OK) return rc;
+    if (n_pairs == 0) return VSC_OK;
+    vsc::keep_pool_cached();
+    if (!d_sims || !d_off || !d_lq || !d_lr || !d_boxes || !d_n_boxes) {
+        vsc::set_error("vcsl_tn_batch: null device pointer"); return VSC_ERR_INVALID;
+    }
+    vsc::tn::Batch b = {};
+    b.sims = d_sims; b.off = d_off; b.lq = d_lq; b.lr = d_lr; b.n_pairs = n_pairs;
+    b.boxes = d_boxes; b.n_boxes = d_n_boxes; b.box_maxsim = d_box_maxsim; b.status = d_status;
+    fill_batch(b, p, max_lq, max_lr);
+    return run_tn(b, nullptr, false, force_exact_order, stream);
+}
+
+extern "C" int vcsl_tn_batch_from_features(const void *d_q_panel, int64_t q_rows, const void *d_r_panel, int64_t r_rows,
+                                           int32_t k, const int32_t *d_q_start, const int32_t *d_lq,
+                                           const int32_t *d_r_start, const int32_t *d_lr, int32_t n_pairs,
+                                           int32_t max_lq, int32_t max_lr, int32_t min_lr, float similarity_bias,
+                                           const vsc_tn_params *p, float *d_sims_out, const int64_t *d_off,
+                                           int32_t *d_boxes, int32_t *d_n_boxes, float *d_box_maxsim, int32_t *d_status,
+                                           int32_t force_exact_order, vsc_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    int rc = check_params(p, n_pairs, max_lq, max_lr, "vcsl_tn_batch_from_features");
+    if (rc != VSC_OK) return rc;
+    if (n_pairs == 0) return VSC_OK;
+    vsc::keep_pool_cached();
+    if (!d_q_panel || !d_r_panel || !d_q_start || !d_lq || !d_r_start || !d_lr || !d_boxes || !d_n_boxes ||
+        (d_sims_out && !d_off)) {
+        vsc::set_error("vcsl_tn_batch_from_features: null device pointer"); return VSC_ERR_INVALID;
+    }
+    vsc::tn::Batch b = {};
+    b.lq = d_lq; b.lr = d_lr; b.n_pairs = n_pairs;
+    b.boxes = d_boxes; b.n_boxes = d_n_boxes; b.box_maxsim = d_box_maxsim; b.status = d_status;
+    fill_batch(b, p, max_lq, max_lr);
+    vsc::tn::PairOperands op = {d_q_panel, d_r_panel, q_rows, r_rows, k, d_q_start, d_r_start, similarity_bias};
+
+    // The row top-K runs out of tensor memory when every pair has at least tn_top_k columns and at most 512; the
+    // similarity matrices are only written when the caller wants them back or a MaxSim score has to read them.
+    const bool direct = !force_exact_order && min_lr >= p->tn_top_k && vsc::tn::graph_supported(b) &&
+                        vsc::tn::pair_topk_supported(b);
+    const bool need_sims = d_sims_out || d_box_maxsim || !direct;
+    float *sims = d_sims_out;
+    int64_t *off_tmp = nullptr;
+    float *sims_tmp = nullptr;
+    if (need_sims && !sims) {   // scratch matrices: pair p at p * stride
+        const int64_t stride = (((int64_t)b.max_lq * (max_lr > 0 ? max_lr : 1)) + 3) & ~(int64_t)3;
+        VSC_CUDA_CHECK(cudaMallocAsync(&sims_tmp, sizeof(float) * (size_t)stride * n_pairs + 16, stream));
+        VSC_CUDA_CHECK(cudaMallocAsync(&off_tmp, sizeof(int64_t) * n_pairs, stream));
+        strided_offsets_kernel<<<(n_pairs + 255) / 256, 256, 0, stream>>>(off_tmp, n_pairs, stride);
+        vsc::count_launch();
+        sims = sims_tmp; d_off = off_tmp;
+    }
+    b.sims = sims; b.off = d_off;
+    if (direct) {
+        rc = run_tn(b, &op, true, 0, stream);
+    } else {
+        rc = vsc_pair_similarity(d_q_panel, q_rows, d_r_panel, r_rows, k, d_q_start, d_lq, d_r_start, d_lr, n_pairs,
+                                 max_lq, max_lr, similarity_bias, sims, d_off, stream_);
+        if (rc == VSC_OK) rc = run_tn(b, nullptr, false, force_exact_order, stream);
+    }
+    if (sims_tmp) cudaFreeAsync(sims_tmp, stream);
+    if (off_tmp) cudaFreeAsync(off_tmp, stream);
     return rc;
 }

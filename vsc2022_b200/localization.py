@@ -1,18 +1,24 @@
 """`vsc.baseline.localization` mirror (localization.py:16-96): align candidate pairs, emit Match rows.
 
-Same classes and signatures as the reference.  `VCSLLocalization.localize_all` keeps everything on the device:
-the frame descriptors of the videos involved are uploaded once, each pair's similarity matrix Q.R^T + bias is
-written straight into the packed buffer the TN kernels read (pairs of equal shape are multiplied together as one
-strided-batched fp32 GEMM -- a plain library GEMM, the fused tensor-core kernel for it is listed in DESIGN.md),
-the TN pipeline aligns the whole batch in one call, and the MaxSim box score comes back from the same call.
-Only the boxes (a few integers per pair) return to the host, where they are mapped to timestamps.
+Same classes and signatures as the reference.  `VCSLLocalization.localize_all` is one engine call per batch:
+
+* the frame descriptors of the videos involved are uploaded once (a collection that consists of row views of one big
+  array -- what `storage.load_features` returns -- goes up in a single copy; float16 descriptors are widened on the
+  device) and turned into the K-major bf16 panels of the tensor-core GEMM (3-term split unless every value is
+  bf16-representable, see gemm.py);
+* `vcsl_tn_batch_from_features` multiplies every pair Q_p . R_p^T + bias on tcgen05 tensor cores and runs the temporal
+  network on the result; for the usual shapes the Lq x Lr matrices never leave tensor memory
+  (csrc/pair_gemm.cu).  They are written out only when a scorer reads them (MaxSim) -- and even then stay on the device:
+  the box maxima come back with the boxes;
+* only the boxes (a few integers per pair) return to the host, where they are mapped to timestamps with array
+  operations (no per-pair Python work for pairs without a match).
 """
 import abc
 from typing import Dict, List
 
 import numpy as np
 
-from . import _lib
+from . import _lib, gemm
 from .index import VideoFeature
 from .metrics import CandidatePair, Match
 
@@ -39,41 +45,130 @@ class LocalizationWithMetadata(Localization):
         return np.matmul(self.queries[candidate.query_id].feature, self.refs[candidate.ref_id].feature.T)
 
 
+def _root_of(arr: np.ndarray):
+    """(root array, first row of `arr` inside it) if `arr` is a block of whole rows of a 2-D base array, else None."""
+    root = arr
+    while isinstance(root.base, np.ndarray):
+        root = root.base
+    if root is arr or arr.ndim != 2 or root.ndim != 2 or arr.dtype != root.dtype:
+        return None
+    if arr.shape[1] != root.shape[1] or root.strides != (root.shape[1] * root.itemsize, root.itemsize):
+        return None
+    if arr.shape[0] and arr.strides != root.strides:
+        return None
+    delta = arr.__array_interface__["data"][0] - root.__array_interface__["data"][0]
+    row, rem = divmod(delta, root.strides[0])
+    if rem or row < 0 or row + arr.shape[0] > root.shape[0]:
+        return None
+    return root, int(row)
+
+
 class _DeviceVideos:
-    """Frame descriptors of a video collection, concatenated on the device, uploaded lazily per video."""
+    """Frame descriptors (and timestamps) of a video collection on the device, uploaded lazily.
+
+    Rows live in one float32 matrix; `start[id]` / `length[id]` locate a video.  Videos that are row views of a
+    shared base array are uploaded with that array in one copy; anything else is concatenated on the host first."""
+
+    MAX_WASTE = 8   # upload a shared base whole unless it is this many times larger than what the batch needs
 
     def __init__(self, videos: Dict[object, VideoFeature], device):
         self.videos, self.device = videos, device
-        self.slot: Dict[object, int] = {}
-        self.start: List[int] = []
-        self.length: List[int] = []
-        self.chunks = []
+        self.start: Dict[object, int] = {}
+        self.length: Dict[object, int] = {}
+        self.segments = []          # device float32 [rows_i, d]
         self.rows = 0
+        self.version = 0            # bumps whenever rows are added
+        self._roots = {}            # id(root) -> (root, first device row)
         self._cat = None
+        self._ts = [[], []]         # per segment: host arrays of frame start / end timestamps
+        self._ts_cat = None
+        self.h2d_bytes = 0
+
+    def _upload(self, host: np.ndarray):
+        torch = _lib.require_cuda()
+        if host.dtype not in (np.float32, np.float16):
+            host = host.astype(np.float32)
+        t = torch.from_numpy(host)
+        self.h2d_bytes += t.numel() * t.element_size()
+        d = t.to(self.device, non_blocking=True)
+        if d.dtype != torch.float32:
+            d = d.float()           # --store_fp16 descriptors (inference_impl.py:230-231): widened on the device
+        first = self.rows
+        self.segments.append(d)
+        self.rows += d.shape[0]
+        self._ts[0].append(np.zeros(d.shape[0]))
+        self._ts[1].append(np.zeros(d.shape[0]))
+        self._cat = self._ts_cat = None
+        self.version += 1
+        return first, len(self.segments) - 1
+
+    def _register(self, vid, first_row: int, seg: int, seg_first: int):
+        v = self.videos[vid]
+        n = len(v)
+        self.start[vid], self.length[vid] = first_row, n
+        ts = np.asarray(v.timestamps)
+        lo = first_row - seg_first
+        if ts.ndim == 1:          # VideoMetadata.get_timestamps: (t, t) for instants, (t[0], t[1]) for intervals
+            self._ts[0][seg][lo:lo + n] = ts
+            self._ts[1][seg][lo:lo + n] = ts
+        else:
+            self._ts[0][seg][lo:lo + n] = ts[:, 0]
+            self._ts[1][seg][lo:lo + n] = ts[:, 1]
+        self._ts_cat = None
 
     def ensure(self, ids):
-        torch = _lib.require_cuda()
-        new = [i for i in dict.fromkeys(ids) if i not in self.slot]
-        if new:
-            host = np.concatenate([np.asarray(self.videos[i].feature, dtype=np.float32) for i in new])
-            self.chunks.append(torch.from_numpy(host).to(self.device, non_blocking=True))
-            for i in new:
-                self.slot[i] = len(self.start)
-                self.start.append(self.rows)
-                self.length.append(len(self.videos[i]))
-                self.rows += len(self.videos[i])
-            self._cat = None
+        new = [i for i in dict.fromkeys(ids) if i not in self.start]
+        if not new:
+            return
+        loose = []
+        by_root = {}
+        for i in new:
+            f = np.asarray(self.videos[i].feature)
+            if f.ndim != 2:
+                raise ValueError("descriptors must be 2-D (frames x dimensions)")
+            where = _root_of(f)
+            if where is None:
+                loose.append(i)
+            else:
+                by_root.setdefault(id(where[0]), (where[0], []))[1].append((i, where[1]))
+        for key, (root, members) in by_root.items():
+            if key not in self._roots:
+                need = sum(len(self.videos[i]) for i, _ in members)
+                if root.shape[0] > self.MAX_WASTE * max(need, 1) and root.nbytes > (1 << 28):
+                    loose.extend(i for i, _ in members)
+                    continue
+                first, seg = self._upload(root)
+                self._roots[key] = (root, first, seg)
+            _, first, seg = self._roots[key]
+            for i, row in members:
+                self._register(i, first + row, seg, first)
+        if loose:
+            host = np.concatenate([np.asarray(self.videos[i].feature, dtype=np.float32) for i in loose])
+            first, seg = self._upload(host)
+            at = first
+            for i in loose:
+                self._register(i, at, seg, first)
+                at += len(self.videos[i])
 
     def matrix(self):
         torch = _lib.require_cuda()
         if self._cat is None:
-            self._cat = self.chunks[0] if len(self.chunks) == 1 else torch.cat(self.chunks)
-            self.chunks = [self._cat]
+            dims = {s.shape[1] for s in self.segments}
+            if len(dims) != 1:
+                raise ValueError(f"descriptors of different dimensions in one collection: {sorted(dims)}")
+            self._cat = self.segments[0] if len(self.segments) == 1 else torch.cat(self.segments)
         return self._cat
+
+    def timestamps(self):
+        if self._ts_cat is None:
+            self._ts_cat = (np.concatenate(self._ts[0]), np.concatenate(self._ts[1]))
+        return self._ts_cat
 
 
 class VCSLLocalization(LocalizationWithMetadata):
-    GROUP_ROWS = 1 << 22   # gathered descriptor rows per batched GEMM (bounds the temporary to ~8 GB at d=512)
+    # what score() reads from its `similarity` argument: "none", "boxmax" (only similarity[x1:x2, y1:y2].max()) or
+    # "full" (anything: the matrices are brought to the host; subclasses with their own score() get this)
+    similarity_use = "none"
 
     def __init__(self, queries, refs, model_type, similarity_bias=0.0, **kwargs):
         super().__init__(queries, refs)
@@ -81,71 +176,96 @@ class VCSLLocalization(LocalizationWithMetadata):
         self.model = build_vta_model(model_type, **kwargs)
         self.similarity_bias = similarity_bias
         self._dq = self._dr = None
+        self._panels = None
 
     def similarity(self, candidate: CandidatePair):
         """Add an optional similarity bias (some aligners do not tolerate negative values well)."""
         return super().similarity(candidate) + self.similarity_bias
 
     # ---- device path ----------------------------------------------------------------------------------------
-    def _pack_similarities(self, candidates):
-        """All similarity matrices, computed on the device, in one packed float32 buffer (16-byte aligned pairs)."""
-        torch = _lib.require_cuda()
-        dev = self.model._device()
+    def _stores(self):
         if self._dq is None:
+            dev = self.model._device()
             self._dq, self._dr = _DeviceVideos(self.queries, dev), _DeviceVideos(self.refs, dev)
-        self._dq.ensure([c.query_id for c in candidates])
-        self._dr.ensure([c.ref_id for c in candidates])
-        Q, R = self._dq.matrix(), self._dr.matrix()
-        n = len(candidates)
-        qs = np.array([self._dq.slot[c.query_id] for c in candidates])
-        rs = np.array([self._dr.slot[c.ref_id] for c in candidates])
-        q_start, q_len = np.array(self._dq.start)[qs], np.array(self._dq.length)[qs]
-        r_start, r_len = np.array(self._dr.start)[rs], np.array(self._dr.length)[rs]
-        sizes = q_len.astype(np.int64) * r_len
-        off = np.zeros(n, dtype=np.int64)
-        padded = (sizes + 3) & ~np.int64(3)
-        if n:
-            off[1:] = np.cumsum(padded[:-1])
-        sims = torch.empty((int(padded.sum()) + 4,), dtype=torch.float32, device=dev)
-        # equal-shaped pairs -> one strided-batched GEMM writing straight into the packed buffer
-        order = np.lexsort((r_len, q_len))
-        bounds = np.flatnonzero(np.diff(q_len[order]) | np.diff(r_len[order])) + 1
-        for grp in np.split(order, bounds):
-            lq, lr = int(q_len[grp[0]]), int(r_len[grp[0]])
-            if lq == 0 or lr == 0:
-                continue
-            step = max(1, self.GROUP_ROWS // max(lq + lr, 1))
-            for s in range(0, len(grp), step):
-                g = grp[s:s + step]
-                qi = torch.from_numpy(q_start[g][:, None] + np.arange(lq)[None, :]).to(dev)
-                ri = torch.from_numpy(r_start[g][:, None] + np.arange(lr)[None, :]).to(dev)
-                prod = torch.bmm(Q[qi], R[ri].transpose(1, 2))
-                if self.similarity_bias:
-                    prod += self.similarity_bias
-                dst = torch.from_numpy(off[g][:, None] + np.arange(lq * lr)[None, :]).to(dev)
-                sims[dst.reshape(-1)] = prod.reshape(-1)
-        return sims, off, q_len.astype(np.int32), r_len.astype(np.int32)
+        return self._dq, self._dr
+
+    def _operands(self):
+        """bf16 panels of all uploaded query / reference rows; the split is chosen for both sides together."""
+        dq, dr = self._stores()
+        key = (dq.version, dr.version)
+        if self._panels is None or self._panels[0] != key:
+            Q, R = dq.matrix(), dr.matrix()
+            if Q.shape[1] != R.shape[1]:
+                raise ValueError(f"query descriptors have {Q.shape[1]} dimensions, reference descriptors {R.shape[1]}")
+            oq, orr = gemm.prepare_pair(Q, R, precise=True)
+            self._panels = (key, oq, orr)
+        return self._panels[1], self._panels[2]
+
+    def _similarity_use(self):
+        known = (VCSLLocalization.score, VCSLLocalizationMaxSim.score, VCSLLocalizationCandidateScore.score)
+        return self.similarity_use if type(self).score in known else "full"
 
     def localize_all(self, candidates: List[CandidatePair]) -> List[Match]:
         if not candidates:
             return []
         torch = _lib.require_cuda()
-        sims, off, lq, lr = self._pack_similarities(candidates)
-        dev = sims.device
+        from .vta import tn_batch_from_features
+        dq, dr = self._stores()
+        dev = dq.device
+        q_ids = [c.query_id for c in candidates]
+        r_ids = [c.ref_id for c in candidates]
+        dq.ensure(q_ids)
+        dr.ensure(r_ids)
+        oq, orr = self._operands()
         n = len(candidates)
-        meta = torch.from_numpy(np.concatenate([lq, lr])).to(dev)
-        res = self.model.align_device(sims, torch.from_numpy(off).to(dev), meta[:n], meta[n:], n,
-                                      int(lq.max()), int(lr.max()), want_maxsim=True)
+        meta = np.empty((4, n), dtype=np.int32)      # q_start, lq, r_start, lr
+        meta[0] = [dq.start[i] for i in q_ids]
+        meta[1] = [dq.length[i] for i in q_ids]
+        meta[2] = [dr.start[i] for i in r_ids]
+        meta[3] = [dr.length[i] for i in r_ids]
+        d_meta = torch.from_numpy(meta).to(dev, non_blocking=True)
+        use = self._similarity_use()
+        sims = d_off = off = None
+        if use == "full":
+            sizes = meta[1].astype(np.int64) * meta[3]
+            padded = (sizes + 3) & ~np.int64(3)
+            off = np.zeros(n, dtype=np.int64)
+            off[1:] = np.cumsum(padded[:-1])
+            sims = torch.empty((int(padded.sum()) + 4,), dtype=torch.float32, device=dev)
+            d_off = torch.from_numpy(off).to(dev, non_blocking=True)
+        res = tn_batch_from_features(
+            oq.panel, orr.panel, oq.k, d_meta[0], d_meta[1], d_meta[2], d_meta[3], n, int(meta[1].max()),
+            int(meta[3].max()), int(meta[3].min()), float(self.similarity_bias), self.model.params,
+            want_maxsim=(use == "boxmax"), sims_out=sims, d_off=d_off, force_exact_order=self.model.force_exact_order)
+        self.model.last_result = res
         boxes, n_boxes, maxsim, _ = res.to_host()
+
+        # ---- boxes -> Match rows (localization.py:61-78), vectorised over all boxes of the batch
+        pair_of = np.repeat(np.arange(n), n_boxes)
+        if len(pair_of) == 0:
+            return []
+        slot = np.arange(len(pair_of)) - np.repeat(np.cumsum(n_boxes) - n_boxes, n_boxes)
+        bx = boxes[pair_of, slot].astype(np.int64)
+        tq0, tq1 = dq.timestamps()
+        tr0, tr1 = dr.timestamps()
+        qs, rs = meta[0][pair_of].astype(np.int64), meta[2][pair_of].astype(np.int64)
+        q_start, q_end = tq0[qs + bx[:, 0]].tolist(), tq1[qs + bx[:, 2]].tolist()
+        r_start, r_end = tr0[rs + bx[:, 1]].tolist(), tr1[rs + bx[:, 3]].tolist()
         matches = []
-        for i, c in enumerate(candidates):
-            query, ref = self.queries[c.query_id], self.refs[c.ref_id]
-            for k in range(n_boxes[i]):
-                x1, y1, x2, y2 = (int(v) for v in boxes[i, k])
-                m = Match(query_id=c.query_id, ref_id=c.ref_id,
-                          query_start=query.get_timestamps(x1)[0], query_end=query.get_timestamps(x2)[1],
-                          ref_start=ref.get_timestamps(y1)[0], ref_end=ref.get_timestamps(y2)[1], score=0.0)
-                matches.append(m._replace(score=self.score(c, m, (x1, y1, x2, y2), _BoxMax(maxsim[i, k]))))
+        if use == "full":
+            host_sims = sims.cpu().numpy()
+        for j, p in enumerate(pair_of.tolist()):
+            c = candidates[p]
+            m = Match(query_id=c.query_id, ref_id=c.ref_id, query_start=q_start[j], query_end=q_end[j],
+                      ref_start=r_start[j], ref_end=r_end[j], score=0.0)
+            box = tuple(int(v) for v in bx[j])
+            if use == "boxmax":
+                similarity = _BoxMax(maxsim[p, slot[j]])
+            elif use == "full":
+                similarity = host_sims[off[p]:off[p] + int(meta[1][p]) * int(meta[3][p])].reshape(int(meta[1][p]), -1)
+            else:
+                similarity = None
+            matches.append(m._replace(score=self.score(c, m, box, similarity)))
         return matches
 
     def localize(self, candidate: CandidatePair) -> List[Match]:
@@ -170,6 +290,8 @@ class _BoxMax:
 
 
 class VCSLLocalizationMaxSim(VCSLLocalization):
+    similarity_use = "boxmax"
+
     def score(self, candidate: CandidatePair, match: Match, box, similarity) -> float:
         x1, y1, x2, y2 = box
         return similarity[x1:x2, y1:y2].max() - self.similarity_bias

@@ -21,17 +21,48 @@ from . import _lib
 
 
 class TnResult:
-    """Device-resident result of one TN batch (boxes, counts, MaxSim scores)."""
+    """Device-resident result of one TN batch (boxes, counts, MaxSim scores) in ONE int32 buffer, so that a single
+    device-to-host copy brings everything back."""
 
-    def __init__(self, boxes, n_boxes, maxsim, status, box_cap):
-        self.boxes, self.n_boxes, self.maxsim, self.status, self.box_cap = boxes, n_boxes, maxsim, status, box_cap
+    def __init__(self, buf, n_pairs, box_cap, has_maxsim):
+        self.buf, self.n_pairs, self.box_cap, self.has_maxsim = buf, n_pairs, box_cap, has_maxsim
+        n, cap = max(n_pairs, 1), box_cap
+        self._o_boxes, self._o_nb, self._o_ms, self._o_st = 0, n * cap * 4, n * cap * 4 + n, n * cap * 5 + n
+
+    # device views
+    @property
+    def boxes(self):
+        return self.buf[self._o_boxes:self._o_nb].view(-1, self.box_cap, 4)[:self.n_pairs]
+
+    @property
+    def n_boxes(self):
+        return self.buf[self._o_nb:self._o_ms][:self.n_pairs]
+
+    @property
+    def maxsim(self):
+        if not self.has_maxsim:
+            return None
+        torch = _lib.require_cuda()
+        return self.buf[self._o_ms:self._o_st].view(torch.float32).view(-1, self.box_cap)[:self.n_pairs]
+
+    @property
+    def status(self):
+        return self.buf[self._o_st:][:self.n_pairs]
 
     def to_host(self):
-        nb = self.n_boxes.cpu().numpy()
-        bx = self.boxes.cpu().numpy().reshape(len(nb), self.box_cap, 4)
-        ms = self.maxsim.cpu().numpy().reshape(len(nb), self.box_cap) if self.maxsim is not None else None
-        st = self.status.cpu().numpy() if self.status is not None else None
+        h = self.buf.cpu().numpy()
+        n, cap = self.n_pairs, self.box_cap
+        bx = h[self._o_boxes:self._o_nb].reshape(-1, cap, 4)[:n]
+        nb = h[self._o_nb:self._o_ms][:n]
+        ms = h[self._o_ms:self._o_st].view(np.float32).reshape(-1, cap)[:n] if self.has_maxsim else None
+        st = h[self._o_st:][:n]
         return bx, nb, ms, st
+
+
+def _result_buffer(n_pairs: int, cap: int, dev):
+    torch = _lib.require_cuda()
+    n = max(n_pairs, 1)
+    return torch.zeros((n * cap * 5 + 2 * n,), dtype=torch.int32, device=dev)
 
 
 def tn_params(tn_max_step=10, tn_top_k=5, max_path=10, min_sim=0.2, min_length=5, max_iou=0.3) -> "_lib.TnParams":
@@ -51,20 +82,56 @@ def tn_batch_device(d_sims, d_off, d_lq, d_lr, n_pairs: int, max_lq: int, max_lr
     lib = _lib.load()
     dev = d_sims.device
     cap = params.max_path + 1
-    boxes = torch.empty((max(n_pairs, 1), cap, 4), dtype=torch.int32, device=dev)
-    n_boxes = torch.zeros((max(n_pairs, 1),), dtype=torch.int32, device=dev)
-    maxsim = torch.zeros((max(n_pairs, 1), cap), dtype=torch.float32, device=dev) if want_maxsim else None
-    status = torch.zeros((max(n_pairs, 1),), dtype=torch.int32, device=dev)
+    res = TnResult(_result_buffer(n_pairs, cap, dev), n_pairs, cap, want_maxsim)
+    base = res.buf.data_ptr()
     s = stream if stream is not None else torch.cuda.current_stream(dev)
     with torch.cuda.device(dev):
         rc = lib.vcsl_tn_batch(
             d_sims.data_ptr(), d_off.data_ptr(), d_lq.data_ptr(), d_lr.data_ptr(), n_pairs,
-            int(max_lq), int(max_lr), ctypes.byref(params), boxes.data_ptr(), n_boxes.data_ptr(),
-            maxsim.data_ptr() if want_maxsim else None, status.data_ptr(),
+            int(max_lq), int(max_lr), ctypes.byref(params), base + 4 * res._o_boxes, base + 4 * res._o_nb,
+            base + 4 * res._o_ms if want_maxsim else None, base + 4 * res._o_st,
             1 if force_exact_order else 0, ctypes.c_void_p(s.cuda_stream))
     _lib.check(rc, "vcsl_tn_batch")
-    return TnResult(boxes[:n_pairs], n_boxes[:n_pairs], maxsim[:n_pairs] if want_maxsim else None,
-                    status[:n_pairs], cap)
+    return res
+
+
+def tn_batch_from_features(q_panel, r_panel, k: int, d_q_start, d_lq, d_r_start, d_lr, n_pairs: int, max_lq: int,
+                           max_lr: int, min_lr: int, bias: float, params: "_lib.TnParams", want_maxsim: bool = False,
+                           sims_out=None, d_off=None, force_exact_order: bool = False, stream=None) -> TnResult:
+    """Align `n_pairs` pairs whose similarity matrices are Q_p . R_p^T + bias of rows of two descriptor panels
+    (bf16 CUDA tensors [rows, k] from gemm.prepare): the batch form of localization.py:57-58.  Asynchronous."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    dev = q_panel.device
+    cap = params.max_path + 1
+    res = TnResult(_result_buffer(n_pairs, cap, dev), n_pairs, cap, want_maxsim)
+    base = res.buf.data_ptr()
+    s = stream if stream is not None else torch.cuda.current_stream(dev)
+    with torch.cuda.device(dev):
+        rc = lib.vcsl_tn_batch_from_features(
+            q_panel.data_ptr(), q_panel.shape[0], r_panel.data_ptr(), r_panel.shape[0], int(k),
+            d_q_start.data_ptr(), d_lq.data_ptr(), d_r_start.data_ptr(), d_lr.data_ptr(), n_pairs,
+            int(max_lq), int(max_lr), int(min_lr), float(bias), ctypes.byref(params),
+            sims_out.data_ptr() if sims_out is not None else None, d_off.data_ptr() if d_off is not None else None,
+            base + 4 * res._o_boxes, base + 4 * res._o_nb, base + 4 * res._o_ms if want_maxsim else None,
+            base + 4 * res._o_st, 1 if force_exact_order else 0, ctypes.c_void_p(s.cuda_stream))
+    _lib.check(rc, "vcsl_tn_batch_from_features")
+    return res
+
+
+def pair_similarity(q_panel, r_panel, k: int, d_q_start, d_lq, d_r_start, d_lr, n_pairs: int, max_lq: int, max_lr: int,
+                    bias: float, sims_out, d_off, stream=None):
+    """sims_out[d_off[p] + i * lr[p] + j] = Q[q_start[p] + i] . R[r_start[p] + j] + bias (localization.py:33-36,49-54)."""
+    torch = _lib.require_cuda()
+    dev = q_panel.device
+    s = stream if stream is not None else torch.cuda.current_stream(dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().vsc_pair_similarity(
+            q_panel.data_ptr(), q_panel.shape[0], r_panel.data_ptr(), r_panel.shape[0], int(k), d_q_start.data_ptr(),
+            d_lq.data_ptr(), d_r_start.data_ptr(), d_lr.data_ptr(), n_pairs, int(max_lq), int(max_lr), float(bias),
+            sims_out.data_ptr(), d_off.data_ptr(), ctypes.c_void_p(s.cuda_stream))
+    _lib.check(rc, "vsc_pair_similarity")
+    return sims_out
 
 
 def pack_sims(sims: Sequence[np.ndarray]):
