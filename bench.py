@@ -1,24 +1,28 @@
 #!/usr/bin/env python3
-"""Headline benchmark: query-ref pairs localized / second (BASELINE.json metric).
+"""Headline benchmark: query-ref pairs localized / second (BASELINE.json metric), configs[3].
 
-Workload (config.workload = "c4_tn_localization"): BASELINE.json configs[3] -- per GPU 8000
-candidate pairs, each a 300x300 float32 frame-similarity matrix (sims = Q.R^T + 0.5 from
-L2-normalised descriptors with 0-2 planted diagonal copies), temporal-network alignment with the
-vsc2022 parameters (tn_max_step=5, tn_top_k=5, max_path=10, min_sim=0.2, min_length=4, max_iou=0.3).
-One step = one pass of the hot path over the whole batch.
+Workload (config.workload = "c4_matching_localization", vsc2022_b200.workloads.C4Workload): 8000 candidate pairs IN
+TOTAL -- 1600 query videos x 5 candidates each (sscd_baseline.py:111) against a pool of 1600 reference videos, every
+video 300 frames of L2-normalised 512-d float32 descriptors, every second pair with a planted copy of 20-80 frames --
+localized the way `sscd_baseline.localize_and_verify` does with score normalisation: similarity = Q.R^T + 0.5 per pair,
+VCSL temporal network (tn_max_step=5, tn_top_k=5, max_path=10, min_sim=0.2, min_length=4, max_iou=0.3), MaxSim box
+scores.  One step = one pass over all pairs of the rank.  With N GPUs the 8000 pairs are split into contiguous shards
+(strong scaling); the per-rank box counts are gathered with one small NCCL all-gather inside the timed region.
 
-  value   device time only: similarity matrices already resident in HBM (2.88 GB per GPU, larger
-          than the 126 MB L2, so no flush is needed between steps); CUDA events on the launch stream.
-  e2e     the same batch through the public host-buffer API (vcsl.vta-style TN.forward_packed):
-          pinned host matrices -> H2D -> kernels -> boxes D2H, all inside the timed region.
-  roofline  HBM: algorithmic bytes = 4*Lq*Lr per pair over the device time of the
-          whole TN pipeline call; per-kernel times are listed under roofline.stages_ms.
-  cpu_baseline  the oracle's port of the reference CPU path (VCSL TN on networkx, one process per
-          host core) on a bounded sample of the same workload -- a reported baseline, not a target.
-
-`--impl reference` runs only that CPU arm (bounded sample per step) and prints the same JSON shape.
-Multi-GPU (`torchrun ... bench.py --gpus N`): pairs are independent, every rank aligns its own 8000
-pairs (weak scaling), no data-path collective; time = max over ranks.
+  value     the temporal network on the 300x300 float32 similarity matrices of those pairs, matrices resident in
+            HBM (2.88 GB at N=1, larger than the 126 MB L2: no flush needed), one vcsl_tn_batch call per step, CUDA
+            events on the launch stream.  This is the stage BASELINE.json configs[3] names ("300x300 frame-sim
+            matrices, TN DP") and the one the HBM roofline is quoted on.
+  e2e       the reference-facing call: VCSLLocalizationMaxSim(queries, refs, "TN", ...).localize_all(candidates)
+            (vsc/baseline/localization.py:56-79) on HOST VideoFeature arrays (pinned), a fresh object per step: descriptor
+            upload, panel preparation, per-pair tensor-core GEMM + TN (vcsl_tn_batch_from_features), result download
+            and the Match rows are all inside the timed region.
+  roofline  HBM: algorithmic bytes = 4*Lq*Lr per pair over the device time of the whole
+            vcsl_tn_batch call; per-kernel times under roofline.stages_ms.
+  stages    device-resident timings of the same pairs straight from descriptors (per-pair GEMM fused with the TN
+            row top-K), the other two stages of the path (descriptor search, SSCD inference) and the small pipeline.
+  cpu_baseline / --impl reference   the reference's CPU path restated by the oracle (numpy matmul + bias, VCSL TN on
+            networkx over a process pool, MaxSim scores) on a bounded sample of THE SAME pairs.
 """
 import argparse
 import json
@@ -31,11 +35,14 @@ import time
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
-PAIRS_PER_GPU = 8000
-LQ = LR = 300
+N_PAIRS = 8000
+FRAMES = 300
+DIM = 512
+BIAS = 0.5
 TN_CFG = dict(tn_max_step=5, tn_top_k=5, max_path=10, min_sim=0.2, min_length=4, max_iou=0.3)
 METRIC = "query-ref pairs localized/sec"
 UNIT = "pairs/s"
+CPU_SAMPLE = 96      # pairs per CPU step / cpu_baseline sample
 
 
 def measured_peaks():
@@ -88,44 +95,60 @@ class ClockSampler(threading.Thread):
                 "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def _tn_job(args):
-    from oracle import tn_networkx
-    return tn_networkx.tn(args, **TN_CFG)
+def _config(world, per_rank):
+    return {"workload": "c4_matching_localization", "pairs_total": N_PAIRS, "pairs_per_gpu": per_rank,
+            "queries": N_PAIRS // 5, "candidates_per_query": 5, "ref_pool": 1600, "frames": FRAMES, "dim": DIM,
+            "similarity_bias": BIAS, "scoring": "MaxSim", **TN_CFG,
+            "l2": "inputs (2.88 GB of matrices / 1.97 GB of descriptors at N=1) larger than L2; no flush needed",
+            "parallelism": f"pairs sharded contiguously over {world} GPU(s); one all-gather of box counts per step"}
 
 
-def cpu_reference_run(n_pairs, seed):
-    """The reference CPU path (oracle port: VCSL TN on networkx) over all host cores."""
-    import multiprocessing as mp
+def cpu_localize(wl, lo, hi, cores):
+    """The reference's localize_all on the CPU (oracle restatement, vsc/baseline/localization.py:56-79 + VCSL TN):
+    numpy matmul + bias per pair, the matrices pickled to a process pool running TN on networkx, MaxSim scores."""
     import numpy as np
-    from oracle import synth
-    rng = np.random.default_rng(seed)
-    sims = [synth.sim_matrix(rng, LQ, LR, dim=64, max_copies=2, bias=0.5) for _ in range(n_pairs)]
-    cores = os.cpu_count() or 1
+    from oracle import tn_networkx
+    q_ids, r_ids, Q, R = wl.videos_for(lo, hi)
+    qpos, rpos = {q: i for i, q in enumerate(q_ids)}, {r: i for i, r in enumerate(r_ids)}
+    f = wl.frames
     t0 = time.perf_counter()
-    with mp.get_context("fork").Pool(cores) as pool:
-        boxes = pool.map(_tn_job, sims, chunksize=max(1, n_pairs // (cores * 4)))
+    data = []
+    for p in range(lo, hi):
+        qi, ri = qpos[int(wl.pair_query[p])], rpos[int(wl.pair_ref[p])]
+        data.append((str(p), np.matmul(Q[qi * f:(qi + 1) * f], R[ri * f:(ri + 1) * f].T) + BIAS))
+    model = tn_networkx.build_vta_model("TN", concurrency=cores, **{k: v for k, v in TN_CFG.items()})
+    out = model.forward_sim(data)
+    boxes, scores = [], []
+    for (key, sim), (key2, bx) in zip(data, out):
+        assert key == key2
+        boxes.append(bx)
+        scores.append([float(sim[x1:x2, y1:y2].max() - BIAS) for x1, y1, x2, y2 in bx])
     dt = time.perf_counter() - t0
-    return n_pairs / dt, cores, dt, sum(len(b) for b in boxes)
+    return boxes, scores, dt
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    sample = 64
+    from vsc2022_b200.workloads import C4Workload
+    wl = C4Workload(N_PAIRS, frames=FRAMES, dim=DIM)
+    cores = os.cpu_count() or 1
     rates = []
     for step in range(args.warmup + args.steps):
-        rate, cores, dt, _ = cpu_reference_run(sample, seed=100 + step)
+        lo = (step * CPU_SAMPLE) % (N_PAIRS - CPU_SAMPLE)
+        _, _, dt = cpu_localize(wl, lo, lo + CPU_SAMPLE, cores)
         if step >= args.warmup:
-            rates.append(rate)
+            rates.append(CPU_SAMPLE / dt)
     value = statistics.mean(rates)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sample / value,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "c4_tn_localization", "pairs_per_step": sample, "lq": LQ, "lr": LR, **TN_CFG},
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * CPU_SAMPLE / value,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": _config(args.gpus, N_PAIRS // max(args.gpus, 1)),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample} pairs of {LQ}x{LR} per step; VCSL TN restated on networkx "
-                                   f"(real VCSL/FAISS not installable here), multiprocessing.Pool({cores})"},
+                         "sample": f"{CPU_SAMPLE} consecutive pairs of the workload per step (different pairs each step): "
+                                   f"numpy matmul + bias, VCSL TN restated on networkx (real VCSL/FAISS not installable "
+                                   f"here) over multiprocessing.Pool({cores}), MaxSim scores"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -276,23 +299,59 @@ def stage_numbers(dev, peaks):
 
 
 def run_gpu(args, rank, local_rank, world):
+    import ctypes
     import numpy as np
     import torch
     import torch.distributed as dist
-    from vsc2022_b200 import _lib, vta, workloads
+    from vsc2022_b200 import _lib, gemm, vta
+    from vsc2022_b200.index import VideoFeature
+    from vsc2022_b200.localization import VCSLLocalizationMaxSim
+    from vsc2022_b200.metrics import CandidatePair
+    from vsc2022_b200.workloads import C4Workload
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
-    n = PAIRS_PER_GPU
-    w = workloads.tn_pairs_device(n, LQ, LR, seed=4 + rank, device=dev)
+    wl = C4Workload(N_PAIRS, frames=FRAMES, dim=DIM)
+    lo, hi = rank * N_PAIRS // world, (rank + 1) * N_PAIRS // world       # this rank's contiguous shard
+    n = hi - lo
+    f = FRAMES
+
+    # ---- the rank's videos, generated into pinned host arrays (the e2e arm uploads from them)
+    q_ids = sorted(set(wl.pair_query[lo:hi].tolist()))
+    r_ids = sorted(set(wl.pair_ref[lo:hi].tolist()))
+
+    def host_array(rows):
+        try:
+            return torch.empty((rows, DIM), dtype=torch.float32, pin_memory=True), True
+        except RuntimeError:
+            return torch.empty((rows, DIM), dtype=torch.float32), False
+    q_host, pinned = host_array(len(q_ids) * f)
+    r_host, pinned_r = host_array(len(r_ids) * f)
+    pinned = pinned and pinned_r
+    wl.videos_for(lo, hi, q_base=q_host.numpy(), r_base=r_host.numpy())
+    qpos, rpos = {q: i for i, q in enumerate(q_ids)}, {r: i for i, r in enumerate(r_ids)}
+    meta = np.stack([np.array([qpos[int(q)] * f for q in wl.pair_query[lo:hi]]), np.full(n, f),
+                     np.array([rpos[int(r)] * f for r in wl.pair_ref[lo:hi]]), np.full(n, f)]).astype(np.int32)
+
+    # ---- device-resident inputs of `value`: the similarity matrices of the shard (computed by the pair GEMM)
+    Qd, Rd = q_host.to(dev), r_host.to(dev)
+    oq, orr = gemm.prepare_pair(Qd, Rd, precise=True)
+    d_meta = torch.from_numpy(meta).to(dev)
+    sims = torch.empty((n * f * f + 4,), dtype=torch.float32, device=dev)
+    off = torch.arange(n, device=dev, dtype=torch.int64) * (f * f)
+    vta.pair_similarity(oq.panel, orr.panel, oq.k, d_meta[0], d_meta[1], d_meta[2], d_meta[3], n, f, f, BIAS, sims, off)
     model = vta.build_vta_model("TN", concurrency=16, **{k: v for k, v in TN_CFG.items()})
     stream = torch.cuda.current_stream(dev)
+    counts = torch.zeros((world, 1), dtype=torch.int64, device=dev)
 
     def device_step():
-        return model.align_device(w.sims, w.off, w.lq, w.lr, n, LQ, LR, want_maxsim=False)
+        res = model.align_device(sims, off, d_meta[1], d_meta[3], n, f, f, want_maxsim=True)
+        if world > 1:   # the job's result lives on every rank: gather the per-rank box totals
+            dist.all_gather_into_tensor(counts, res.n_boxes.sum(dtype=torch.int64).reshape(1, 1))
+        return res
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -300,8 +359,9 @@ def run_gpu(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---------------- value: device-resident inputs
-    for _ in range(max(args.warmup, 3)):
+    # ---------------- value: matrices resident in HBM
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         res = device_step()
     lib.vsc_tn_set_profiling(1)
     sampler = ClockSampler(local_rank)
@@ -317,89 +377,144 @@ def run_gpu(args, rank, local_rank, world):
     sampler.stop_flag = True
     launches = _lib.launch_count() - launches0
     ms = ev0.elapsed_time(ev1) / args.steps
-    import ctypes
     stage = (ctypes.c_float * 4)()
     lib.vsc_tn_last_stage_ms(stage)
-    lib.vsc_tn_set_profiling(0)
-    _, n_boxes, _, status = res.to_host()
+    boxes_v, n_boxes, maxsim_v, status = res.to_host()
 
-    # ---------------- e2e: pinned host buffers through the host-facing API
-    try:
-        host_sims = torch.empty(w.sims.numel() + 4, dtype=torch.float32, pin_memory=True)
-        pinned = True
-    except RuntimeError:   # N ranks pin N x 2.88 GB; a host that refuses still gets an (honest, slower) e2e number
-        host_sims = torch.empty(w.sims.numel() + 4, dtype=torch.float32)
-        pinned = False
-    host_sims[:w.sims.numel()].copy_(w.sims)
-    off_h, lq_h, lr_h = w.off.cpu().numpy(), w.lq.cpu().numpy(), w.lr.cpu().numpy()
+    # ---------------- the same pairs straight from descriptors (device resident): per-pair GEMM fused with the TN
+    def timed(fn, reps=5):
+        fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            out = fn()
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / reps, out
+    params = model.params
+    ff = lambda ms_, op_q, op_r: vta.tn_batch_from_features(op_q.panel, op_r.panel, op_q.k, d_meta[0], d_meta[1], d_meta[2],
+                                                            d_meta[3], n, f, f, f, BIAS, params, want_maxsim=ms_)
+    ms_ff, res_ff = timed(lambda: ff(True, oq, orr))
+    st_ff = (ctypes.c_float * 4)()
+    lib.vsc_tn_last_stage_ms(st_ff)
+    ms_ff_boxes, _ = timed(lambda: ff(False, oq, orr))
+    ms_prep, _ = timed(lambda: gemm.prepare_pair(Qd, Rd, precise=True), reps=3)
+    ms_sim, _ = timed(lambda: vta.pair_similarity(oq.panel, orr.panel, oq.k, d_meta[0], d_meta[1], d_meta[2], d_meta[3],
+                                                  n, f, f, BIAS, sims, off), reps=3)
+    lib.vsc_tn_set_profiling(0)
+    bx_ff, nb_ff, ms_ff_scores, _ = res_ff.to_host()
+    same_boxes = bool((nb_ff == n_boxes).all()) and bool((bx_ff == boxes_v).all())
+
+    # ---------------- e2e: the reference-facing call on host VideoFeatures, a fresh object per step
+    ts_q = np.tile(np.arange(f, dtype=np.float64), len(q_ids))
+    ts_r = np.tile(np.arange(f, dtype=np.float64), len(r_ids))
+    qh, rh = q_host.numpy(), r_host.numpy()
+    queries = [VideoFeature(video_id=f"Q{q:06d}", timestamps=ts_q[i * f:(i + 1) * f], feature=qh[i * f:(i + 1) * f])
+               for i, q in enumerate(q_ids)]
+    refs = [VideoFeature(video_id=f"R{r:06d}", timestamps=ts_r[i * f:(i + 1) * f], feature=rh[i * f:(i + 1) * f])
+            for i, r in enumerate(r_ids)]
+    cands = [CandidatePair(f"Q{int(wl.pair_query[p]):06d}", f"R{int(wl.pair_ref[p]):06d}", 1.0) for p in range(lo, hi)]
+
+    def e2e_step():
+        loc = VCSLLocalizationMaxSim(queries, refs, "TN", tn_max_step=5, min_length=4, concurrency=16, similarity_bias=BIAS)
+        matches = loc.localize_all(cands)
+        return loc, matches
     for _ in range(2):
-        boxes_h = model.forward_packed(host_sims, off_h, lq_h, lr_h)
+        loc, matches = e2e_step()
     barrier()
-    t0 = time.perf_counter()
     e2e_steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        boxes_h = model.forward_packed(host_sims, off_h, lq_h, lr_h)
+        loc, matches = e2e_step()
     torch.cuda.synchronize(dev)
     e2e_s = (time.perf_counter() - t0) / e2e_steps
-    h2d = w.sims.numel() * 4 + off_h.nbytes + lq_h.nbytes + lr_h.nbytes
-    d2h = n * (TN_CFG["max_path"] + 1) * 4 * 4 + n * 4
+    h2d = loc._dq.h2d_bytes + loc._dr.h2d_bytes + meta.nbytes
+    d2h = loc.model.last_result.buf.numel() * 4
+    matches_ok = len(matches) == int(n_boxes.sum())
 
     # ---------------- max over ranks
-    times = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    times = torch.tensor([ms, e2e_s * 1e3, ms_ff, ms_ff_boxes], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms_max, e2e_ms_max = times.tolist()
+    ms_max, e2e_ms_max, ms_ff_max, ms_ffb_max = times.tolist()
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
-        algo_bytes = n * 4 * LQ * LR
+        algo_bytes = n * 4 * f * f
         achieved = algo_bytes / (ms_max * 1e-3) / 1e9
-        stages = None
-        if world == 1 and not args.no_stages:
-            del host_sims
-            stages = stage_numbers(dev, peaks)
+        # ---- checks outside the timed regions: the first pairs of the shard against the oracle
+        check = {"boxes_per_pair": float(np.mean(n_boxes)),
+                 "pairs_on_fast_pipeline": int((status == 0).sum()),
+                 "pairs_on_general_kernel": int((status == 2).sum()),
+                 "pairs_on_exact_order_kernel": int((status == 1).sum()),
+                 "from_descriptors_boxes_identical": same_boxes, "e2e_match_rows_equal_box_count": matches_ok}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            rate, cores, dt, _ = cpu_reference_run(96, seed=4)
-            cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"96 pairs of {LQ}x{LR} ({dt:.1f} s): VCSL TN restated on networkx "
-                             f"(real VCSL not installable here), multiprocessing.Pool({cores})"}
+            from oracle import tn_fast
+            m = 512
+            host = sims[:m * f * f].cpu().numpy().reshape(m, f, f)
+            want = tn_fast.tn_batch(list(host), **TN_CFG)
+            check["oracle_tn_fast_on_gpu_matrices_512_pairs_equal"] = all(
+                boxes_v[i, :n_boxes[i]].tolist() == want[i] for i in range(m))
+            cores = os.cpu_count() or 1
+            cpu_boxes, cpu_scores, dt = cpu_localize(wl, 0, CPU_SAMPLE, cores)
+            diff = [i for i in range(CPU_SAMPLE) if boxes_v[i, :n_boxes[i]].tolist() != cpu_boxes[i]]
+            check["cpu_path_same_boxes"] = f"{CPU_SAMPLE - len(diff)} of {CPU_SAMPLE} pairs (CPU: numpy sgemm matrices; GPU: split-bf16 tensor-core matrices)"
+            errs = [abs(float(maxsim_v[i, k]) - BIAS - s) for i in range(CPU_SAMPLE) if i not in diff
+                    for k, s in enumerate(cpu_scores[i])]
+            check["cpu_path_max_score_diff"] = max(errs) if errs else None
+            cpu = {"value": CPU_SAMPLE / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"the first {CPU_SAMPLE} pairs of the workload ({dt:.1f} s): numpy matmul + bias, VCSL TN "
+                             f"restated on networkx (real VCSL not installable here) over multiprocessing.Pool({cores}), "
+                             f"MaxSim scores"}
+        stages = {
+            "c1_c4_from_descriptors": {
+                "what": "vcsl_tn_batch_from_features on the shard, descriptor panels resident: per-pair tcgen05 GEMM "
+                        "(3-term bf16 split, K'=%d) with the TN row top-K out of tensor memory, matrices written for the "
+                        "MaxSim scores, graph stage" % oq.k,
+                "ms_with_maxsim": ms_ff_max, "pairs_per_s_with_maxsim": N_PAIRS / (ms_ff_max * 1e-3),
+                "ms_boxes_only": ms_ffb_max, "pairs_per_s_boxes_only": N_PAIRS / (ms_ffb_max * 1e-3),
+                "stages_ms": {"pair_gemm_topk_kernel": st_ff[0], "tn_edges_kernel": st_ff[1], "tn_dp_kernel": st_ff[2],
+                              "tn_maxsim_kernel": st_ff[3]},
+                "prepare_panels_ms": ms_prep, "pair_similarity_only_ms": ms_sim,
+                "gemm_tflops_algorithmic": 2.0 * n * f * f * DIM / (st_ff[0] * 1e-3) / 1e12 if st_ff[0] > 0 else None,
+                "gemm_tflops_issued": 2.0 * n * f * f * oq.k / (st_ff[0] * 1e-3) / 1e12 if st_ff[0] > 0 else None}}
+        if world == 1 and not args.no_stages:
+            del sims, Qd, Rd, oq, orr
+            torch.cuda.empty_cache()
+            stages.update(stage_numbers(dev, peaks))
         line = {
-            "metric": METRIC, "value": world * n / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "metric": METRIC, "value": N_PAIRS / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": warm, "ms_per_step": ms_max,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": "c4_tn_localization", "pairs_per_gpu": n, "lq": LQ, "lr": LR, **TN_CFG,
-                       "l2": "inputs (2.88 GB/GPU) larger than L2; no flush needed",
-                       "parallelism": f"pairs sharded over {world} GPU(s), no data-path collective"},
+            "config": _config(world, n),
             "clocks": sampler.summary(),
-            "e2e": {"value": world * n / (e2e_ms_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+            "e2e": {"value": N_PAIRS / (e2e_ms_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_max,
-                    "api": "vsc2022_b200.vta.TN.forward_packed (%s host similarity matrices in, boxes out)"
-                           % ("pinned" if pinned else "pageable")},
+                    "api": "vsc2022_b200.localization.VCSLLocalizationMaxSim(queries, refs, 'TN', ...).localize_all(candidates): "
+                           "%s host descriptors in, Match rows out; a fresh object per step" % ("pinned" if pinned else "pageable")},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"], "peak_source": peak_src,
-                         "kernel": "TN pipeline of one vcsl_tn_batch call (tn_topk + tn_edges + tn_dp)",
+                         "kernel": "TN pipeline of one vcsl_tn_batch call (tn_topk + tn_edges + tn_dp + tn_maxsim)",
                          "algorithmic_bytes_per_launch": algo_bytes,
-                         "traffic": TRAFFIC_BYTES_PER_CALL,
+                         "traffic": TRAFFIC_BYTES_PER_CALL * n / 8000.0,
                          "stages_ms": {"tn_topk_kernel": stage[0], "tn_edges_kernel": stage[1],
-                                       "tn_dp_kernel": stage[2]},
+                                       "tn_dp_kernel": stage[2], "tn_maxsim_kernel": stage[3]},
                          "tn_topk_frac": algo_bytes / (stage[0] * 1e-3) / 1e9 / peaks["hbm_gbs"] if stage[0] > 0 else None},
             "cpu_baseline": cpu,
             "stages": stages,
-            "result_check": {"boxes_per_pair": float(np.mean(n_boxes)),
-                             "pairs_on_fast_pipeline": int((status == 0).sum()),
-                             "pairs_on_general_kernel": int((status == 2).sum()),
-                             "pairs_on_exact_order_kernel": int((status == 1).sum())},
+            "result_check": check,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum over the three kernels of one call, from the ncu capture
-# committed under profiles/ (profiles/r01_tn_launches_final.csv, per-launch table r01_tn_launches_final.txt).
+# dram__bytes_read.sum + dram__bytes_write.sum over the kernels of one 8000-pair call, from the ncu capture
+# committed under profiles/ (per-launch table: profiles/r01_tn_launches_final.txt).
 TRAFFIC_BYTES_PER_CALL = 3.88e9  # tn_topk 3.014+0.213, tn_edges 0.152+0.058, tn_dp 0.326+0.116 GB (profiles/r01_tn_summary.md)
 
 

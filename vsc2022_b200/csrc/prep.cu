@@ -14,27 +14,46 @@ namespace {
 
 enum { MODE_HI = 0, MODE_SPLIT_A = 1, MODE_SPLIT_B = 2 };
 
-// one thread per (row, k) element of the padded panel; rows are contiguous so writes coalesce
+// One thread per four consecutive k of a row (16-byte loads when the rows allow it, 8-byte stores); the panel rows are
+// contiguous, so a warp writes 256 contiguous bytes per panel part.
+template <bool VEC>
 __global__ void __launch_bounds__(256) prepare_kernel(const float *__restrict__ x, int64_t n, int d, int64_t ld,
                                                       int kpad, int mode, __nv_bfloat16 *__restrict__ out,
-                                                      int *__restrict__ lo_flag, float *__restrict__ sq_norm) {
+                                                      int *__restrict__ lo_flag) {
+    const int quads = kpad >> 2;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t row = idx / kpad;
-    const int k = (int)(idx - row * kpad);
-    if (row >= n) return;
-    const float v = k < d ? x[row * ld + k] : 0.0f;
-    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-    if (mode == MODE_HI) {
-        out[row * kpad + k] = hi;
-    } else {
-        __nv_bfloat16 *o = out + row * (int64_t)(3 * kpad);
-        o[k] = hi;
-        o[kpad + k] = mode == MODE_SPLIT_A ? hi : lo;
-        o[2 * kpad + k] = mode == MODE_SPLIT_A ? lo : hi;
+    const int64_t row = idx / quads;
+    const int k = (int)(idx - row * quads) * 4;
+    bool any_lo = false;
+    if (row < n) {
+        float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        const float *src = x + row * ld + k;
+        if (VEC && k + 3 < d) {
+            const float4 f = *reinterpret_cast<const float4 *>(src);
+            v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (k + j < d) v[j] = src[j];
+        }
+        __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            hi[j] = __float2bfloat16_rn(v[j]);
+            lo[j] = __float2bfloat16_rn(v[j] - __bfloat162float(hi[j]));
+            any_lo = any_lo || __bfloat162float(lo[j]) != 0.0f;
+        }
+        const uint2 hi2 = *reinterpret_cast<const uint2 *>(hi), lo2 = *reinterpret_cast<const uint2 *>(lo);
+        if (mode == MODE_HI) {
+            *reinterpret_cast<uint2 *>(out + row * kpad + k) = hi2;
+        } else {
+            __nv_bfloat16 *o = out + row * (int64_t)(3 * kpad) + k;
+            *reinterpret_cast<uint2 *>(o) = hi2;
+            *reinterpret_cast<uint2 *>(o + kpad) = mode == MODE_SPLIT_A ? hi2 : lo2;
+            *reinterpret_cast<uint2 *>(o + 2 * kpad) = mode == MODE_SPLIT_A ? lo2 : hi2;
+        }
     }
-    if (lo_flag && __bfloat162float(lo) != 0.0f) atomicOr(lo_flag, 1);
-    (void)sq_norm;
+    if (lo_flag && __any_sync(vsc::kFullMask, any_lo) && (threadIdx.x & 31) == 0) atomicOr(lo_flag, 1);
 }
 
 // squared L2 norm per row (float32, sequential-in-k per warp lane then warp reduce): for the L2 metric
@@ -60,9 +79,14 @@ extern "C" int vsc_prepare_operand(const float *d_x, int64_t n, int32_t d, int64
         vsc::set_error("vsc_prepare_operand: kpad=%d must be a multiple of 64 and >= d=%d; mode in 0..2", kpad, d);
         return VSC_ERR_INVALID;
     }
-    const int64_t total = n * kpad;
-    prepare_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
-        d_x, n, d, ld, kpad, mode, static_cast<__nv_bfloat16 *>(d_out_bf16), d_lo_flag, nullptr);
+    const int64_t total = n * (kpad / 4);
+    const bool vec = (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(d_x) & 15u) == 0;
+    if (vec)
+        prepare_kernel<true><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+            d_x, n, d, ld, kpad, mode, static_cast<__nv_bfloat16 *>(d_out_bf16), d_lo_flag);
+    else
+        prepare_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+            d_x, n, d, ld, kpad, mode, static_cast<__nv_bfloat16 *>(d_out_bf16), d_lo_flag);
     VSC_CUDA_CHECK(cudaGetLastError());
     vsc::count_launch();
     return VSC_OK;

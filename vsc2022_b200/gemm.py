@@ -50,12 +50,16 @@ def prepare(x, mode: int = MODE_HI, want_flag: bool = False):
 
 
 def prepare_pair(a, b, precise: bool = True):
-    """Prepare query-side `a` and reference-side `b`; split only if some value is not bf16-representable."""
-    oa, fa = prepare(a, MODE_HI, want_flag=precise)
-    ob, fb = prepare(b, MODE_HI, want_flag=precise)
-    if precise and (int(fa.item()) | int(fb.item())):
-        oa, _ = prepare(a, MODE_SPLIT_A)
-        ob, _ = prepare(b, MODE_SPLIT_B)
+    """Prepare query-side `a` and reference-side `b`; split only if some value is not bf16-representable.
+    Real descriptors never are, so the split panels are produced first (one pass, the flag comes with it) and only
+    bf16-representable inputs pay a second pass for the short panels."""
+    if not precise:
+        return prepare(a, MODE_HI)[0], prepare(b, MODE_HI)[0]
+    oa, fa = prepare(a, MODE_SPLIT_A, want_flag=True)
+    ob, fb = prepare(b, MODE_SPLIT_B, want_flag=True)
+    if not (int(fa.item()) | int(fb.item())):
+        oa, _ = prepare(a, MODE_HI)
+        ob, _ = prepare(b, MODE_HI)
     return oa, ob
 
 

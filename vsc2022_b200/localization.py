@@ -14,6 +14,7 @@ Same classes and signatures as the reference.  `VCSLLocalization.localize_all` i
   operations (no per-pair Python work for pairs without a match).
 """
 import abc
+import gc
 from typing import Dict, List
 
 import numpy as np
@@ -45,22 +46,27 @@ class LocalizationWithMetadata(Localization):
         return np.matmul(self.queries[candidate.query_id].feature, self.refs[candidate.ref_id].feature.T)
 
 
-def _root_of(arr: np.ndarray):
-    """(root array, first row of `arr` inside it) if `arr` is a block of whole rows of a 2-D base array, else None."""
-    root = arr
+def _root_of(arr: np.ndarray, cache: dict = None):
+    """(root array, first row of `arr` inside it) if `arr` is a block of whole rows of a base array (1-D or 2-D,
+    C-contiguous), else None.  `cache` memoises the per-root facts (this runs once per video of a collection)."""
+    root = arr.base
+    if not isinstance(root, np.ndarray):
+        return None
     while isinstance(root.base, np.ndarray):
         root = root.base
-    if root is arr or arr.ndim != 2 or root.ndim != 2 or arr.dtype != root.dtype:
+    info = cache.get(id(root)) if cache is not None else None
+    if info is None:
+        ok = root.ndim in (1, 2) and root.flags.c_contiguous and root.shape[0] > 0
+        info = (root, ok, root.__array_interface__["data"][0], root.strides, root.shape[1:], root.dtype, root.shape[0])
+        if cache is not None:
+            cache[id(root)] = info
+    _, ok, ptr, strides, tail, dtype, rows = info
+    if not ok or arr.dtype != dtype or arr.shape[1:] != tail or (arr.shape[0] and arr.strides != strides):
         return None
-    if arr.shape[1] != root.shape[1] or root.strides != (root.shape[1] * root.itemsize, root.itemsize):
+    row, rem = divmod(arr.__array_interface__["data"][0] - ptr, strides[0])
+    if rem or row < 0 or row + arr.shape[0] > rows:
         return None
-    if arr.shape[0] and arr.strides != root.strides:
-        return None
-    delta = arr.__array_interface__["data"][0] - root.__array_interface__["data"][0]
-    row, rem = divmod(delta, root.strides[0])
-    if rem or row < 0 or row + arr.shape[0] > root.shape[0]:
-        return None
-    return root, int(row)
+    return root, row
 
 
 class _DeviceVideos:
@@ -82,6 +88,7 @@ class _DeviceVideos:
         self._cat = None
         self._ts = [[], []]         # per segment: host arrays of frame start / end timestamps
         self._ts_cat = None
+        self._root_cache = {}       # id(root) -> facts about that base array (keeps the array alive: ids stay unique)
         self.h2d_bytes = 0
 
     def _upload(self, host: np.ndarray):
@@ -102,19 +109,30 @@ class _DeviceVideos:
         self.version += 1
         return first, len(self.segments) - 1
 
-    def _register(self, vid, first_row: int, seg: int, seg_first: int):
-        v = self.videos[vid]
-        n = len(v)
-        self.start[vid], self.length[vid] = first_row, n
-        ts = np.asarray(v.timestamps)
-        lo = first_row - seg_first
+    def _stamp(self, seg: int, lo: int, ts: np.ndarray):
+        n = ts.shape[0]
         if ts.ndim == 1:          # VideoMetadata.get_timestamps: (t, t) for instants, (t[0], t[1]) for intervals
             self._ts[0][seg][lo:lo + n] = ts
             self._ts[1][seg][lo:lo + n] = ts
         else:
             self._ts[0][seg][lo:lo + n] = ts[:, 0]
             self._ts[1][seg][lo:lo + n] = ts[:, 1]
+
+    def _register(self, vid, first_row: int, seg: int, seg_first: int):
+        v = self.videos[vid]
+        self.start[vid], self.length[vid] = first_row, len(v)
+        self._stamp(seg, first_row - seg_first, np.asarray(v.timestamps))
         self._ts_cat = None
+
+    def prefetch(self, vid):
+        """Start the upload of the base array `vid`'s descriptors are a view of (asynchronous from pinned memory), so
+        that the copy runs while the host walks the rest of the collection."""
+        if vid in self.start:
+            return
+        where = _root_of(self.videos[vid].feature, self._root_cache)
+        if where is not None and id(where[0]) not in self._roots and where[0].shape[0] <= self.MAX_WASTE * (1 << 20):
+            first, seg = self._upload(where[0])
+            self._roots[id(where[0])] = (where[0], first, seg)
 
     def ensure(self, ids):
         new = [i for i in dict.fromkeys(ids) if i not in self.start]
@@ -123,10 +141,10 @@ class _DeviceVideos:
         loose = []
         by_root = {}
         for i in new:
-            f = np.asarray(self.videos[i].feature)
+            f = self.videos[i].feature
             if f.ndim != 2:
                 raise ValueError("descriptors must be 2-D (frames x dimensions)")
-            where = _root_of(f)
+            where = _root_of(f, self._root_cache)
             if where is None:
                 loose.append(i)
             else:
@@ -140,8 +158,22 @@ class _DeviceVideos:
                 first, seg = self._upload(root)
                 self._roots[key] = (root, first, seg)
             _, first, seg = self._roots[key]
-            for i, row in members:
-                self._register(i, first + row, seg, first)
+            # timestamps: when they are row views of one array laid out like the descriptors (storage.load_features),
+            # one bulk copy; otherwise video by video
+            ts_where = [_root_of(self.videos[i].timestamps, self._root_cache) for i, _ in members]
+            ts_root = ts_where[0][0] if ts_where[0] is not None else None
+            bulk = ts_root is not None and ts_root.shape[0] == root.shape[0] and all(
+                w is not None and w[0] is ts_root and w[1] == row for w, (_, row) in zip(ts_where, members))
+            if bulk:
+                if ("ts", key) not in self._roots:
+                    self._stamp(seg, 0, ts_root)
+                    self._roots[("ts", key)] = ts_root
+                self.start.update((i, first + row) for i, row in members)
+                self.length.update((i, len(self.videos[i])) for i, _ in members)
+                self._ts_cat = None
+            else:
+                for i, row in members:
+                    self._register(i, first + row, seg, first)
         if loose:
             host = np.concatenate([np.asarray(self.videos[i].feature, dtype=np.float32) for i in loose])
             first, seg = self._upload(host)
@@ -214,6 +246,8 @@ class VCSLLocalization(LocalizationWithMetadata):
         dev = dq.device
         q_ids = [c.query_id for c in candidates]
         r_ids = [c.ref_id for c in candidates]
+        dq.prefetch(q_ids[0])
+        dr.prefetch(r_ids[0])
         dq.ensure(q_ids)
         dr.ensure(r_ids)
         oq, orr = self._operands()
@@ -251,22 +285,34 @@ class VCSLLocalization(LocalizationWithMetadata):
         qs, rs = meta[0][pair_of].astype(np.int64), meta[2][pair_of].astype(np.int64)
         q_start, q_end = tq0[qs + bx[:, 0]].tolist(), tq1[qs + bx[:, 2]].tolist()
         r_start, r_end = tr0[rs + bx[:, 1]].tolist(), tr1[rs + bx[:, 3]].tolist()
-        matches = []
-        if use == "full":
+        pairs_l = pair_of.tolist()
+        qid, rid = [q_ids[p] for p in pairs_l], [r_ids[p] for p in pairs_l]
+        scorer = type(self).score
+        if scorer is VCSLLocalizationMaxSim.score:        # similarity[x1:x2, y1:y2].max() - bias, float32 like numpy's
+            scores = list(maxsim[pair_of, slot] - self.similarity_bias)
+        elif scorer is VCSLLocalizationCandidateScore.score:
+            scores = [candidates[p].score for p in pairs_l]
+        elif scorer is VCSLLocalization.score:
+            scores = [1.0] * len(qid)
+        else:                                              # a subclass with its own score(): the reference's calling convention
             host_sims = sims.cpu().numpy()
-        for j, p in enumerate(pair_of.tolist()):
-            c = candidates[p]
-            m = Match(query_id=c.query_id, ref_id=c.ref_id, query_start=q_start[j], query_end=q_end[j],
-                      ref_start=r_start[j], ref_end=r_end[j], score=0.0)
-            box = tuple(int(v) for v in bx[j])
-            if use == "boxmax":
-                similarity = _BoxMax(maxsim[p, slot[j]])
-            elif use == "full":
-                similarity = host_sims[off[p]:off[p] + int(meta[1][p]) * int(meta[3][p])].reshape(int(meta[1][p]), -1)
-            else:
-                similarity = None
-            matches.append(m._replace(score=self.score(c, m, box, similarity)))
-        return matches
+            scores = []
+            for j, p in enumerate(pairs_l):
+                lq_p, lr_p = int(meta[1][p]), int(meta[3][p])
+                m = Match(query_id=qid[j], ref_id=rid[j], query_start=q_start[j], query_end=q_end[j],
+                          ref_start=r_start[j], ref_end=r_end[j], score=0.0)
+                similarity = host_sims[off[p]:off[p] + lq_p * lr_p].reshape(lq_p, lr_p)
+                scores.append(self.score(candidates[p], m, tuple(int(v) for v in bx[j]), similarity))
+        # Match is a NamedTuple: field order (query_id, ref_id, score, query_start, query_end, ref_start, ref_end).  Tens of
+        # thousands of new container objects would trigger the cyclic collector again and again (6x slower): off for
+        # the duration of the list construction.
+        new, was_on = tuple.__new__, gc.isenabled()
+        gc.disable()
+        try:
+            return [new(Match, row) for row in zip(qid, rid, scores, q_start, q_end, r_start, r_end)]
+        finally:
+            if was_on:
+                gc.enable()
 
     def localize(self, candidate: CandidatePair) -> List[Match]:
         return self.localize_all([candidate])
