@@ -87,6 +87,9 @@ int vcsl_tn_batch_from_features(const void *d_q_panel, int64_t q_rows, const voi
  * around each stage).  vsc_tn_last_stage_ms fills {row top-K, edges, sweeps, MaxSim} in ms for the
  * most recent vcsl_tn_batch call; synchronise the stream first. */
 int vsc_tn_set_profiling(int on);
+/* Graph stage of the fast pipeline: 0 = layer-by-layer sweeps (default), 1 = compact graph relaxed by Kahn generation
+ * (csrc/tn_graph.cu; parameter sets with (tn_max_step-1)*tn_top_k <= 32).  Identical results. */
+int vsc_tn_set_graph_variant(int variant);
 int vsc_tn_last_stage_ms(float *out4);
 
 /* Development aid: DP phase clocks summed over warps since the last call (reading resets them):

@@ -118,3 +118,23 @@ def test_empty_batch_and_bad_params():
         vta.build_vta_model("TN", tn_top_k=9).forward_sim([("a", np.zeros((4, 4), np.float32))])
     with pytest.raises(_lib.EngineError):
         vta.build_vta_model("TN", tn_max_step=20).forward_sim([("a", np.zeros((4, 4), np.float32))])
+
+
+def test_compact_graph_variant_matches():
+    """csrc/tn_graph.cu (graph stage on a compact graph, by Kahn generation) against the oracle and the default kernels."""
+    from vsc2022_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(8)
+    sims = [synth.sim_matrix(rng, 300, 300, dim=512) for _ in range(96)] + _random_cases(seed=12, count=120, max_len=90)
+    cfg = dict(tn_max_step=5, tn_top_k=5, max_path=10, min_sim=0.2, min_length=4, max_iou=0.3)
+    want = tn_fast.tn_batch(sims, **cfg)
+    try:
+        _lib.check(lib.vsc_tn_set_graph_variant(1), "vsc_tn_set_graph_variant")
+        got, maxsim, status = run_gpu(sims, **VSC_CFG)
+    finally:
+        lib.vsc_tn_set_graph_variant(0)
+    assert got == want
+    assert (status[:96] == 0).mean() > 0.9
+    for i, s in enumerate(sims[:96]):
+        for k, (x1, y1, x2, y2) in enumerate(got[i]):
+            assert maxsim[i, k] == s[x1:x2, y1:y2].max()

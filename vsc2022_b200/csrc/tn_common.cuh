@@ -85,6 +85,11 @@ bool pipeline_supported(const Batch &b);
 int launch_pipeline_from_features(const PairOperands &op, const Batch &b, const Workspace &w, const WorkList &out,
                                   cudaStream_t stream);
 bool graph_supported(const Batch &b);
+// Graph stage on a compact graph (tn_graph.cu): narrow predecessor masks ((step-1)*topk <= 32)
+bool graph_v2_supported(const Batch &b);
+size_t graph_v2_scratch_bytes(const Batch &b);
+int launch_graph_v2(const Batch &b, const Workspace &w, const WorkList &out, unsigned char *graphs, cudaStream_t stream,
+                    void (*mark_between)(cudaStream_t));
 int workspace_alloc(const Batch &b, Workspace *w, void **base_out, cudaStream_t stream);
 
 }  // namespace tn

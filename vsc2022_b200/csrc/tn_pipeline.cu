@@ -23,6 +23,7 @@
 // slot = (step-1-(q_dst-q_src))*K + a of pred[v_dst]; ascending slot == networkx predecessor
 // insertion order (see oracle/tn_fast.c).
 #include <limits.h>
+#include <stdlib.h>
 
 #include "row_select.cuh"
 #include "tn_common.cuh"
@@ -835,12 +836,24 @@ static int launch_row_topk(const Batch &b, const Workspace &w, const WorkList &o
 }
 
 // edges + longest-path sweeps (+ MaxSim when the similarity matrices are in memory) on the node records of `w`
+// Graph-stage variant: 0 = layer-by-layer kernels (default: fewer warp instructions at batch sizes that fill the GPU),
+// 1 = compact graph by Kahn generation (tn_graph.cu; profiles/r02_tn_graph_variants.md).  VSC_TN_GRAPH=compact or
+// vsc_tn_set_graph_variant(1) selects the latter.
+static int g_graph_variant = [] { const char *e = getenv("VSC_TN_GRAPH"); return e && e[0] == 'c' ? 1 : 0; }();
+static bool use_graph_v2() { return g_graph_variant == 1; }
+
 static int launch_graph(const Batch &b, const Workspace &w, const WorkList &out, cudaStream_t stream) {
     const bool wide = (b.step - 1) * 8 > 32;
     int rc = VSC_OK;
     auto fail = [&](cudaError_t e, const char *what) {
         if (e != cudaSuccess && rc == VSC_OK) { vsc::set_error("%s: %s", what, cudaGetErrorString(e)); rc = VSC_ERR_CUDA; }
     };
+    if (use_graph_v2() && graph_v2_supported(b)) {
+        unsigned char *graphs = nullptr;
+        VSC_CUDA_CHECK(cudaMallocAsync(&graphs, graph_v2_scratch_bytes(b), stream));
+        rc = launch_graph_v2(b, w, out, graphs, stream, [](cudaStream_t s) { mark(2, s); });
+        cudaFreeAsync(graphs, stream);
+    } else {
     {
         const long long threads = (long long)b.n_pairs * b.max_lq;
         const int grid = (int)((threads + 255) / 256);
@@ -858,6 +871,7 @@ static int launch_graph(const Batch &b, const Workspace &w, const WorkList &out,
                   : launch_dp<uint32_t, 1>(b, w, out, grid, smem, stream), "tn_dp_kernel");
         fail(cudaGetLastError(), "tn_dp_kernel");
         vsc::count_launch();
+    }
     }
     mark(3, stream);
     if (rc == VSC_OK && b.box_maxsim && b.sims) {
@@ -888,6 +902,12 @@ int launch_pipeline_from_features(const PairOperands &op, const Batch &b, const 
 
 }  // namespace tn
 }  // namespace vsc
+
+extern "C" int vsc_tn_set_graph_variant(int variant) {
+    if (variant != 0 && variant != 1) { vsc::set_error("vsc_tn_set_graph_variant: 0 (layers) or 1 (compact)"); return VSC_ERR_INVALID; }
+    vsc::tn::g_graph_variant = variant;
+    return VSC_OK;
+}
 
 extern "C" int vsc_tn_set_profiling(int on) {
     vsc::tn::g_profile = on != 0;
