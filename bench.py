@@ -338,11 +338,13 @@ def run_gpu(args, rank, local_rank, world):
 
     # ---- device-resident inputs of `value`: the similarity matrices of the shard (computed by the pair GEMM)
     Qd, Rd = q_host.to(dev), r_host.to(dev)
-    oq, orr = gemm.prepare_pair(Qd, Rd, precise=True)
+    oq, orr = gemm.prepare_pair(Qd, Rd)
+    pairing = gemm.Pairing(oq, orr)
     d_meta = torch.from_numpy(meta).to(dev)
     sims = torch.empty((n * f * f + 4,), dtype=torch.float32, device=dev)
     off = torch.arange(n, device=dev, dtype=torch.int64) * (f * f)
-    vta.pair_similarity(oq.panel, orr.panel, oq.k, d_meta[0], d_meta[1], d_meta[2], d_meta[3], n, f, f, BIAS, sims, off)
+    vta.pair_similarity(oq.panel, orr.panel, pairing.k, d_meta[0], d_meta[1], d_meta[2], d_meta[3], n, f, f, BIAS, sims, off,
+                        fmt=pairing)
     model = vta.build_vta_model("TN", concurrency=16, **{k: v for k, v in TN_CFG.items()})
     stream = torch.cuda.current_stream(dev)
     counts = torch.zeros((world, 1), dtype=torch.int64, device=dev)
@@ -393,15 +395,15 @@ def run_gpu(args, rank, local_rank, world):
         torch.cuda.synchronize(dev)
         return e0.elapsed_time(e1) / reps, out
     params = model.params
-    ff = lambda ms_, op_q, op_r: vta.tn_batch_from_features(op_q.panel, op_r.panel, op_q.k, d_meta[0], d_meta[1], d_meta[2],
-                                                            d_meta[3], n, f, f, f, BIAS, params, want_maxsim=ms_)
+    ff = lambda ms_, op_q, op_r: vta.tn_batch_from_features(op_q.panel, op_r.panel, pairing.k, d_meta[0], d_meta[1], d_meta[2],
+                                                            d_meta[3], n, f, f, f, BIAS, params, want_maxsim=ms_, fmt=pairing)
     ms_ff, res_ff = timed(lambda: ff(True, oq, orr))
     st_ff = (ctypes.c_float * 4)()
     lib.vsc_tn_last_stage_ms(st_ff)
     ms_ff_boxes, _ = timed(lambda: ff(False, oq, orr))
-    ms_prep, _ = timed(lambda: gemm.prepare_pair(Qd, Rd, precise=True), reps=3)
-    ms_sim, _ = timed(lambda: vta.pair_similarity(oq.panel, orr.panel, oq.k, d_meta[0], d_meta[1], d_meta[2], d_meta[3],
-                                                  n, f, f, BIAS, sims, off), reps=3)
+    ms_prep, _ = timed(lambda: gemm.prepare_pair(Qd, Rd), reps=3)
+    ms_sim, _ = timed(lambda: vta.pair_similarity(oq.panel, orr.panel, pairing.k, d_meta[0], d_meta[1], d_meta[2], d_meta[3],
+                                                  n, f, f, BIAS, sims, off, fmt=pairing), reps=3)
     lib.vsc_tn_set_profiling(0)
     bx_ff, nb_ff, ms_ff_scores, _ = res_ff.to_host()
     same_boxes = bool((nb_ff == n_boxes).all()) and bool((bx_ff == boxes_v).all())
@@ -460,7 +462,7 @@ def run_gpu(args, rank, local_rank, world):
             cores = os.cpu_count() or 1
             cpu_boxes, cpu_scores, dt = cpu_localize(wl, 0, CPU_SAMPLE, cores)
             diff = [i for i in range(CPU_SAMPLE) if boxes_v[i, :n_boxes[i]].tolist() != cpu_boxes[i]]
-            check["cpu_path_same_boxes"] = f"{CPU_SAMPLE - len(diff)} of {CPU_SAMPLE} pairs (CPU: numpy sgemm matrices; GPU: split-bf16 tensor-core matrices)"
+            check["cpu_path_same_boxes"] = f"{CPU_SAMPLE - len(diff)} of {CPU_SAMPLE} pairs (CPU: numpy sgemm matrices; GPU: fp16-split tensor-core matrices)"
             errs = [abs(float(maxsim_v[i, k]) - BIAS - s) for i in range(CPU_SAMPLE) if i not in diff
                     for k, s in enumerate(cpu_scores[i])]
             check["cpu_path_max_score_diff"] = max(errs) if errs else None
@@ -471,17 +473,17 @@ def run_gpu(args, rank, local_rank, world):
         stages = {
             "c1_c4_from_descriptors": {
                 "what": "vcsl_tn_batch_from_features on the shard, descriptor panels resident: per-pair tcgen05 GEMM "
-                        "(3-term bf16 split, K'=%d) with the TN row top-K out of tensor memory, matrices written for the "
-                        "MaxSim scores, graph stage" % oq.k,
+                        "(fp16 split, three partial products, K'=%d) with the TN row top-K out of tensor memory, matrices written for the "
+                        "MaxSim scores, graph stage" % pairing.k,
                 "ms_with_maxsim": ms_ff_max, "pairs_per_s_with_maxsim": N_PAIRS / (ms_ff_max * 1e-3),
                 "ms_boxes_only": ms_ffb_max, "pairs_per_s_boxes_only": N_PAIRS / (ms_ffb_max * 1e-3),
                 "stages_ms": {"pair_gemm_topk_kernel": st_ff[0], "tn_edges_kernel": st_ff[1], "tn_dp_kernel": st_ff[2],
                               "tn_maxsim_kernel": st_ff[3]},
                 "prepare_panels_ms": ms_prep, "pair_similarity_only_ms": ms_sim,
                 "gemm_tflops_algorithmic": 2.0 * n * f * f * DIM / (st_ff[0] * 1e-3) / 1e12 if st_ff[0] > 0 else None,
-                "gemm_tflops_issued": 2.0 * n * f * f * oq.k / (st_ff[0] * 1e-3) / 1e12 if st_ff[0] > 0 else None}}
+                "gemm_tflops_issued": 2.0 * n * f * f * pairing.k / (st_ff[0] * 1e-3) / 1e12 if st_ff[0] > 0 else None}}
         if world == 1 and not args.no_stages:
-            del sims, Qd, Rd, oq, orr
+            del sims, Qd, Rd, oq, orr, pairing
             torch.cuda.empty_cache()
             stages.update(stage_numbers(dev, peaks))
         line = {

@@ -25,6 +25,14 @@ extern "C" {
 
 typedef void *vsc_stream_t;     /* cudaStream_t */
 
+/* Operand format of the tensor-core GEMM entry points (see vsc_prepare_operand_f16); NULL = bf16 panels with row
+ * stride k and no output scale. */
+typedef struct {
+    int32_t ab_f16;            /* 0: bf16 panels, 1: fp16 panels */
+    int64_t lda, ldb;          /* row strides in elements (0: = k) */
+    const float *d_out_scale;  /* device scalar, NULL = 1 */
+} vsc_gemm_format;
+
 const char *vsc_last_error(void);
 int vsc_abi_version(void);
 
@@ -75,13 +83,14 @@ int vcsl_tn_batch(const float *d_sims, const int64_t *d_off, const int32_t *d_lq
 int vsc_pair_similarity(const void *d_q_panel, int64_t q_rows, const void *d_r_panel, int64_t r_rows, int32_t k,
                         const int32_t *d_q_start, const int32_t *d_lq, const int32_t *d_r_start, const int32_t *d_lr,
                         int32_t n_pairs, int32_t max_lq, int32_t max_lr, float bias, float *d_sims, const int64_t *d_off,
-                        vsc_stream_t stream);
+                        const vsc_gemm_format *fmt, vsc_stream_t stream);
 int vcsl_tn_batch_from_features(const void *d_q_panel, int64_t q_rows, const void *d_r_panel, int64_t r_rows, int32_t k,
                                 const int32_t *d_q_start, const int32_t *d_lq, const int32_t *d_r_start,
                                 const int32_t *d_lr, int32_t n_pairs, int32_t max_lq, int32_t max_lr, int32_t min_lr,
                                 float similarity_bias, const vsc_tn_params *params, float *d_sims_out,
                                 const int64_t *d_off, int32_t *d_boxes, int32_t *d_n_boxes, float *d_box_maxsim,
-                                int32_t *d_status, int32_t force_exact_order, vsc_stream_t stream);
+                                int32_t *d_status, int32_t force_exact_order, const vsc_gemm_format *fmt,
+                                vsc_stream_t stream);
 
 /* Per-stage device timing of the TN fast pipeline (CUDA events recorded on the caller's stream
  * around each stage).  vsc_tn_last_stage_ms fills {row top-K, edges, sweeps, MaxSim} in ms for the
@@ -110,6 +119,19 @@ int vsc_tn_debug_counters(unsigned long long *out8);
  * so that one GEMM with k = 3*kpad yields hi.hi + hi.lo + lo.hi (fp32-class products).
  * *d_lo_flag (may be NULL) is OR-ed with 1 when some lo != 0, i.e. x is not bf16-representable.
  * ------------------------------------------------------------------------- */
+/* Operand format of the GEMM entry points below (NULL = bf16 panels with row stride k, no output scale).
+ * fp16 panels come from vsc_prepare_operand_f16: x is scaled by a power of two 2^e chosen from max|x| (device side, no
+ * host round trip) so that hi = fp16(x 2^e) and lo = fp16((x 2^e - hi) 2^11) keep 22 significant bits of every value:
+ *   side 0 (queries)     [hi 2^-11 | lo 2^-11 | hi]        side 1 (references)   [lo | hi | hi]
+ * one GEMM over k = 3*kpad gives hi.lo + lo.hi + hi.hi with every product exact in the fp32 accumulator; what is left
+ * is the accumulator itself, which TRUNCATES (measured: median |error| 7e-8 on unit-norm 512-d rows, up to ~1.5e-6 on
+ * identical rows, where all products have one sign; an fp32 sgemm: 1e-8 / 6e-7).  The small cross products come first
+ * for that reason.  k = kpad over the last third (pointer + 2*kpad elements, row stride lda / ldb = 3*kpad) is exact
+ * whenever *d_lo_flag stays 0, i.e. every value has at most 11 significant bits.
+ * *d_out_scale = 2^-(e_a + e_b) (the product of the two operands' *d_inv_scale) is multiplied into the accumulators. */
+int vsc_prepare_operand_f16(const float *d_x, int64_t n, int32_t d, int64_t ld, int32_t kpad, int32_t side,
+                            void *d_out_f16, float *d_inv_scale, int32_t *d_lo_flag, uint32_t *d_scratch,
+                            vsc_stream_t stream);
 int vsc_prepare_operand(const float *d_x, int64_t n, int32_t d, int64_t ld, int32_t kpad, int32_t mode,
                         void *d_out_bf16, int32_t *d_lo_flag, vsc_stream_t stream);
 int vsc_row_sqnorm(const float *d_x, int64_t n, int32_t d, int64_t ld, float *d_out, vsc_stream_t stream);
@@ -127,15 +149,15 @@ int vsc_compact_hits(const float *d_score, const int32_t *d_row, const int32_t *
 
 /* C[m][n] = A . B^T in fp32 (tests, per-pair similarity matrices). */
 int vsc_gemm_store(const void *d_a, int64_t m, const void *d_b, int64_t n, int32_t k, float *d_c, int64_t ldc,
-                   vsc_stream_t stream);
+                   const vsc_gemm_format *fmt, vsc_stream_t stream);
 /* d_rowmax[i] = max_j A_i . B_j  -- FAISS index.search(x, 1) similarities
  * (score_normalization.py:93-96) without materialising the matrix. */
 int vsc_gemm_rowmax(const void *d_a, int64_t m, const void *d_b, int64_t n, int32_t k, float *d_rowmax,
-                    vsc_stream_t stream);
+                    const vsc_gemm_format *fmt, vsc_stream_t stream);
 /* FAISS index.search(x, 1) proper (index.py:169-174 with k = 1): best score and its column per row, lowest
  * column on exact ties.  d_scratch: m x 8 bytes of workspace. */
 int vsc_gemm_rowargmax(const void *d_a, int64_t m, const void *d_b, int64_t n, int32_t k, float *d_score,
-                       int64_t *d_col, unsigned long long *d_scratch, vsc_stream_t stream);
+                       int64_t *d_col, unsigned long long *d_scratch, const vsc_gemm_format *fmt, vsc_stream_t stream);
 /* FAISS range_search (index.py:147-154): counts the scores strictly beyond count_thr into
  * d_counters[1] and appends (score, row + row_offset, col + col_offset) of those strictly beyond
  * emit_thr into slots claimed from d_counters[0] (entries past `capacity` are dropped but still claimed).  Slots are
@@ -146,7 +168,7 @@ int vsc_gemm_rowargmax(const void *d_a, int64_t m, const void *d_b, int64_t n, i
 int vsc_gemm_emit(const void *d_a, int64_t m, const void *d_b, int64_t n, int32_t k, const float *d_a_norm,
                   const float *d_b_norm, int32_t metric_l2, float count_thr, float emit_thr, int64_t row_offset,
                   int64_t col_offset, float *d_score, int32_t *d_row, int32_t *d_col, uint64_t capacity,
-                  unsigned long long *d_counters, vsc_stream_t stream);
+                  unsigned long long *d_counters, const vsc_gemm_format *fmt, vsc_stream_t stream);
 
 /* -------------------------------------------------------------------------
  * Stage A: SSCD ResNet-50 frame descriptors (vsc/baseline/inference_impl.py:210-239 runs the TorchScript model;

@@ -39,9 +39,9 @@ def test_golden_localize_all(golden_tn):
     assert [[m.query_id, m.ref_id] for m in matches] == g["loc_match_ids"].tolist()
     got_ts = np.array([[m.query_start, m.query_end, m.ref_start, m.ref_end] for m in matches])
     assert np.array_equal(got_ts, g["loc_match_ts"])             # segment boundaries: exact
-    # the matrices come from the tensor-core split GEMM: products of identical rows carry the dropped lo.lo term
-    # (<= 2^-17 relative, measured 2.1e-6 here); BASELINE.json asks for alignment scores within 1e-4
-    np.testing.assert_allclose([m.score for m in matches], g["loc_match_score"], atol=1e-5, rtol=0)
+    # identical (copied) frames score 1.0 in the reference; the tensor-core accumulator truncates ~4e-8 per K=16 step
+    # of a same-sign sum (tests/test_gemm_gpu.py), BASELINE.json asks for alignment scores within 1e-4
+    np.testing.assert_allclose([m.score for m in matches], g["loc_match_score"], atol=3e-6, rtol=0)
 
 
 @pytest.mark.parametrize("tag,sn", [("raw", False), ("sn", True)])

@@ -2,7 +2,7 @@
 per-pair Q.R^T + bias on tensor cores (localization.py:33-36,49-54) and the temporal network fed from tensor memory.
 
 Bar: on grid descriptors (every product and partial sum exact in float32) the similarity matrices equal numpy's
-bit for bit and the boxes equal the oracle's; on Gaussian descriptors the matrices are within the split-bf16 bound and
+bit for bit and the boxes equal the oracle's; on Gaussian descriptors the matrices are within the fp16-split bound and
 the boxes equal the oracle run ON THE MATRICES THE SAME CALL WROTE (the row top-K out of tensor memory must agree with
 the stored matrix exactly).
 """
@@ -43,7 +43,8 @@ def run(q, r, pairs, bias, cfg, want_sims, want_maxsim, force_exact=False):
     from vsc2022_b200 import gemm, vta
     dev = torch.device("cuda")
     Q, R = torch.from_numpy(np.concatenate(q)).to(dev), torch.from_numpy(np.concatenate(r)).to(dev)
-    oq, orr = gemm.prepare_pair(Q, R, precise=True)
+    oq, orr = gemm.prepare_pair(Q, R)
+    pairing = gemm.Pairing(oq, orr)
     qs, rs = np.cumsum([0] + [len(x) for x in q]), np.cumsum([0] + [len(x) for x in r])
     meta = np.array([[qs[i] for i, _ in pairs], [len(q[i]) for i, _ in pairs],
                      [rs[j] for _, j in pairs], [len(r[j]) for _, j in pairs]], dtype=np.int32)
@@ -57,17 +58,17 @@ def run(q, r, pairs, bias, cfg, want_sims, want_maxsim, force_exact=False):
         off[1:] = np.cumsum(padded[:-1])
         sims = torch.full((int(padded.sum()) + 4,), np.nan, dtype=torch.float32, device=dev)
         d_off = torch.from_numpy(off).to(dev)
-    res = vta.tn_batch_from_features(oq.panel, orr.panel, oq.k, d_meta[0], d_meta[1], d_meta[2], d_meta[3], n,
+    res = vta.tn_batch_from_features(oq.panel, orr.panel, pairing.k, d_meta[0], d_meta[1], d_meta[2], d_meta[3], n,
                                      int(meta[1].max()), int(meta[3].max()), int(meta[3].min()), bias,
                                      vta.tn_params(**cfg), want_maxsim=want_maxsim, sims_out=sims, d_off=d_off,
-                                     force_exact_order=force_exact)
+                                     force_exact_order=force_exact, fmt=pairing)
     boxes, n_boxes, maxsim, status = res.to_host()
     got = [boxes[i, :n_boxes[i]].tolist() for i in range(n)]
     mats = None
     if want_sims:
         h = sims.cpu().numpy()
         mats = [h[off[p]:off[p] + meta[1][p] * meta[3][p]].reshape(meta[1][p], meta[3][p]) for p in range(n)]
-    return got, maxsim, status, mats, oq.split
+    return got, maxsim, status, mats, pairing.split
 
 
 def check_case(q, r, pairs, bias, cfg=VSC, exact_products=True):
@@ -78,7 +79,7 @@ def check_case(q, r, pairs, bias, cfg=VSC, exact_products=True):
         if exact_products:
             assert np.array_equal(m, w)
         else:
-            np.testing.assert_allclose(m, w, atol=1.6e-5, rtol=0)   # 2^-16: the dropped lo.lo term of identical rows
+            np.testing.assert_allclose(m, w, atol=3e-6, rtol=0)   # fp16 split; the bound is the truncating accumulator on identical rows
     want = tn_fast.tn_batch(mats, **full)          # the oracle on the matrices this very call produced
     bad = [p for p in range(len(pairs)) if got[p] != want[p]]
     assert not bad, (bad[:5], [(got[p], want[p], mats[p].shape) for p in bad[:2]])
@@ -165,6 +166,7 @@ def test_pair_similarity_entry_point():
     q, r = make_videos(rng, [130, 1, 300], 192), make_videos(rng, [900, 2, 257], 192)
     dev = torch.device("cuda")
     oq, orr = gemm.prepare_pair(torch.from_numpy(np.concatenate(q)).to(dev), torch.from_numpy(np.concatenate(r)).to(dev))
+    pairing = gemm.Pairing(oq, orr)
     pairs = [(i, j) for i in range(3) for j in range(3)]
     qs, rs = np.cumsum([0] + [len(x) for x in q]), np.cumsum([0] + [len(x) for x in r])
     meta = np.array([[qs[i] for i, _ in pairs], [len(q[i]) for i, _ in pairs],
@@ -174,8 +176,8 @@ def test_pair_similarity_entry_point():
     off[1:] = np.cumsum(sizes[:-1])                                    # unpadded: unaligned rows and starts
     sims = torch.full((int(sizes.sum()),), np.nan, dtype=torch.float32, device=dev)
     d_meta = torch.from_numpy(meta).to(dev)
-    vta.pair_similarity(oq.panel, orr.panel, oq.k, d_meta[0], d_meta[1], d_meta[2], d_meta[3], len(pairs),
-                        int(meta[1].max()), int(meta[3].max()), -0.25, sims, torch.from_numpy(off).to(dev))
+    vta.pair_similarity(oq.panel, orr.panel, pairing.k, d_meta[0], d_meta[1], d_meta[2], d_meta[3], len(pairs),
+                        int(meta[1].max()), int(meta[3].max()), -0.25, sims, torch.from_numpy(off).to(dev), fmt=pairing)
     h = sims.cpu().numpy()
     assert not np.isnan(h).any()
     for p, (i, j) in enumerate(pairs):

@@ -14,7 +14,7 @@ g = torch.Generator(device=dev); g.manual_seed(3)
 q = torch.randn((nq, d), generator=g, device=dev).bfloat16().float()
 r = torch.randn((nr, d), generator=g, device=dev).bfloat16().float()
 oa, ob = gemm.prepare_pair(q, r)
-print("split:", oa.split, "k:", oa.k)
+print("split:", gemm.Pairing(oa, ob).split, "k:", gemm.Pairing(oa, ob).k)
 
 
 def timeit(fn, n=5):

@@ -33,8 +33,9 @@ for p in range(0, n_pairs, 2):   # planted copies: 20-80 frames of the reference
         R[ri[p] * L + b: ri[p] * L + b + n] + 0.1 / dim ** 0.5 * torch.randn((n, dim), generator=gen, device=dev), dim=1)
 if kind == "grid":
     Q, R = Q.bfloat16().float(), R.bfloat16().float()
-oq, orr = gemm.prepare_pair(Q, R, precise=True)
-print(f"pairs {n_pairs}  frames {L}  dim {dim}  split {oq.split}  K' {oq.k}")
+oq, orr = gemm.prepare_pair(Q, R)
+pairing = gemm.Pairing(oq, orr)
+print(f"pairs {n_pairs}  frames {L}  dim {dim}  split {pairing.split}  K' {pairing.k}")
 meta = np.stack([qi * L, np.full(n_pairs, L), ri * L, np.full(n_pairs, L)]).astype(np.int32)
 d_meta = torch.from_numpy(meta).to(dev)
 params = vta.tn_params(tn_max_step=5, min_length=4)
@@ -60,8 +61,8 @@ def stages():
     return [round(x, 3) for x in out]
 
 
-direct = lambda ms: vta.tn_batch_from_features(oq.panel, orr.panel, oq.k, d_meta[0], d_meta[1], d_meta[2], d_meta[3], n_pairs,
-                                               L, L, L, 0.5, params, want_maxsim=ms)
+direct = lambda ms: vta.tn_batch_from_features(oq.panel, orr.panel, pairing.k, d_meta[0], d_meta[1], d_meta[2], d_meta[3], n_pairs,
+                                               L, L, L, 0.5, params, want_maxsim=ms, fmt=pairing)
 t, res = timed(lambda: direct(False))
 print(f"from_features (boxes only)      {t:.3f} ms  {n_pairs / t / 1e3:.2f} M pairs/s  stages[topk, edges, dp, maxsim] {stages()}")
 boxes, nb, _, st = res.to_host()
@@ -70,9 +71,9 @@ t, res2 = timed(lambda: direct(True))
 print(f"from_features (+MaxSim scores)  {t:.3f} ms  {n_pairs / t / 1e3:.2f} M pairs/s  stages {stages()}")
 sims = torch.empty((n_pairs * L * L + 4,), dtype=torch.float32, device=dev)
 off = torch.arange(n_pairs, device=dev, dtype=torch.int64) * (L * L)
-t, _ = timed(lambda: vta.pair_similarity(oq.panel, orr.panel, oq.k, d_meta[0], d_meta[1], d_meta[2], d_meta[3], n_pairs,
-                                         L, L, 0.5, sims, off))
-flops = 2.0 * n_pairs * L * L * oq.k
+t, _ = timed(lambda: vta.pair_similarity(oq.panel, orr.panel, pairing.k, d_meta[0], d_meta[1], d_meta[2], d_meta[3], n_pairs,
+                                         L, L, 0.5, sims, off, fmt=pairing))
+flops = 2.0 * n_pairs * L * L * pairing.k
 print(f"pair_similarity (matrices out)  {t:.3f} ms  {flops / t / 1e9:.0f} TFLOP/s  {n_pairs * L * L * 4 / t / 1e6:.0f} GB/s written")
 model = vta.TN(tn_max_step=5, min_length=4)
 t, res3 = timed(lambda: model.align_device(sims, off, d_meta[1], d_meta[3], n_pairs, L, L, want_maxsim=False))

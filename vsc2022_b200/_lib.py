@@ -24,6 +24,18 @@ class TnParams(ctypes.Structure):
     ]
 
 
+class GemmFormat(ctypes.Structure):
+    """vsc_gemm_format: operand format of the tensor-core GEMM entry points."""
+    _fields_ = [
+        ("ab_f16", ctypes.c_int32),
+        ("lda", ctypes.c_int64),
+        ("ldb", ctypes.c_int64),
+        ("d_out_scale", ctypes.c_void_p),
+    ]
+
+
+_FMT = ctypes.POINTER(GemmFormat)
+
 EXPORTS = {
     # name: (restype, argtypes)
     "vsc_last_error": (ctypes.c_char_p, []),
@@ -36,20 +48,23 @@ EXPORTS = {
     "vsc_prepare_operand": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int64,
                                            ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
                                            ctypes.c_void_p]),
+    "vsc_prepare_operand_f16": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int64,
+                                               ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
+                                               ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "vsc_row_sqnorm": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int64,
                                       ctypes.c_void_p, ctypes.c_void_p]),
     "vsc_gemm_store": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
-                                      ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
+                                      ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64, _FMT, ctypes.c_void_p]),
     "vsc_gemm_rowmax": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
-                                       ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]),
+                                       ctypes.c_int32, ctypes.c_void_p, _FMT, ctypes.c_void_p]),
     "vsc_gemm_rowargmax": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
                                           ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
-                                          ctypes.c_void_p]),
+                                          _FMT, ctypes.c_void_p]),
     "vsc_gemm_emit": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
                                      ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
                                      ctypes.c_float, ctypes.c_float, ctypes.c_int64, ctypes.c_int64,
                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64,
-                                     ctypes.c_void_p, ctypes.c_void_p]),
+                                     ctypes.c_void_p, _FMT, ctypes.c_void_p]),
     "vsc_gemm_conv": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32,
                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64,
                                      ctypes.c_void_p]),
@@ -82,13 +97,13 @@ EXPORTS = {
         ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32,
         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
         ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p,
-        ctypes.c_void_p]),
+        _FMT, ctypes.c_void_p]),
     "vcsl_tn_batch_from_features": (ctypes.c_int, [
         ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32,
         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
         ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_float, ctypes.POINTER(TnParams),
         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
-        ctypes.c_int32, ctypes.c_void_p]),
+        ctypes.c_int32, _FMT, ctypes.c_void_p]),
     "vcsl_tn_batch": (ctypes.c_int, [
         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
         ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(TnParams),

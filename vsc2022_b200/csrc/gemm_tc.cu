@@ -67,6 +67,10 @@ struct GemmArgs {
     int conv_ho, conv_wo, conv_stride, conv_cblocks, conv_ksize, conv_pad;
     // A_SHIFT (stem): k-block kb reads rows m + kb * a_row_shift of an overlapping-row view (see vsc_conv_stem)
     int64_t a_row_shift;
+    // operand format (vsc_gemm_format): fp16 instead of bf16 panels, panel row strides, accumulator scale
+    int ab_f16;
+    int64_t lda, ldb;
+    const float *out_scale;
 };
 
 template <int BN>
@@ -107,14 +111,14 @@ __device__ __forceinline__ void emit_pad(const GemmArgs &g, EmitState &e, int la
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const GemmArgs &g, float &best, int64_t &best_col, int64_t row,
                                                int64_t col0, int valid, const uint32_t (&acc)[32], int lane,
-                                               EmitState &emit, uint32_t taddr) {
+                                               EmitState &emit, uint32_t taddr, float osc) {
     const bool row_ok = row < g.M;
     const uint32_t valid_mask = valid >= 32 ? 0xFFFFFFFFu : ((1u << valid) - 1u);
     if (EPI == EPI_STORE) {
         if (row_ok) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-                if (j < valid) g.c[row * g.ldc + col0 + j] = __uint_as_float(acc[j]) + (g.bias ? g.bias[col0 + j] : 0.0f);
+                if (j < valid) g.c[row * g.ldc + col0 + j] = __fmaf_rn(__uint_as_float(acc[j]), osc, g.bias ? g.bias[col0 + j] : 0.0f);
         }
     } else if (EPI == EPI_ROWARGMAX) {
         int arg = -1;
@@ -137,7 +141,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs &g, float &best, i
         // EMIT: strict comparisons; IP keeps larger scores, squared-L2 keeps smaller distances
         uint32_t hits = 0, counted = 0;
         float s[32];
-        const float emit_thr = g.emit_thr, count_thr = g.count_thr;
+        // inner product: the comparisons run on the raw accumulators against thresholds divided by the (power-of-two,
+        // hence exact) output scale; only the emitted scores are scaled
+        const float inv = g.metric_l2 ? 1.0f : 1.0f / osc;
+        const float emit_thr = g.emit_thr * inv, count_thr = g.count_thr * inv;
         const bool two = emit_thr != count_thr;  // uniform: the common case has one threshold
         float an = 0.0f;
         if (!g.metric_l2) {
@@ -157,7 +164,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs &g, float &best, i
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 const float bn = j < valid ? g.b_norm[col0 + j] : 0.0f;
-                s[j] = l2_score(an, bn, __uint_as_float(acc[j]));
+                s[j] = l2_score(an, bn, __uint_as_float(acc[j]) * osc);
                 hits |= (s[j] < emit_thr ? 1u : 0u) << j;
                 counted |= (s[j] < count_thr ? 1u : 0u) << j;
             }
@@ -200,7 +207,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs &g, float &best, i
                 asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(raw) : "r"(taddr + (uint32_t)j));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if ((hits >> j) & 1) {
-                    const float v = g.metric_l2 ? l2_score(an, g.b_norm[col0 + j], __uint_as_float(raw)) : __uint_as_float(raw);
+                    const float v = g.metric_l2 ? l2_score(an, g.b_norm[col0 + j], __uint_as_float(raw) * osc) : __uint_as_float(raw) * osc;
                     if (at < g.capacity) {
                         g.out_score[at] = v;
                         g.out_row[at] = (int32_t)(row + g.row_offset);
@@ -215,7 +222,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs &g, float &best, i
         for (int j = 0; j < 32; ++j) {
             if ((hits >> j) & 1) {
                 if (at < g.capacity) {
-                    g.out_score[at] = s[j];
+                    g.out_score[at] = g.metric_l2 ? s[j] : s[j] * osc;
                     g.out_row[at] = (int32_t)(row + g.row_offset);
                     g.out_col[at] = (int32_t)(col0 + j + g.col_offset);
                 }
@@ -402,7 +409,7 @@ __global__ void __launch_bounds__(cta_threads(EPI), 1) gemm_kernel(const __grid_
     } else if (warp == 1) {
         // ===== MMA issuer (single thread) =====
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+            const uint32_t idesc = umma_idesc_f16(BM, BN, !g.ab_f16);
             int stage = 0; uint32_t phase = 0;
             uint32_t it = 0;
             for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
@@ -428,6 +435,7 @@ __global__ void __launch_bounds__(cta_threads(EPI), 1) gemm_kernel(const __grid_
     } else {
         // ===== epilogue warps: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32) =====
         const int quad = warp & 3;
+        const float osc = g.out_scale ? *g.out_scale : 1.0f;
         int64_t bias_blk = -1;
         EmitState emit = {0ull, 0, 0ull};
         ConvCtx cx;
@@ -496,16 +504,16 @@ __global__ void __launch_bounds__(cta_threads(EPI), 1) gemm_kernel(const __grid_
                     uint32_t v[32];
                     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + c * 32;
                     tmem_ld32(taddr, v);
-                    epilogue_chunk<EPI>(g, best, best_col, row, col0, valid, v, lane, emit, taddr);
+                    epilogue_chunk<EPI>(g, best, best_col, row, col0, valid, v, lane, emit, taddr, osc);
                 }
             }
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.tmem_empty[acc]);
             if (EPI == EPI_ROWMAX && row < g.M)
-                atomicMax(&g.rowmax_key[row], vsc::float_to_key(best));
+                atomicMax(&g.rowmax_key[row], vsc::float_to_key(best * osc));
             if (EPI == EPI_ROWARGMAX && row < g.M && best_col >= 0)
-                atomicMax(&g.rowbest[row], ((unsigned long long)vsc::float_to_key(best) << 32) |
+                atomicMax(&g.rowbest[row], ((unsigned long long)vsc::float_to_key(best * osc) << 32) |
                                                (unsigned long long)(0xFFFFFFFFu - (uint32_t)best_col));
         }
         if (EPI == EPI_EMIT) {   // retire the warp's last block, publish its hit count
@@ -561,9 +569,9 @@ int launch(const void *a, const void *b, const GemmArgs &g, cudaStream_t stream,
     CUtensorMap ma, mb;
     int rc = VSC_OK;
     if (map_a) ma = *map_a;
-    else rc = make_map(&ma, a, g.M, g.K, BM);
+    else rc = make_map(&ma, a, g.M, g.K, BM, g.lda);
     if (rc != VSC_OK) return rc;
-    rc = make_map(&mb, b, g.N, g.K, BN);
+    rc = make_map(&mb, b, g.N, g.K, BN, g.ldb);
     if (rc != VSC_OK) return rc;
     const size_t smem = sizeof(SharedStorage<BN>) + 1024;
     VSC_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<EPI, BN, ALOAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -596,18 +604,25 @@ __global__ void keys_to_float(const uint32_t *k, float *out, int64_t n) {
 
 }  // namespace
 
+static void apply_format(GemmArgs &g, const vsc_gemm_format *fmt) {
+    if (!fmt) return;
+    g.ab_f16 = fmt->ab_f16; g.lda = fmt->lda; g.ldb = fmt->ldb; g.out_scale = fmt->d_out_scale;
+}
+
 extern "C" int vsc_gemm_store(const void *d_a, int64_t m, const void *d_b, int64_t n, int32_t k, float *d_c,
-                              int64_t ldc, vsc_stream_t stream) {
+                              int64_t ldc, const vsc_gemm_format *fmt, vsc_stream_t stream) {
     GemmArgs g = {};
+    apply_format(g, fmt);
     g.M = m; g.N = n; g.K = k; g.c = d_c; g.ldc = ldc;
     return launch<EPI_STORE, 256>(d_a, d_b, g, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int vsc_gemm_rowmax(const void *d_a, int64_t m, const void *d_b, int64_t n, int32_t k, float *d_rowmax,
-                               vsc_stream_t stream_) {
+                               const vsc_gemm_format *fmt, vsc_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (m <= 0) return VSC_OK;
     GemmArgs g = {};
+    apply_format(g, fmt);
     g.M = m; g.N = n; g.K = k;
     // the fp32 output buffer doubles as the key buffer: keys first, converted in place afterwards
     g.rowmax_key = reinterpret_cast<uint32_t *>(d_rowmax);
@@ -713,10 +728,12 @@ extern "C" int vsc_gemm_linear(const void *d_a, int64_t m, const void *d_w, int6
 }
 
 extern "C" int vsc_gemm_rowargmax(const void *d_a, int64_t m, const void *d_b, int64_t n, int32_t k, float *d_score,
-                                  int64_t *d_col, unsigned long long *d_scratch, vsc_stream_t stream_) {
+                                  int64_t *d_col, unsigned long long *d_scratch, const vsc_gemm_format *fmt,
+                                  vsc_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (m <= 0) return VSC_OK;
     GemmArgs g = {};
+    apply_format(g, fmt);
     g.M = m; g.N = n; g.K = k; g.rowbest = d_scratch;
     VSC_CUDA_CHECK(cudaMemsetAsync(d_scratch, 0, sizeof(unsigned long long) * (size_t)m, stream));
     int rc = launch<EPI_ROWARGMAX, 256>(d_a, d_b, g, stream);
@@ -730,9 +747,11 @@ extern "C" int vsc_gemm_rowargmax(const void *d_a, int64_t m, const void *d_b, i
 extern "C" int vsc_gemm_emit(const void *d_a, int64_t m, const void *d_b, int64_t n, int32_t k, const float *d_a_norm,
                              const float *d_b_norm, int32_t metric_l2, float count_thr, float emit_thr,
                              int64_t row_offset, int64_t col_offset, float *d_score, int32_t *d_row, int32_t *d_col,
-                             uint64_t capacity, unsigned long long *d_counters, vsc_stream_t stream) {
+                             uint64_t capacity, unsigned long long *d_counters, const vsc_gemm_format *fmt,
+                             vsc_stream_t stream) {
     if (metric_l2 && (!d_a_norm || !d_b_norm)) { vsc::set_error("vsc_gemm_emit: L2 metric needs squared norms"); return VSC_ERR_INVALID; }
     GemmArgs g = {};
+    apply_format(g, fmt);
     g.M = m; g.N = n; g.K = k;
     g.a_norm = d_a_norm; g.b_norm = d_b_norm; g.metric_l2 = metric_l2;
     g.count_thr = count_thr; g.emit_thr = emit_thr; g.row_offset = row_offset; g.col_offset = col_offset;

@@ -56,6 +56,9 @@ struct PairArgs {
     int n_bufs;            // tensor-memory accumulators in use (n_bufs * bn <= 512)
     int stages;            // operand ring depth
     float bias;
+    int ab_f16;            // fp16 instead of bf16 panels (vsc_gemm_format)
+    int64_t ldq, ldr;      // panel row strides in elements (0: = K)
+    const float *out_scale;   // device scalar multiplied into the accumulators (null: 1)
     // STORE
     float *sims;
     const int64_t *off;    // element offset of pair p (null: p * pair_stride)
@@ -140,15 +143,16 @@ __device__ __forceinline__ void insert_max(float x, float (&top)[K]) {   // sort
 }
 
 // one 32-column chunk of the accumulator row of this thread: + bias, columns past the row end -> -inf
-__device__ __forceinline__ void load_chunk(uint32_t taddr, float bias, int valid, float (&v)[32]) {
+// (the output scale is a power of two, so acc * scale is exact and the fused multiply-add rounds once: fl(dot + bias))
+__device__ __forceinline__ void load_chunk(uint32_t taddr, float osc, float bias, int valid, float (&v)[32]) {
     uint32_t raw[32];
     tmem_ld32(taddr, raw);
     if (valid >= 32) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __fadd_rn(__uint_as_float(raw[j]), bias);
+        for (int j = 0; j < 32; ++j) v[j] = __fmaf_rn(__uint_as_float(raw[j]), osc, bias);
     } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = j < valid ? __fadd_rn(__uint_as_float(raw[j]), bias) : -INFINITY;
+        for (int j = 0; j < 32; ++j) v[j] = j < valid ? __fmaf_rn(__uint_as_float(raw[j]), osc, bias) : -INFINITY;
     }
 }
 
@@ -230,7 +234,7 @@ __global__ void __launch_bounds__(kThreads, 1) pair_gemm_kernel(const __grid_con
     } else if (warp == 1) {
         // ===== MMA issuer (single thread) =====
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(BM, g.bn);
+            const uint32_t idesc = umma_idesc_f16(BM, g.bn, !g.ab_f16);
             int stage = 0; uint32_t phase = 0;
             int buf = 0; uint32_t buf_phase = 0;   // accumulator ring position
             for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
@@ -261,6 +265,7 @@ __global__ void __launch_bounds__(kThreads, 1) pair_gemm_kernel(const __grid_con
         // ===== epilogue warps: warp w may touch TMEM lanes [32*(w%4), +32).  The kSub warps of a quadrant own the
         // same 32 rows and take the 32-column chunks of a unit round-robin (chunk index % kSub == sub). =====
         const int quad = warp & 3, sub = (warp - 2) >> 2;
+        const float osc = g.out_scale ? *g.out_scale : 1.0f;
         const int qrow = quad * 32 + lane;                  // row slot in the scratch arrays
         const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
         int buf = 0; uint32_t buf_phase = 0;
@@ -298,7 +303,7 @@ __global__ void __launch_bounds__(kThreads, 1) pair_gemm_kernel(const __grid_con
                     if (((i * chunks_per_tile + c) & (kSub - 1)) != sub) continue;
                     const int valid = min(32, lr - col0);
                     float v[32];
-                    load_chunk(lane_base + (uint32_t)(buf * g.bn + c * 32), g.bias, valid, v);
+                    load_chunk(lane_base + (uint32_t)(buf * g.bn + c * 32), osc, g.bias, valid, v);
                     if (STORE && row_ok) store_chunk(out_row + col0, aligned, valid, v);
                     if (TOPK) {
                         if (small) {
@@ -357,7 +362,7 @@ __global__ void __launch_bounds__(kThreads, 1) pair_gemm_kernel(const __grid_con
                         if (((i * chunks_per_tile + c) & (kSub - 1)) != sub) continue;
                         const int valid = min(32, lr - col0);
                         float v[32];
-                        load_chunk(lane_base + (uint32_t)(b2 * g.bn + c * 32), g.bias, valid, v);
+                        load_chunk(lane_base + (uint32_t)(b2 * g.bn + c * 32), osc, g.bias, valid, v);
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             if (v[j] >= t) {
@@ -396,7 +401,7 @@ __global__ void __launch_bounds__(kThreads, 1) pair_gemm_kernel(const __grid_con
                             if (col0 >= lr) break;
                             const int valid = min(32, lr - col0);
                             float v[32];
-                            load_chunk(lane_base + (uint32_t)(b2 * g.bn + c * 32), g.bias, valid, v);
+                            load_chunk(lane_base + (uint32_t)(b2 * g.bn + c * 32), osc, g.bias, valid, v);
                             if (redo) {
 #pragma unroll
                                 for (int j = 0; j < 32; ++j) exact_insert<K>(v[j], col0 + j, val, col);
@@ -465,9 +470,9 @@ int launch_k(const void *q_panel, int64_t q_rows, const void *r_panel, int64_t r
     g.stages = 4;
     while (g.stages > 2 && pair_smem_bytes(g.bn, g.stages, TOPK) > 200 * 1024) --g.stages;
     CUtensorMap mq, mr;
-    int rc = make_map(&mq, q_panel, q_rows, g.K, BM);
+    int rc = make_map(&mq, q_panel, q_rows, g.K, BM, g.ldq);
     if (rc != VSC_OK) return rc;
-    rc = make_map(&mr, r_panel, r_rows, g.K, g.bn);
+    rc = make_map(&mr, r_panel, r_rows, g.K, g.bn, g.ldr);
     if (rc != VSC_OK) return rc;
     const size_t smem = pair_smem_bytes(g.bn, g.stages, TOPK);
     VSC_CUDA_CHECK(cudaFuncSetAttribute(pair_gemm_kernel<K, TOPK, STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -509,6 +514,7 @@ int launch_pair_topk(const PairOperands &op, const Batch &b, const Workspace &w,
     PairArgs g = {};
     g.q_start = op.q_start; g.lq = b.lq; g.r_start = op.r_start; g.lr = b.lr; g.n_pairs = b.n_pairs;
     g.K = op.k; g.m_tiles = (b.max_lq + BM - 1) / BM; g.bias = op.bias;
+    g.ab_f16 = op.ab_f16; g.ldq = op.ldq; g.ldr = op.ldr; g.out_scale = op.out_scale;
     g.sims = sims; g.off = off; g.pair_stride = pair_stride;
     g.topk = b.topk; g.max_nodes = b.max_nodes; g.min_sim = b.min_sim; g.w = w;
     g.out_count = out.count; g.out_list = out.list;
@@ -525,7 +531,7 @@ bool pair_topk_supported(const Batch &b) { return b.max_lr <= 512 && b.topk >= 1
 extern "C" int vsc_pair_similarity(const void *d_q_panel, int64_t q_rows, const void *d_r_panel, int64_t r_rows, int32_t k,
                                    const int32_t *d_q_start, const int32_t *d_lq, const int32_t *d_r_start,
                                    const int32_t *d_lr, int32_t n_pairs, int32_t max_lq, int32_t max_lr, float bias,
-                                   float *d_sims, const int64_t *d_off, vsc_stream_t stream) {
+                                   float *d_sims, const int64_t *d_off, const vsc_gemm_format *fmt, vsc_stream_t stream) {
     if (n_pairs <= 0 || max_lq <= 0 || max_lr <= 0) return VSC_OK;
     if (!d_q_panel || !d_r_panel || !d_q_start || !d_lq || !d_r_start || !d_lr || !d_sims || !d_off) {
         vsc::set_error("vsc_pair_similarity: null pointer"); return VSC_ERR_INVALID;
@@ -533,6 +539,7 @@ extern "C" int vsc_pair_similarity(const void *d_q_panel, int64_t q_rows, const 
     PairArgs g = {};
     g.q_start = d_q_start; g.lq = d_lq; g.r_start = d_r_start; g.lr = d_lr; g.n_pairs = n_pairs;
     g.K = k; g.m_tiles = (max_lq + BM - 1) / BM; g.bias = bias;
+    if (fmt) { g.ab_f16 = fmt->ab_f16; g.ldq = fmt->lda; g.ldr = fmt->ldb; g.out_scale = fmt->d_out_scale; }
     g.sims = d_sims; g.off = d_off;
     return launch_k<1, false, true>(d_q_panel, q_rows, d_r_panel, r_rows, g, max_lr, static_cast<cudaStream_t>(stream));
 }

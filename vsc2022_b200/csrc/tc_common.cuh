@@ -84,13 +84,14 @@ __device__ __forceinline__ uint64_t umma_desc_k_major_sw128(uint32_t smem_addr) 
     d |= (uint64_t)2 << 61;                                // [61,64) layout: SWIZZLE_128B
     return d;
 }
-// Instruction descriptor, kind::f16: D fp32, A/B bf16, both K-major, shape M x N.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
-    return (1u << 4)                     // D format: fp32
-           | (1u << 7) | (1u << 10)      // A, B format: bf16
-           | ((uint32_t)(n >> 3) << 17)  // N / 8
-           | ((uint32_t)(m >> 4) << 24); // M / 16
+// Instruction descriptor, kind::f16: D fp32, A/B bf16 (format 1) or fp16 (format 0), both K-major, shape M x N.
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int m, int n, bool bf16) {
+    return (1u << 4)                                         // D format: fp32
+           | ((bf16 ? 1u : 0u) << 7) | ((bf16 ? 1u : 0u) << 10)   // A, B format
+           | ((uint32_t)(n >> 3) << 17)                      // N / 8
+           | ((uint32_t)(m >> 4) << 24);                     // M / 16
 }
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) { return umma_idesc_f16(m, n, true); }
 
 // ---------------------------------------------------------------- host side: tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -109,12 +110,13 @@ inline EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// 2D bf16 tensor [rows][k], K contiguous; box = box_rows x 64 elements, 128-byte swizzle.
-inline int make_map(CUtensorMap *map, const void *ptr, int64_t rows, int k, int box_rows) {
+// 2D tensor of 16-bit elements (bf16 or fp16: the copy does not care) [rows][k], K contiguous, row stride `ld`
+// elements (0: = k); box = box_rows x 64 elements, 128-byte swizzle.
+inline int make_map(CUtensorMap *map, const void *ptr, int64_t rows, int k, int box_rows, int64_t ld = 0) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) { vsc::set_error("cuTensorMapEncodeTiled entry point not available"); return VSC_ERR_CUDA; }
     cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)k * 2};
+    cuuint64_t strides[1] = {(cuuint64_t)(ld > 0 ? ld : k) * 2};
     cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,

@@ -66,6 +66,9 @@ struct PairOperands {
     int k;
     const int32_t *q_start, *r_start;
     float bias;
+    int ab_f16;                      // vsc_gemm_format
+    int64_t ldq, ldr;
+    const float *out_scale;
 };
 int launch_pair_topk(const PairOperands &op, const Batch &b, const Workspace &w, const WorkList &out, float *sims,
                      const int64_t *off, int64_t pair_stride, cudaStream_t stream);

@@ -1042,7 +1042,7 @@ extern "C" int vcsl_tn_batch_from_features(const void *d_q_panel, int64_t q_rows
                                            int32_t max_lq, int32_t max_lr, int32_t min_lr, float similarity_bias,
                                            const vsc_tn_params *p, float *d_sims_out, const int64_t *d_off,
                                            int32_t *d_boxes, int32_t *d_n_boxes, float *d_box_maxsim, int32_t *d_status,
-                                           int32_t force_exact_order, vsc_stream_t stream_) {
+                                           int32_t force_exact_order, const vsc_gemm_format *fmt, vsc_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     int rc = check_params(p, n_pairs, max_lq, max_lr, "vcsl_tn_batch_from_features");
     if (rc != VSC_OK) return rc;
@@ -1056,7 +1056,8 @@ extern "C" int vcsl_tn_batch_from_features(const void *d_q_panel, int64_t q_rows
     b.lq = d_lq; b.lr = d_lr; b.n_pairs = n_pairs;
     b.boxes = d_boxes; b.n_boxes = d_n_boxes; b.box_maxsim = d_box_maxsim; b.status = d_status;
     fill_batch(b, p, max_lq, max_lr);
-    vsc::tn::PairOperands op = {d_q_panel, d_r_panel, q_rows, r_rows, k, d_q_start, d_r_start, similarity_bias};
+    vsc::tn::PairOperands op = {d_q_panel, d_r_panel, q_rows, r_rows, k, d_q_start, d_r_start, similarity_bias, 0, 0, 0, nullptr};
+    if (fmt) { op.ab_f16 = fmt->ab_f16; op.ldq = fmt->lda; op.ldr = fmt->ldb; op.out_scale = fmt->d_out_scale; }
 
     // The row top-K runs out of tensor memory when every pair has at least tn_top_k columns and at most 512; the
     // similarity matrices are only written when the caller wants them back or a MaxSim score has to read them.
@@ -1079,7 +1080,7 @@ extern "C" int vcsl_tn_batch_from_features(const void *d_q_panel, int64_t q_rows
         rc = run_tn(b, &op, true, 0, stream);
     } else {
         rc = vsc_pair_similarity(d_q_panel, q_rows, d_r_panel, r_rows, k, d_q_start, d_lq, d_r_start, d_lr, n_pairs,
-                                 max_lq, max_lr, similarity_bias, sims, d_off, stream_);
+                                 max_lq, max_lr, similarity_bias, sims, d_off, fmt, stream_);
         if (rc == VSC_OK) rc = run_tn(b, nullptr, false, force_exact_order, stream);
     }
     if (sims_tmp) cudaFreeAsync(sims_tmp, stream);

@@ -1,71 +1,98 @@
 """Host wrappers of the tensor-core descriptor GEMM (csrc/gemm_tc.cu, csrc/prep.cu).
 
-Operands are prepared once (fp32 descriptors -> K-major bf16 panels) and reused across launches.
-`precise=True` uses the 3-term bf16 split (fp32-class products, K' = 3K) whenever the values are not
-bf16-representable; bf16-representable descriptors take the single-pass path automatically.
+Operands are prepared once (fp32 descriptors -> K-major fp16 split panels, include/vsc_b200.h vsc_gemm_format) and
+reused across launches.  A pair of operands multiplies over k = 3*kpad (hi.hi + hi.lo + lo.hi: every product exact in
+the fp32 accumulator, ~3e-7 absolute on unit-norm rows -- the level of an fp32 sgemm) unless every value of both
+has at most 11 significant bits (grid / test data), in which case the hi parts alone (k = kpad, same panels) are
+exact.  `precise=False` always takes the single pass.
 """
 import ctypes
-from dataclasses import dataclass
 from typing import Optional
 
 import numpy as np
 
 from . import _lib
 
-MODE_HI, MODE_SPLIT_A, MODE_SPLIT_B = 0, 1, 2
+SIDE_A, SIDE_B = 0, 1     # query side / reference side of the split (vsc_prepare_operand_f16)
 
 
 def _stream_ptr(torch, dev):
     return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
-@dataclass
 class Operand:
-    """A prepared GEMM operand: bf16 panel [rows][k] on the device."""
-    panel: "object"      # torch bf16 tensor
-    rows: int
-    k: int               # padded inner dimension actually multiplied (kpad or 3*kpad)
-    split: bool
+    """A prepared GEMM operand: fp16 panel [rows, 3*kpad] on the device + its power-of-two scale."""
+
+    def __init__(self, panel, rows: int, kpad: int, inv_scale, lo_flag, side: int):
+        self.panel, self.rows, self.kpad, self.inv_scale, self.lo_flag, self.side = panel, rows, kpad, inv_scale, lo_flag, side
+        self._needs_split: Optional[bool] = None
+        self._scales = {}
+
+    @property
+    def ld(self) -> int:
+        return 3 * self.kpad
+
+    def needs_split(self) -> bool:
+        """True unless every value is exactly representable by the hi part (one 4-byte read back, cached)."""
+        if self._needs_split is None:
+            self._needs_split = bool(int(self.lo_flag.item()))
+        return self._needs_split
+
+    def ptr(self, split: bool) -> int:
+        """Device address of the columns a GEMM reads: the whole panel, or only its last third (the hi parts)."""
+        return self.panel.data_ptr() + (0 if split else 2 * self.kpad * 2)
+
+    def rows_slice(self, r0: int, r1: int) -> "Operand":
+        sub = Operand(self.panel[r0:r1], r1 - r0, self.kpad, self.inv_scale, self.lo_flag, self.side)
+        sub._needs_split, sub._scales = self._needs_split, self._scales
+        return sub
+
+
+class Pairing:
+    """How two operands multiply: inner dimension, the format struct of the C ABI (kept alive with its scale)."""
+
+    def __init__(self, a: Operand, b: Operand, precise: bool = True):
+        assert a.kpad == b.kpad, "operands of different dimensions"
+        assert a.side == SIDE_A and b.side == SIDE_B, "first operand must be prepared as SIDE_A, second as SIDE_B"
+        self.split = precise and (a.needs_split() or b.needs_split())
+        self.k = 3 * a.kpad if self.split else a.kpad
+        key = id(b.inv_scale)
+        if key not in a._scales:
+            a._scales[key] = (a.inv_scale * b.inv_scale, b.inv_scale)    # keeps b's tensor alive: ids stay unique
+        self.scale = a._scales[key][0]
+        self.fmt = _lib.GemmFormat(1, a.ld, b.ld, self.scale.data_ptr())
+        self.col_off = 0 if self.split else 2 * a.kpad * 2      # bytes into a panel row where the multiplied columns start
+
+    def ref(self):
+        return ctypes.byref(self.fmt)
 
 
 def pad_k(d: int) -> int:
     return (d + 63) // 64 * 64
 
 
-def prepare(x, mode: int = MODE_HI, want_flag: bool = False):
-    """x: float32 CUDA tensor [n, d] (row stride may exceed d).  Returns (Operand, lo_flag tensor|None)."""
+def prepare(x, side: int) -> Operand:
+    """x: float32 CUDA tensor [n, d] (row stride may exceed d)."""
     torch = _lib.require_cuda()
     lib = _lib.load()
-    assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+    assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and (x.shape[0] == 0 or x.stride(1) == 1)
     n, d = x.shape
     kpad = pad_k(d)
-    k = kpad if mode == MODE_HI else 3 * kpad
-    out = torch.empty((max(n, 1), k), dtype=torch.bfloat16, device=x.device)
-    flag = torch.zeros((1,), dtype=torch.int32, device=x.device) if want_flag else None
+    out = torch.empty((max(n, 1), 3 * kpad), dtype=torch.float16, device=x.device)
+    meta = torch.zeros((4,), dtype=torch.int32, device=x.device)     # [inv_scale (f32 bits), lo flag, absmax scratch, -]
+    inv_scale = meta[0:1].view(torch.float32)
     with torch.cuda.device(x.device):
-        rc = lib.vsc_prepare_operand(x.data_ptr(), n, d, x.stride(0), kpad, mode, out.data_ptr(),
-                                     flag.data_ptr() if want_flag else None, _stream_ptr(torch, x.device))
-    _lib.check(rc, "vsc_prepare_operand")
-    return Operand(out, n, k, mode != MODE_HI), flag
+        rc = lib.vsc_prepare_operand_f16(x.data_ptr(), n, d, x.stride(0) if n else d, kpad, side, out.data_ptr(),
+                                         inv_scale.data_ptr(), meta[1:2].data_ptr(), meta[2:3].data_ptr(),
+                                         _stream_ptr(torch, x.device))
+    _lib.check(rc, "vsc_prepare_operand_f16")
+    return Operand(out, n, kpad, inv_scale, meta[1:2], side)
 
 
 def prepare_pair(a, b, precise: bool = True):
-    """Prepare query-side `a` and reference-side `b`; split only if some value is not bf16-representable.
-    Real descriptors never are, so the split panels are produced first (one pass, the flag comes with it) and only
-    bf16-representable inputs pay a second pass for the short panels."""
-    if not precise:
-        return prepare(a, MODE_HI)[0], prepare(b, MODE_HI)[0]
-    oa, fa = prepare(a, MODE_SPLIT_A, want_flag=True)
-    ob, fb = prepare(b, MODE_SPLIT_B, want_flag=True)
-    if not (int(fa.item()) | int(fb.item())):
-        oa, _ = prepare(a, MODE_HI)
-        ob, _ = prepare(b, MODE_HI)
-    return oa, ob
-
-
-def prepare_like(x, role: int, split: bool) -> Operand:
-    """Prepare `x` for the given role (MODE_SPLIT_A / MODE_SPLIT_B) matching an existing partner."""
-    return prepare(x, role if split else MODE_HI)[0]
+    """Prepare query-side `a` and reference-side `b`.  Returns (Operand, Operand); Pairing(oa, ob, precise) decides the
+    inner dimension."""
+    return prepare(a, SIDE_A), prepare(b, SIDE_B)
 
 
 def row_sqnorm(x):
@@ -78,39 +105,39 @@ def row_sqnorm(x):
     return out
 
 
-def gemm_store(a: Operand, b: Operand):
+def gemm_store(a: Operand, b: Operand, precise: bool = True):
     torch = _lib.require_cuda()
-    assert a.k == b.k
+    p = Pairing(a, b, precise)
     c = torch.empty((a.rows, b.rows), dtype=torch.float32, device=a.panel.device)
     with torch.cuda.device(c.device):
-        rc = _lib.load().vsc_gemm_store(a.panel.data_ptr(), a.rows, b.panel.data_ptr(), b.rows, a.k, c.data_ptr(),
-                                        b.rows, _stream_ptr(torch, c.device))
+        rc = _lib.load().vsc_gemm_store(a.ptr(p.split), a.rows, b.ptr(p.split), b.rows, p.k, c.data_ptr(),
+                                        b.rows, p.ref(), _stream_ptr(torch, c.device))
     _lib.check(rc, "vsc_gemm_store")
     return c
 
 
-def gemm_rowmax(a: Operand, b: Operand):
+def gemm_rowmax(a: Operand, b: Operand, precise: bool = True):
     torch = _lib.require_cuda()
-    assert a.k == b.k
+    p = Pairing(a, b, precise)
     out = torch.empty((max(a.rows, 1),), dtype=torch.float32, device=a.panel.device)
     with torch.cuda.device(out.device):
-        rc = _lib.load().vsc_gemm_rowmax(a.panel.data_ptr(), a.rows, b.panel.data_ptr(), b.rows, a.k,
-                                         out.data_ptr(), _stream_ptr(torch, out.device))
+        rc = _lib.load().vsc_gemm_rowmax(a.ptr(p.split), a.rows, b.ptr(p.split), b.rows, p.k,
+                                         out.data_ptr(), p.ref(), _stream_ptr(torch, out.device))
     _lib.check(rc, "vsc_gemm_rowmax")
     return out[:a.rows]
 
 
-def gemm_rowargmax(a: Operand, b: Operand):
+def gemm_rowargmax(a: Operand, b: Operand, precise: bool = True):
     """(best score, its column) per row of a.b^T; lowest column on exact ties."""
     torch = _lib.require_cuda()
-    assert a.k == b.k
+    p = Pairing(a, b, precise)
     dev = a.panel.device
     score = torch.empty((max(a.rows, 1),), dtype=torch.float32, device=dev)
     col = torch.empty((max(a.rows, 1),), dtype=torch.int64, device=dev)
     scratch = torch.empty((max(a.rows, 1),), dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
-        rc = _lib.load().vsc_gemm_rowargmax(a.panel.data_ptr(), a.rows, b.panel.data_ptr(), b.rows, a.k,
-                                            score.data_ptr(), col.data_ptr(), scratch.data_ptr(),
+        rc = _lib.load().vsc_gemm_rowargmax(a.ptr(p.split), a.rows, b.ptr(p.split), b.rows, p.k,
+                                            score.data_ptr(), col.data_ptr(), scratch.data_ptr(), p.ref(),
                                             _stream_ptr(torch, dev))
     _lib.check(rc, "vsc_gemm_rowargmax")
     return score[:a.rows], col[:a.rows]
@@ -133,10 +160,11 @@ class HitBuffer:
 
 
 def gemm_emit(a: Operand, b: Operand, hits: HitBuffer, count_thr: float, emit_thr: float, metric_l2: bool = False,
-              a_norm=None, b_norm=None, row_offset: int = 0, col_offset: int = 0, rows: Optional[slice] = None):
+              a_norm=None, b_norm=None, row_offset: int = 0, col_offset: int = 0, rows: Optional[slice] = None,
+              pairing: Optional[Pairing] = None):
     """Append the scores of a (or a[rows]) x b beyond the thresholds to `hits` (asynchronous)."""
     torch = _lib.require_cuda()
-    assert a.k == b.k
+    p = pairing if pairing is not None else Pairing(a, b)
     a_panel, m, an = a.panel, a.rows, a_norm
     if rows is not None:
         a_panel = a.panel[rows]
@@ -144,9 +172,9 @@ def gemm_emit(a: Operand, b: Operand, hits: HitBuffer, count_thr: float, emit_th
         an = a_norm[rows] if a_norm is not None else None
     with torch.cuda.device(hits.score.device):
         rc = _lib.load().vsc_gemm_emit(
-            a_panel.data_ptr(), m, b.panel.data_ptr(), b.rows, a.k,
+            a_panel.data_ptr() + p.col_off, m, b.ptr(p.split), b.rows, p.k,
             an.data_ptr() if an is not None else None, b_norm.data_ptr() if b_norm is not None else None,
             1 if metric_l2 else 0, float(count_thr), float(emit_thr), int(row_offset), int(col_offset),
             hits.score.data_ptr(), hits.row.data_ptr(), hits.col.data_ptr(), hits.capacity,
-            hits.counters.data_ptr(), _stream_ptr(torch, hits.score.device))
+            hits.counters.data_ptr(), p.ref(), _stream_ptr(torch, hits.score.device))
     _lib.check(rc, "vsc_gemm_emit")

@@ -141,7 +141,7 @@ class FlatIndex:
             return D, I
         oa, ob = gemm.prepare_pair(xq, xb, self.precise)
         if k == 1 and keep_max:
-            best, col = gemm.gemm_rowargmax(oa, ob)   # fused epilogue: nothing is materialised
+            best, col = gemm.gemm_rowargmax(oa, ob, self.precise)   # fused epilogue: nothing is materialised
             D[:, 0], I[:, 0] = best.cpu().numpy(), col.cpu().numpy()
             return D, I
         kk = min(k, nb)
@@ -154,7 +154,7 @@ class FlatIndex:
         assert self.metric_type == METRIC_INNER_PRODUCT
         xq = self._to_device(x)
         oa, ob = gemm.prepare_pair(xq, self.database(), self.precise)
-        return gemm.gemm_rowmax(oa, ob)
+        return gemm.gemm_rowmax(oa, ob, self.precise)
 
     def _knn_dense(self, xq, xb, oa, ob, k):
         """General k: per-row top-k from stored score tiles (row blocks sized to ~1 GiB of scores)."""
@@ -169,8 +169,7 @@ class FlatIndex:
         I = np.empty((nq, k), np.int64)
         for r0 in range(0, nq, step):
             r1 = min(nq, r0 + step)
-            sub = gemm.Operand(oa.panel[r0:r1], r1 - r0, oa.k, oa.split)
-            s = gemm.gemm_store(sub, ob)
+            s = gemm.gemm_store(oa.rows_slice(r0, r1), ob, self.precise)
             if not keep_max:
                 s = qn[r0:r1, None] + bn[None, :] - 2.0 * s
             # stable order: best first, equal scores by ascending database index
@@ -221,6 +220,7 @@ class FlatIndex:
         if capacity is None:
             capacity = max(4 * max_results, min(32 * nb, 1 << 26)) + 65536
         hits = gemm.HitBuffer(int(capacity), dev)
+        pairing = gemm.Pairing(oa, ob, self.precise)
         held, total, prune, padded = 0, 0, radius, False
         unbounded = True   # radius still at its initial value: every pair is a hit, emission size is known
         for b0, b1 in exponential_batches(nq):
@@ -239,7 +239,7 @@ class FlatIndex:
                     hits.counters[0] = held
                     hits.counters[1] = 0
                     gemm.gemm_emit(oa, ob, hits, radius, prune, metric_l2=not keep_max, a_norm=qn, b_norm=bn,
-                                   row_offset=r0, rows=slice(r0, r0 + rows))
+                                   row_offset=r0, rows=slice(r0, r0 + rows), pairing=pairing)
                     stored, counted = hits.read_counters()
                 if rows < 1 or stored > hits.capacity:
                     # does not fit: forget this launch, prune (or grow), retry with fewer rows

@@ -4,8 +4,8 @@ Same classes and signatures as the reference.  `VCSLLocalization.localize_all` i
 
 * the frame descriptors of the videos involved are uploaded once (a collection that consists of row views of one big
   array -- what `storage.load_features` returns -- goes up in a single copy; float16 descriptors are widened on the
-  device) and turned into the K-major bf16 panels of the tensor-core GEMM (3-term split unless every value is
-  bf16-representable, see gemm.py);
+  device) and turned into the K-major fp16 split panels of the tensor-core GEMM (three partial products unless every
+  value fits the hi part, see gemm.py);
 * `vcsl_tn_batch_from_features` multiplies every pair Q_p . R_p^T + bias on tcgen05 tensor cores and runs the temporal
   network on the result; for the usual shapes the Lq x Lr matrices never leave tensor memory
   (csrc/pair_gemm.cu).  They are written out only when a scorer reads them (MaxSim) -- and even then stay on the device:
@@ -229,9 +229,9 @@ class VCSLLocalization(LocalizationWithMetadata):
             Q, R = dq.matrix(), dr.matrix()
             if Q.shape[1] != R.shape[1]:
                 raise ValueError(f"query descriptors have {Q.shape[1]} dimensions, reference descriptors {R.shape[1]}")
-            oq, orr = gemm.prepare_pair(Q, R, precise=True)
-            self._panels = (key, oq, orr)
-        return self._panels[1], self._panels[2]
+            oq, orr = gemm.prepare_pair(Q, R)
+            self._panels = (key, oq, orr, gemm.Pairing(oq, orr, precise=True))
+        return self._panels[1], self._panels[2], self._panels[3]
 
     def _similarity_use(self):
         known = (VCSLLocalization.score, VCSLLocalizationMaxSim.score, VCSLLocalizationCandidateScore.score)
@@ -250,7 +250,7 @@ class VCSLLocalization(LocalizationWithMetadata):
         dr.prefetch(r_ids[0])
         dq.ensure(q_ids)
         dr.ensure(r_ids)
-        oq, orr = self._operands()
+        oq, orr, pairing = self._operands()
         n = len(candidates)
         meta = np.empty((4, n), dtype=np.int32)      # q_start, lq, r_start, lr
         meta[0] = [dq.start[i] for i in q_ids]
@@ -268,9 +268,10 @@ class VCSLLocalization(LocalizationWithMetadata):
             sims = torch.empty((int(padded.sum()) + 4,), dtype=torch.float32, device=dev)
             d_off = torch.from_numpy(off).to(dev, non_blocking=True)
         res = tn_batch_from_features(
-            oq.panel, orr.panel, oq.k, d_meta[0], d_meta[1], d_meta[2], d_meta[3], n, int(meta[1].max()),
+            oq.panel, orr.panel, pairing.k, d_meta[0], d_meta[1], d_meta[2], d_meta[3], n, int(meta[1].max()),
             int(meta[3].max()), int(meta[3].min()), float(self.similarity_bias), self.model.params,
-            want_maxsim=(use == "boxmax"), sims_out=sims, d_off=d_off, force_exact_order=self.model.force_exact_order)
+            want_maxsim=(use == "boxmax"), sims_out=sims, d_off=d_off, force_exact_order=self.model.force_exact_order,
+            fmt=pairing)
         self.model.last_result = res
         boxes, n_boxes, maxsim, _ = res.to_host()
 

@@ -97,9 +97,10 @@ def tn_batch_device(d_sims, d_off, d_lq, d_lr, n_pairs: int, max_lq: int, max_lr
 
 def tn_batch_from_features(q_panel, r_panel, k: int, d_q_start, d_lq, d_r_start, d_lr, n_pairs: int, max_lq: int,
                            max_lr: int, min_lr: int, bias: float, params: "_lib.TnParams", want_maxsim: bool = False,
-                           sims_out=None, d_off=None, force_exact_order: bool = False, stream=None) -> TnResult:
+                           sims_out=None, d_off=None, force_exact_order: bool = False, stream=None, fmt=None) -> TnResult:
     """Align `n_pairs` pairs whose similarity matrices are Q_p . R_p^T + bias of rows of two descriptor panels
-    (bf16 CUDA tensors [rows, k] from gemm.prepare): the batch form of localization.py:57-58.  Asynchronous."""
+    (CUDA tensors from gemm.prepare; `fmt`: their gemm.Pairing, None for plain bf16 panels of row stride k): the batch
+    form of localization.py:57-58.  Asynchronous."""
     torch = _lib.require_cuda()
     lib = _lib.load()
     dev = q_panel.device
@@ -108,28 +109,32 @@ def tn_batch_from_features(q_panel, r_panel, k: int, d_q_start, d_lq, d_r_start,
     base = res.buf.data_ptr()
     s = stream if stream is not None else torch.cuda.current_stream(dev)
     with torch.cuda.device(dev):
+        off = fmt.col_off if fmt is not None else 0
         rc = lib.vcsl_tn_batch_from_features(
-            q_panel.data_ptr(), q_panel.shape[0], r_panel.data_ptr(), r_panel.shape[0], int(k),
+            q_panel.data_ptr() + off, q_panel.shape[0], r_panel.data_ptr() + off, r_panel.shape[0], int(k),
             d_q_start.data_ptr(), d_lq.data_ptr(), d_r_start.data_ptr(), d_lr.data_ptr(), n_pairs,
             int(max_lq), int(max_lr), int(min_lr), float(bias), ctypes.byref(params),
             sims_out.data_ptr() if sims_out is not None else None, d_off.data_ptr() if d_off is not None else None,
             base + 4 * res._o_boxes, base + 4 * res._o_nb, base + 4 * res._o_ms if want_maxsim else None,
-            base + 4 * res._o_st, 1 if force_exact_order else 0, ctypes.c_void_p(s.cuda_stream))
+            base + 4 * res._o_st, 1 if force_exact_order else 0, fmt.ref() if fmt is not None else None,
+            ctypes.c_void_p(s.cuda_stream))
     _lib.check(rc, "vcsl_tn_batch_from_features")
     return res
 
 
 def pair_similarity(q_panel, r_panel, k: int, d_q_start, d_lq, d_r_start, d_lr, n_pairs: int, max_lq: int, max_lr: int,
-                    bias: float, sims_out, d_off, stream=None):
+                    bias: float, sims_out, d_off, stream=None, fmt=None):
     """sims_out[d_off[p] + i * lr[p] + j] = Q[q_start[p] + i] . R[r_start[p] + j] + bias (localization.py:33-36,49-54)."""
     torch = _lib.require_cuda()
     dev = q_panel.device
     s = stream if stream is not None else torch.cuda.current_stream(dev)
     with torch.cuda.device(dev):
+        off = fmt.col_off if fmt is not None else 0
         rc = _lib.load().vsc_pair_similarity(
-            q_panel.data_ptr(), q_panel.shape[0], r_panel.data_ptr(), r_panel.shape[0], int(k), d_q_start.data_ptr(),
+            q_panel.data_ptr() + off, q_panel.shape[0], r_panel.data_ptr() + off, r_panel.shape[0], int(k), d_q_start.data_ptr(),
             d_lq.data_ptr(), d_r_start.data_ptr(), d_lr.data_ptr(), n_pairs, int(max_lq), int(max_lr), float(bias),
-            sims_out.data_ptr(), d_off.data_ptr(), ctypes.c_void_p(s.cuda_stream))
+            sims_out.data_ptr(), d_off.data_ptr(), fmt.ref() if fmt is not None else None,
+            ctypes.c_void_p(s.cuda_stream))
     _lib.check(rc, "vsc_pair_similarity")
     return sims_out
 
