@@ -141,11 +141,36 @@ int vsc_row_sqnorm(const float *d_x, int64_t n, int32_t d, int64_t ld, float *d_
 int vsc_kth_best(const float *d_scores, int64_t n, int64_t k, int32_t largest, float *d_out, void *d_scratch,
                  vsc_stream_t stream);
 
+/* One radix-selection pass in two halves, for a k-th best over scores spread over several GPUs (query-sharded search):
+ * vsc_select_hist counts this GPU's scores into the 2048-bin histogram at the start of d_state (8224 bytes: histogram,
+ * then {prefix, mask, k}; pass 0 initialises it with k), the caller sums the histograms over the GPUs (all-reduce),
+ * vsc_select_pick narrows the key prefix.  Passes 0, 1, 2; after the last pick *d_out is the k-th best. */
+int vsc_select_hist(const float *d_scores, int64_t n, int64_t k, int32_t largest, int32_t pass, void *d_state,
+                    vsc_stream_t stream);
+int vsc_select_pick(int32_t largest, int32_t pass, void *d_state, float *d_out, vsc_stream_t stream);
+
 /* The re-filter of apply_maxres: copy the entries of (score, row, col)[0..n) strictly beyond `radius` to the output
  * arrays (unspecified order, no overlap with the inputs); *d_count receives how many. */
 int vsc_compact_hits(const float *d_score, const int32_t *d_row, const int32_t *d_col, int64_t n, float radius,
                      int32_t keep_max, float *d_score_out, int32_t *d_row_out, int32_t *d_col_out,
                      unsigned long long *d_count, vsc_stream_t stream);
+
+/* The whole global-threshold search of VideoIndex._global_threshold_knn_search (vsc/index.py:142-165):
+ *   faiss.contrib.exhaustive_search.range_search_max_results(index, exponential_query_iterator(xq), radius,
+ *                                                            max_results, min_results)
+ * enqueued without a host round trip: per exponential query batch (32, 64, ... rows) one vsc_gemm_emit-style launch whose
+ * thresholds live in the device-side control block, followed by FAISS's bookkeeping there -- when the running total exceeds
+ * max_results the (min_results+1)-th best held score becomes the radius and everything held is re-filtered strictly.
+ * d_a: query panel (row stride a_row_bytes), d_b: reference panel.  Survivors end up in d_score / d_row / d_col[0 .. held)
+ * (d_*2: scratch of the same capacity).  d_control: vsc_search_control_bytes() bytes; after the stream has drained it
+ * holds {float radius; float; int32; int32 overflow; uint64 held; ...}.  overflow != 0: a batch emitted more than
+ * `capacity` entries and the result is incomplete (repeat with more room or batch by batch with vsc_gemm_emit). */
+int vsc_search_global_topk(const void *d_a, int64_t m, const void *d_b, int64_t n, int32_t k, const float *d_a_norm,
+                           const float *d_b_norm, int32_t metric_l2, int64_t max_results, int64_t min_results,
+                           float *d_score, int32_t *d_row, int32_t *d_col, float *d_score2, int32_t *d_row2,
+                           int32_t *d_col2, uint64_t capacity, void *d_control, int32_t a_row_bytes,
+                           const vsc_gemm_format *fmt, vsc_stream_t stream);
+int vsc_search_control_bytes(void);
 
 /* C[m][n] = A . B^T in fp32 (tests, per-pair similarity matrices). */
 int vsc_gemm_store(const void *d_a, int64_t m, const void *d_b, int64_t n, int32_t k, float *d_c, int64_t ldc,

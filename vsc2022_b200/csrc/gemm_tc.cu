@@ -58,6 +58,7 @@ struct GemmArgs {
     const float *a_norm, *b_norm;  // squared norms (L2 metric) or null
     int metric_l2;
     float count_thr, emit_thr;
+    const float *thr_ptr;            // when set: {count_thr, emit_thr} are read from device memory (device-driven search)
     int64_t row_offset, col_offset;  // added to the emitted indices
     float *out_score; int32_t *out_row, *out_col;
     unsigned long long capacity;
@@ -144,7 +145,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs &g, float &best, i
         // inner product: the comparisons run on the raw accumulators against thresholds divided by the (power-of-two,
         // hence exact) output scale; only the emitted scores are scaled
         const float inv = g.metric_l2 ? 1.0f : 1.0f / osc;
-        const float emit_thr = g.emit_thr * inv, count_thr = g.count_thr * inv;
+        const float emit_thr = (g.thr_ptr ? g.thr_ptr[1] : g.emit_thr) * inv, count_thr = (g.thr_ptr ? g.thr_ptr[0] : g.count_thr) * inv;
         const bool two = emit_thr != count_thr;  // uniform: the common case has one threshold
         float an = 0.0f;
         if (!g.metric_l2) {
@@ -743,6 +744,22 @@ extern "C" int vsc_gemm_rowargmax(const void *d_a, int64_t m, const void *d_b, i
     vsc::count_launch();
     return VSC_OK;
 }
+
+namespace vsc {
+// range-search launch with the thresholds in device memory (search.cu): d_thr = {count threshold, emit threshold}
+int launch_emit_device(const void *d_a, int64_t m, const void *d_b, int64_t n, int32_t k, const float *d_a_norm,
+                       const float *d_b_norm, int32_t metric_l2, const float *d_thr, int64_t row_offset, float *d_score,
+                       int32_t *d_row, int32_t *d_col, uint64_t capacity, unsigned long long *d_counters,
+                       const vsc_gemm_format *fmt, cudaStream_t stream) {
+    GemmArgs g = {};
+    apply_format(g, fmt);
+    g.M = m; g.N = n; g.K = k;
+    g.a_norm = d_a_norm; g.b_norm = d_b_norm; g.metric_l2 = metric_l2; g.thr_ptr = d_thr;
+    g.row_offset = row_offset; g.out_score = d_score; g.out_row = d_row; g.out_col = d_col;
+    g.capacity = capacity; g.counters = d_counters;
+    return launch<EPI_EMIT, 256>(d_a, d_b, g, stream);
+}
+}  // namespace vsc
 
 extern "C" int vsc_gemm_emit(const void *d_a, int64_t m, const void *d_b, int64_t n, int32_t k, const float *d_a_norm,
                              const float *d_b_norm, int32_t metric_l2, float count_thr, float emit_thr,

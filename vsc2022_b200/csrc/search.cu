@@ -1,0 +1,54 @@
+// Global-threshold search, whole schedule enqueued from C++ without a host round trip.
+//
+// Replaces VideoIndex._global_threshold_knn_search's engine call (vsc/index.py:142-165):
+//   faiss.contrib.exhaustive_search.range_search_max_results(index, exponential_query_iterator(xq),
+//                                                            radius, max_results=2K, min_results=K)
+// FAISS runs a range search per exponential query batch (32, 64, ... rows), and whenever it holds more than max_results
+// results it makes the (min_results+1)-th best held score the new radius and re-filters everything strictly.  The
+// result is every pair beyond the FINAL radius; the radius trajectory (and with it the behaviour at exact ties) depends
+// on the batch schedule, so the schedule is followed literally -- but the bookkeeping (result count, the decision to
+// tighten, the radius) lives in a device-side control block: each batch is {tensor-core range search with the thresholds
+// read from that block} + {decide, radix-select the radius, strict re-filter}, the last seven kernels doing nothing
+// unless the batch pushed the total over max_results.  The host reads the control block once, at the end.
+// If a batch emits more than the buffer holds the block says so and the caller repeats the search the host-driven way
+// (vsc2022_b200/index.py), which can split batches and prune.
+#include "search_internal.cuh"
+
+extern "C" int vsc_search_global_topk(const void *d_a, int64_t m, const void *d_b, int64_t n, int32_t k,
+                                      const float *d_a_norm, const float *d_b_norm, int32_t metric_l2,
+                                      int64_t max_results, int64_t min_results, float *d_score, int32_t *d_row,
+                                      int32_t *d_col, float *d_score2, int32_t *d_row2, int32_t *d_col2,
+                                      uint64_t capacity, void *d_control, int32_t a_row_bytes,
+                                      const vsc_gemm_format *fmt, vsc_stream_t stream_) {
+    using namespace vsc;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (m < 0 || n < 0 || !d_control || !d_score || !d_row || !d_col || !d_score2 || !d_row2 || !d_col2 ||
+        max_results < min_results || min_results < 0 || a_row_bytes <= 0) {
+        set_error("vsc_search_global_topk: bad arguments"); return VSC_ERR_INVALID;
+    }
+    if (metric_l2 && (!d_a_norm || !d_b_norm)) { set_error("vsc_search_global_topk: L2 metric needs squared norms"); return VSC_ERR_INVALID; }
+    SearchControl *ctl = static_cast<SearchControl *>(d_control);
+    VSC_CUDA_CHECK(cudaMemsetAsync(ctl, 0, sizeof(SearchControl), stream));
+    const float radius0 = metric_l2 ? 1e10f : -1e10f;
+    const float thr0[2] = {radius0, radius0};
+    VSC_CUDA_CHECK(cudaMemcpyAsync(ctl->thr, thr0, sizeof thr0, cudaMemcpyHostToDevice, stream));
+    if (m == 0 || n == 0) return VSC_OK;
+    const int keep_max = metric_l2 ? 0 : 1;
+    // faiss.contrib.exhaustive_search.exponential_query_iterator: 32, 64, ... doubling while < 20000
+    int64_t size = 32;
+    for (int64_t at = 0; at < m;) {
+        const int64_t rows = at + size < m ? size : m - at;
+        int rc = launch_emit_device(static_cast<const char *>(d_a) + at * a_row_bytes, rows, d_b, n, k,
+                                    d_a_norm ? d_a_norm + at : nullptr, d_b_norm, metric_l2, ctl->thr, at, d_score, d_row,
+                                    d_col, capacity, ctl->counters, fmt, stream);
+        if (rc != VSC_OK) return rc;
+        rc = search_after_batch(ctl, d_score, d_row, d_col, d_score2, d_row2, d_col2, capacity, max_results, min_results,
+                                keep_max, stream);
+        if (rc != VSC_OK) return rc;
+        at += rows;
+        if (size < 20000) size *= 2;
+    }
+    return search_final_filter(ctl, d_score, d_row, d_col, d_score2, d_row2, d_col2, keep_max, stream);
+}
+
+extern "C" int vsc_search_control_bytes(void) { return (int)sizeof(vsc::SearchControl); }

@@ -6,16 +6,14 @@
 // scores cost 2-3 ms per tightening and there are five or six tightenings per 40k x 200k search; three histogram
 // passes (11 + 11 + 10 bits of the order-preserving key) read the array three times instead.  HBM-bound.
 #include "common.cuh"
+#include "search_internal.cuh"
 
 namespace {
 
 constexpr int kBins = 2048;
 
-struct SelectState {          // lives in device memory between the passes
-    uint32_t prefix;          // key bits decided so far (aligned to the top)
-    uint32_t mask;            // which bits are decided
-    unsigned long long k;     // rank still to find inside the matching elements (1 = best)
-};
+using vsc::SearchControl;
+using vsc::SelectState;
 
 __device__ __forceinline__ uint32_t order_key(float v, int largest) {
     const uint32_t key = vsc::float_to_key(v);     // ascending with the value
@@ -23,10 +21,17 @@ __device__ __forceinline__ uint32_t order_key(float v, int largest) {
 }
 
 // histogram of `bits` key bits starting at `shift` over the elements that match the decided prefix
+// `ctl` (may be null): device-driven search -- the element count is ctl->counters[0] and the kernel does nothing unless
+// ctl->do_tighten is set.
 __global__ void __launch_bounds__(512) select_hist_kernel(const float *__restrict__ x, int64_t n, int largest, int shift,
                                                           int bits, const SelectState *__restrict__ st,
-                                                          unsigned int *__restrict__ hist) {
+                                                          unsigned int *__restrict__ hist,
+                                                          const SearchControl *__restrict__ ctl) {
     __shared__ unsigned int h[kBins];
+    if (ctl) {
+        if (!ctl->do_tighten || ctl->overflow) return;
+        n = (int64_t)ctl->counters[0];
+    }
     for (int i = threadIdx.x; i < kBins; i += blockDim.x) h[i] = 0;
     __syncthreads();
     const uint32_t prefix = st->prefix, mask = st->mask, field = (1u << bits) - 1u;
@@ -42,8 +47,10 @@ __global__ void __launch_bounds__(512) select_hist_kernel(const float *__restric
 // one block of 256 threads: find the bin (counting from the best = highest key downwards) that holds the remaining
 // rank.  Thread t owns bins [8t, 8t+8); an inclusive suffix sum over the threads' totals locates the owner.
 __global__ void __launch_bounds__(256) select_pick_kernel(SelectState *st, unsigned int *hist, int shift, int bits,
-                                                          int largest, int last, float *out) {
+                                                          int largest, int last, float *out,
+                                                          const SearchControl *__restrict__ ctl) {
     __shared__ unsigned long long suffix[256];
+    if (ctl && !ctl->do_tighten) return;
     const int t = threadIdx.x;
     unsigned int c[8];
     unsigned long long mine = 0;
@@ -80,9 +87,15 @@ __global__ void __launch_bounds__(256) select_pick_kernel(SelectState *st, unsig
 __global__ void __launch_bounds__(256) compact_kernel(const float *__restrict__ s_in, const int32_t *__restrict__ r_in,
                                                       const int32_t *__restrict__ c_in, int64_t n, float radius,
                                                       int keep_max, float *__restrict__ s_out, int32_t *__restrict__ r_out,
-                                                      int32_t *__restrict__ c_out, unsigned long long *__restrict__ count) {
+                                                      int32_t *__restrict__ c_out, unsigned long long *__restrict__ count,
+                                                      const SearchControl *__restrict__ ctl, int always) {
     __shared__ unsigned int warp_total[8];
     __shared__ unsigned long long block_base;
+    if (ctl) {   // device-driven search: count and radius live in the control block
+        if ((!always && !ctl->do_tighten) || ctl->overflow) return;   // after an overflow the count exceeds the buffer
+        n = (int64_t)ctl->counters[0];
+        radius = ctl->thr[0];
+    }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int64_t i0 = (int64_t)blockIdx.x * 256; i0 < n; i0 += (int64_t)gridDim.x * 256) {
         const int64_t i = i0 + threadIdx.x;
@@ -110,7 +123,75 @@ __global__ void __launch_bounds__(256) compact_kernel(const float *__restrict__ 
     }
 }
 
+
+// ---- device-driven FAISS schedule (search.cu): small control kernels
+__global__ void search_decide_kernel(SearchControl *c, unsigned long long capacity, unsigned long long max_results,
+                                     unsigned long long min_results) {
+    c->total += c->counters[1];
+    c->counters[1] = 0;
+    c->kept = 0;
+    if (c->counters[0] > capacity) c->overflow = 1;   // entries were dropped: the host repeats the search its own way
+    c->do_tighten = !c->overflow && c->total > max_results;
+    if (c->do_tighten) { c->sel.prefix = 0; c->sel.mask = 0; c->sel.k = min_results + 1; }
+}
+__global__ void __launch_bounds__(256) search_copy_back_kernel(const SearchControl *__restrict__ c, const float *__restrict__ s2,
+                                                               const int32_t *__restrict__ r2, const int32_t *__restrict__ c2,
+                                                               float *__restrict__ s, int32_t *__restrict__ r,
+                                                               int32_t *__restrict__ cc, int always) {
+    if ((!always && !c->do_tighten) || c->overflow) return;
+    const int64_t n = (int64_t)c->kept;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        s[i] = s2[i]; r[i] = r2[i]; cc[i] = c2[i];
+    }
+}
+__global__ void search_finish_kernel(SearchControl *c, int always) {
+    if ((!always && !c->do_tighten) || c->overflow) return;
+    c->counters[0] = c->kept;
+    if (!always) { c->total = c->kept; c->thr[1] = c->thr[0]; c->n_tighten += 1; }
+    c->do_tighten = 0;
+}
+
 }  // namespace
+
+namespace vsc {
+
+// After one range-search launch of the device-driven schedule: FAISS's bookkeeping, and -- when the running total
+// exceeds max_results -- the new radius ((min_results+1)-th best held score, radix selection) and the strict re-filter.
+int search_after_batch(SearchControl *ctl, float *s, int32_t *r, int32_t *c, float *s2, int32_t *r2, int32_t *c2,
+                       uint64_t capacity, int64_t max_results, int64_t min_results, int keep_max, cudaStream_t stream) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    search_decide_kernel<<<1, 1, 0, stream>>>(ctl, capacity, (unsigned long long)max_results, (unsigned long long)min_results);
+    const int shifts[3] = {21, 10, 0}, bits[3] = {11, 11, 10};
+    for (int p = 0; p < 3; ++p) {
+        select_hist_kernel<<<sms * 4, 512, 0, stream>>>(s, 0, keep_max, shifts[p], bits[p], &ctl->sel, ctl->hist, ctl);
+        select_pick_kernel<<<1, 256, 0, stream>>>(&ctl->sel, ctl->hist, shifts[p], bits[p], keep_max, p == 2, &ctl->thr[0], ctl);
+    }
+    compact_kernel<<<sms * 8, 256, 0, stream>>>(s, r, c, 0, 0.0f, keep_max, s2, r2, c2, &ctl->kept, ctl, 0);
+    search_copy_back_kernel<<<sms * 4, 256, 0, stream>>>(ctl, s2, r2, c2, s, r, c, 0);
+    search_finish_kernel<<<1, 1, 0, stream>>>(ctl, 0);
+    VSC_CUDA_CHECK(cudaGetLastError());
+    vsc::count_launch(10);
+    return VSC_OK;
+}
+
+// End of the schedule: drop the never-accepted fillers of the emit epilogue (strict re-filter with the final radius).
+int search_final_filter(SearchControl *ctl, float *s, int32_t *r, int32_t *c, float *s2, int32_t *r2, int32_t *c2,
+                        int keep_max, cudaStream_t stream) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    VSC_CUDA_CHECK(cudaMemsetAsync(&ctl->kept, 0, sizeof(unsigned long long), stream));
+    compact_kernel<<<sms * 8, 256, 0, stream>>>(s, r, c, 0, 0.0f, keep_max, s2, r2, c2, &ctl->kept, ctl, 1);
+    search_copy_back_kernel<<<sms * 4, 256, 0, stream>>>(ctl, s2, r2, c2, s, r, c, 1);
+    search_finish_kernel<<<1, 1, 0, stream>>>(ctl, 1);
+    VSC_CUDA_CHECK(cudaGetLastError());
+    vsc::count_launch(3);
+    return VSC_OK;
+}
+
+}  // namespace vsc
 
 // Copies the entries of (score, row, col)[0..n) whose score is strictly beyond `radius` (greater for keep_max != 0,
 // smaller otherwise) to the output arrays in unspecified order; *d_count (zeroed here) receives how many.  The
@@ -127,7 +208,7 @@ extern "C" int vsc_compact_hits(const float *d_score, const int32_t *d_row, cons
     const int64_t want = (n + 255) / 256;
     const int grid = (int)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
     compact_kernel<<<grid, 256, 0, stream>>>(d_score, d_row, d_col, n, radius, keep_max, d_score_out, d_row_out,
-                                             d_col_out, d_count);
+                                             d_col_out, d_count, nullptr, 0);
     VSC_CUDA_CHECK(cudaGetLastError());
     vsc::count_launch();
     return VSC_OK;
@@ -154,10 +235,50 @@ extern "C" int vsc_kth_best(const float *d_scores, int64_t n, int64_t k, int32_t
     const int grid = (int)(want < (int64_t)sms * 4 ? want : (int64_t)sms * 4);
     const int shifts[3] = {21, 10, 0}, bits[3] = {11, 11, 10};
     for (int p = 0; p < 3; ++p) {
-        select_hist_kernel<<<grid, 512, 0, stream>>>(d_scores, n, largest, shifts[p], bits[p], st, hist);
-        select_pick_kernel<<<1, 256, 0, stream>>>(st, hist, shifts[p], bits[p], largest, p == 2, d_out);
+        select_hist_kernel<<<grid, 512, 0, stream>>>(d_scores, n, largest, shifts[p], bits[p], st, hist, nullptr);
+        select_pick_kernel<<<1, 256, 0, stream>>>(st, hist, shifts[p], bits[p], largest, p == 2, d_out, nullptr);
     }
     VSC_CUDA_CHECK(cudaGetLastError());
     vsc::count_launch(6);
+    return VSC_OK;
+}
+
+// The two halves of one radix-selection pass, for selections whose histogram is summed over several GPUs between them
+// (query-sharded search: every rank counts its own held scores, the histograms are all-reduced, every rank picks the
+// same bin).  d_state: 8208 + 16 bytes = 2048 histogram bins followed by {prefix, mask, k}; pass 0 initialises it with k.
+// pass in 0..2; after the pick of pass 2, *d_out holds the k-th best score.
+extern "C" int vsc_select_hist(const float *d_scores, int64_t n, int64_t k, int32_t largest, int32_t pass, void *d_state,
+                               vsc_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (pass < 0 || pass > 2 || !d_state || n < 0) { vsc::set_error("vsc_select_hist: bad arguments"); return VSC_ERR_INVALID; }
+    unsigned int *hist = static_cast<unsigned int *>(d_state);
+    SelectState *st = reinterpret_cast<SelectState *>(hist + kBins);
+    if (pass == 0) {
+        VSC_CUDA_CHECK(cudaMemsetAsync(d_state, 0, sizeof(unsigned int) * kBins + sizeof(SelectState), stream));
+        const SelectState init = {0u, 0u, (unsigned long long)k};
+        VSC_CUDA_CHECK(cudaMemcpyAsync(st, &init, sizeof init, cudaMemcpyHostToDevice, stream));
+    }
+    if (n == 0) return VSC_OK;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t want = (n + 511) / 512;
+    const int grid = (int)(want < (int64_t)sms * 4 ? want : (int64_t)sms * 4);
+    const int shifts[3] = {21, 10, 0}, bits[3] = {11, 11, 10};
+    select_hist_kernel<<<grid, 512, 0, stream>>>(d_scores, n, largest, shifts[pass], bits[pass], st, hist, nullptr);
+    VSC_CUDA_CHECK(cudaGetLastError());
+    vsc::count_launch();
+    return VSC_OK;
+}
+
+extern "C" int vsc_select_pick(int32_t largest, int32_t pass, void *d_state, float *d_out, vsc_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (pass < 0 || pass > 2 || !d_state || !d_out) { vsc::set_error("vsc_select_pick: bad arguments"); return VSC_ERR_INVALID; }
+    unsigned int *hist = static_cast<unsigned int *>(d_state);
+    SelectState *st = reinterpret_cast<SelectState *>(hist + kBins);
+    const int shifts[3] = {21, 10, 0}, bits[3] = {11, 11, 10};
+    select_pick_kernel<<<1, 256, 0, stream>>>(st, hist, shifts[pass], bits[pass], largest, pass == 2, d_out, nullptr);
+    VSC_CUDA_CHECK(cudaGetLastError());
+    vsc::count_launch();
     return VSC_OK;
 }

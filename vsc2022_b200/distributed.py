@@ -68,13 +68,42 @@ def global_count(local_count: int, device, group=None) -> int:
     return int(c.item())
 
 
-def agree_radius(local_scores: torch.Tensor, k: int, keep_max: bool, group=None) -> float:
+def agree_radius(local_scores: torch.Tensor, k: int, keep_max: bool, group=None, fallback: float = None) -> float:
     """The k-th best score over the union of every rank's held scores (k-th largest for inner product, k-th
-    smallest for L2) -- FAISS's new radius when the global total exceeds max_results (k = min_results + 1)."""
+    smallest for L2) -- FAISS's new radius when the global total exceeds max_results (k = min_results + 1).
+
+    On CUDA tensors: three radix-selection passes whose 2048-bin histograms are all-reduced (8 KB per pass over
+    NVLink; csrc/select.cu vsc_select_hist / vsc_select_pick) -- no score leaves its GPU.  CPU tensors (the gloo
+    tests of the host logic) gather and sort.  Fewer than k scores in total (possible only after an in-batch prune,
+    which drops the k-th best itself): the answer is the best prune threshold of any rank, passed as `fallback`."""
+    rank, ws = world(group)
+    n_all = global_count(local_scores.numel(), local_scores.device, group)
+    if n_all < k:
+        if fallback is None:
+            raise ValueError(f"agree_radius: only {n_all} scores for k = {k}")
+        t = torch.tensor([fallback], dtype=torch.float64, device=local_scores.device)
+        if ws > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX if keep_max else dist.ReduceOp.MIN, group=group)
+        return float(t.item())
+    if local_scores.is_cuda:
+        import ctypes
+        from . import _lib
+        lib = _lib.load()
+        scores = local_scores.contiguous()
+        state = torch.empty((2048 + 8,), dtype=torch.int32, device=scores.device)
+        out = torch.empty((1,), dtype=torch.float32, device=scores.device)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(scores.device).cuda_stream)
+        with torch.cuda.device(scores.device):
+            for p in range(3):
+                _lib.check(lib.vsc_select_hist(scores.data_ptr(), scores.numel(), int(k), 1 if keep_max else 0, p,
+                                               state.data_ptr(), stream), "vsc_select_hist")
+                if ws > 1:
+                    dist.all_reduce(state[:2048], op=dist.ReduceOp.SUM, group=group)
+                _lib.check(lib.vsc_select_pick(1 if keep_max else 0, p, state.data_ptr(), out.data_ptr(), stream),
+                           "vsc_select_pick")
+        return float(out.item())
     every = all_gather_variable(local_scores, group)
-    if keep_max:
-        return float(torch.topk(every, k, largest=True, sorted=True).values[-1])
-    return float(torch.topk(every, k, largest=False, sorted=True).values[-1])
+    return float(torch.topk(every, k, largest=keep_max, sorted=True).values[-1])
 
 
 def max_over_ranks(value: float, device, group=None) -> float:

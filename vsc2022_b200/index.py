@@ -84,6 +84,7 @@ class FlatIndex:
     def __init__(self, d: int, metric_type: int = METRIC_INNER_PRODUCT, device=None, precise: bool = True):
         self.d, self.metric_type, self.precise = int(d), int(metric_type), precise
         self._device = device
+        self.device_schedule = True   # single GPU: enqueue FAISS's whole batch schedule in one call (csrc/search.cu)
         self._host_chunks: List[np.ndarray] = []
         self._xb = None          # float32 CUDA tensor [ntotal, d]
         self._ntotal = 0
@@ -218,9 +219,14 @@ class FlatIndex:
         if not keep_max:
             qn, bn = gemm.row_sqnorm(xq), gemm.row_sqnorm(xb)
         if capacity is None:
-            capacity = max(4 * max_results, min(32 * nb, 1 << 26)) + 65536
+            capacity = max(4 * max_results, min(32 * nb, 1 << 26)) + EMIT_PAD + 65536   # the first 32-row batch fits
         hits = gemm.HitBuffer(int(capacity), dev)
         pairing = gemm.Pairing(oa, ob, self.precise)
+        if ws == 1 and self.device_schedule:
+            done = self._device_schedule(oa, ob, pairing, qn, bn, hits, max_results, min_results, keep_max)
+            if done is not None:
+                return done
+            hits.counters.zero_()   # a batch overflowed the buffer: batch by batch below, which can split and prune
         held, total, prune, padded = 0, 0, radius, False
         unbounded = True   # radius still at its initial value: every pair is a hit, emission size is known
         for b0, b1 in exponential_batches(nq):
@@ -255,10 +261,16 @@ class FlatIndex:
                 rows = b1 - r0
             total += D.global_count(batch_counted, dev, group) if ws > 1 else batch_counted
             if total > max_results:
+                # the fillers of the emit epilogue go first; then the (min_results+1)-th best of what is held.  After an
+                # in-batch prune fewer than that may be left (the prune drops the k-th best itself, strictly): FAISS's
+                # value is then the prune threshold (the k-th best over everything it would still hold).
+                held = self._refilter(hits, held, prune, keep_max)
                 if ws > 1:
-                    radius = D.agree_radius(hits.score[:held], min_results + 1, keep_max, group)
-                else:
+                    radius = D.agree_radius(hits.score[:held], min_results + 1, keep_max, group, fallback=prune)
+                elif held >= min_results + 1:
                     radius = self._kth_best(hits.score[:held], min_results + 1, keep_max)
+                else:
+                    radius = prune
                 held = self._refilter(hits, held, radius, keep_max)
                 total = D.global_count(held, dev, group) if ws > 1 else held
                 prune, unbounded = radius, False
@@ -267,6 +279,35 @@ class FlatIndex:
                 padded = True
         if padded:   # drop the never-accepted fillers of the emit epilogue's per-warp blocks (see gemm_tc.cu)
             held = self._refilter(hits, held, prune, keep_max)
+        return hits.score[:held], hits.row[:held].long(), hits.col[:held].long(), radius
+
+    def _device_schedule(self, oa, ob, pairing, qn, bn, hits, max_results, min_results, keep_max):
+        """The whole FAISS schedule in one engine call (csrc/search.cu): no host round trip until the end.
+        Returns None if a batch emitted more than the buffer holds."""
+        import ctypes
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        dev = hits.score.device
+        if getattr(hits, "twin", None) is None:
+            hits.twin = (torch.empty_like(hits.score), torch.empty_like(hits.row), torch.empty_like(hits.col))
+            hits.kept = torch.zeros(1, dtype=torch.int64, device=dev)
+        ctl = torch.zeros(((lib.vsc_search_control_bytes() + 7) // 8,), dtype=torch.int64, device=dev)
+        s2, r2, c2 = hits.twin
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        with torch.cuda.device(dev):
+            rc = lib.vsc_search_global_topk(
+                oa.ptr(pairing.split), oa.rows, ob.ptr(pairing.split), ob.rows, pairing.k,
+                qn.data_ptr() if qn is not None else None, bn.data_ptr() if bn is not None else None,
+                0 if keep_max else 1, int(max_results), int(min_results), hits.score.data_ptr(), hits.row.data_ptr(),
+                hits.col.data_ptr(), s2.data_ptr(), r2.data_ptr(), c2.data_ptr(), hits.capacity, ctl.data_ptr(),
+                oa.ld * 2, pairing.ref(), stream)
+        _lib.check(rc, "vsc_search_global_topk")
+        head = ctl[:4].cpu().numpy()                     # the one read back: {radius, -, do_tighten, overflow | held | ...}
+        radius = float(head[:1].view(np.float32)[0])
+        overflow = int(head[1:2].view(np.int32)[1])
+        held = int(head[2])
+        if overflow:
+            return None
         return hits.score[:held], hits.row[:held].long(), hits.col[:held].long(), radius
 
     @staticmethod
