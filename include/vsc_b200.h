@@ -172,6 +172,25 @@ int vsc_search_global_topk(const void *d_a, int64_t m, const void *d_b, int64_t 
                            const vsc_gemm_format *fmt, vsc_stream_t stream);
 int vsc_search_control_bytes(void);
 
+/* Score normalisation around the row-max GEMM (vsc/baseline/score_normalization.py:68-104), one pass each:
+ * vsc_lowvar_dim      *d_out = argmin over columns of the population variance of x[n][d] (:73-76); d_scratch: 16*d bytes.
+ * vsc_l2norm_dropdim  out[i] = x[i] without column *d_drop (NULL: keep all), divided by its L2 norm when normalize != 0
+ *                     (rows of norm 0 stay: sklearn.preprocessing.normalize) (:77-85); has_tail: out[i][kept columns] = tail
+ *                     (the appended 1 of the references, :100-104).  ldo: row stride of out.
+ * vsc_fill_column     out[i][col] = factor * src[i] (the appended -beta * 1-NN similarity of the queries, :97-99). */
+int vsc_lowvar_dim(const float *d_x, int64_t n, int32_t d, int64_t ld, int32_t *d_out, void *d_scratch, vsc_stream_t stream);
+int vsc_l2norm_dropdim(const float *d_x, int64_t n, int32_t d, int64_t ld, const int32_t *d_drop, int32_t normalize,
+                       float *d_out, int64_t ldo, int32_t has_tail, float tail, vsc_stream_t stream);
+int vsc_fill_column(float *d_out, int64_t n, int64_t ldo, int32_t col, const float *d_src, float factor, vsc_stream_t stream);
+/* MaxScoreAggregation over the frame matches of every video pair (vsc/candidates.py:24-40): the n hits arrive sorted
+ * best first (d_row / d_col: query / reference frame rows), d_q_vid / d_r_vid give the video of every row.  Writes the
+ * first `limit` (query video, reference video, best score) triples in order of first appearance -- the reference's dict
+ * order followed by its stable sort -- and the number of distinct pairs.  d_scratch: vsc_pair_max_scratch_bytes(n). */
+int64_t vsc_pair_max_scratch_bytes(int64_t n);
+int vsc_pair_max(const int64_t *d_row, const int64_t *d_col, const float *d_score, int64_t n, const int32_t *d_q_vid,
+                 const int32_t *d_r_vid, int64_t n_ref_videos, int64_t limit, int32_t *d_out_q, int32_t *d_out_r,
+                 float *d_out_score, unsigned long long *d_n_unique, void *d_scratch, vsc_stream_t stream);
+
 /* C[m][n] = A . B^T in fp32 (tests, per-pair similarity matrices). */
 int vsc_gemm_store(const void *d_a, int64_t m, const void *d_b, int64_t n, int32_t k, float *d_c, int64_t ldc,
                    const vsc_gemm_format *fmt, vsc_stream_t stream);

@@ -291,3 +291,42 @@ def test_gaussian_descriptors_against_numpy_search():
     assert sorted(firm([(c.query_id, c.ref_id - 1000, c.score) for c in cands])) == sorted(firm(want_c))
     top = [(c.query_id, c.ref_id - 1000) for c in cands[:15]]
     assert top == [(a, b) for a, b, _ in want_c[:15]]            # the planted copies lead, in the same order
+
+
+def test_score_normalize_device_handoff_and_small_kernels(golden_c1):
+    """score_normalize(on_device=True) -> CandidateGeneration -> localization without a host round trip gives what the
+    host-array path gives; the small kernels against numpy (lowest-variance column, drop + L2 normalise, pair max)."""
+    import torch
+    from vsc2022_b200 import sscd_baseline
+    from vsc2022_b200.device_features import is_device_tensor, to_host
+    from vsc2022_b200.index import VideoFeature
+    from vsc2022_b200.score_normalization import l2norm_dropdim, lowvar_dim, score_normalize
+    g = golden_c1
+    ts = g["timestamps"]
+    vids = lambda x, base: [VideoFeature(video_id=base + i, timestamps=ts, feature=x[i]) for i in range(len(x))]
+    queries, refs, noise = vids(g["q"], 0), vids(g["r"], 100), vids(g["noise"], 200)
+    hq, hr = score_normalize(queries, refs, noise, beta=1.2)
+    dq, dr = score_normalize(queries, refs, noise, beta=1.2, on_device=True)
+    assert all(is_device_tensor(v.feature) for v in dq + dr)
+    for a, b in zip(hq + hr, to_host(dq) + to_host(dr)):
+        assert np.array_equal(a.feature, b.feature)
+    c_host, c_dev = sscd_baseline.search(hq, hr), sscd_baseline.search(dq, dr)
+    assert c_host == c_dev and [[c.query_id, c.ref_id] for c in c_dev] == g["sn_cand_ids"].tolist()
+    m_host = sscd_baseline.localize_and_verify(hq, hr, c_host, score_normalization=True)
+    m_dev = sscd_baseline.localize_and_verify(dq, dr, c_dev, score_normalization=True)
+    assert m_host == m_dev and len(m_dev) == len(g["sn_match_ids"])
+    # kernels against numpy on a larger random matrix
+    rng = np.random.default_rng(53)
+    x = rng.normal(size=(5000, 300)).astype(np.float32) * rng.uniform(0.5, 2.0, size=300).astype(np.float32)
+    x[:, 123] *= 0.01
+    d_x = torch.from_numpy(x).cuda()
+    drop = lowvar_dim(d_x)
+    assert int(drop.item()) == int(x.var(axis=0).argmin()) == 123
+    out, kept = l2norm_dropdim(d_x, drop, True, extra_column=True, tail=1.0)
+    ref = np.delete(x, 123, axis=1)
+    ref = ref / np.linalg.norm(ref, axis=1, keepdims=True)
+    assert kept == 299 and out.shape == (5000, 300)
+    np.testing.assert_allclose(out[:, :299].cpu().numpy(), ref, atol=3e-7, rtol=0)
+    assert (out[:, 299] == 1.0).all()
+    raw, _ = l2norm_dropdim(d_x, None, False, extra_column=False)
+    assert np.array_equal(raw.cpu().numpy(), x)

@@ -47,25 +47,32 @@ class CandidateGeneration:
         return candidates if limit is None else candidates[:limit]
 
     def _query_max_fused(self, queries, global_k, limit, group=None):
+        """Global top-K frame pairs, then the per-video-pair maximum, without leaving the device: csrc/search_ops.cu
+        vsc_pair_max (hash of video pairs -> first appearance in the best-first hit list -> ordered compaction)."""
+        import ctypes
         torch = _lib.require_cuda()
-        feats = np.concatenate([q.feature for q in queries])
-        row, col, score = self.index.global_topk_device(feats, global_k, group=group)
-        if score.numel() == 0:
+        row, col, score = self.index.global_topk_device(queries, global_k, group=group)
+        n = score.numel()
+        if n == 0:
             return []
         dev = score.device
-        q_len = torch.tensor([len(q) for q in queries], dtype=torch.int64, device=dev)
-        r_len = torch.from_numpy(self._ref_lengths).to(dev)
-        q_vid = torch.repeat_interleave(torch.arange(len(queries), device=dev), q_len)[row]
-        r_vid = torch.repeat_interleave(torch.arange(len(self._ref_ids), device=dev), r_len)[col]
-        key = q_vid * len(self._ref_ids) + r_vid
-        # hits are sorted best-first: a pair's first appearance carries its maximum, and first-appearance order
-        # is exactly the reference's dict order followed by its stable sort
-        uniq, inverse = torch.unique(key, return_inverse=True)
-        first = torch.full((uniq.numel(),), key.numel(), dtype=torch.int64, device=dev)
-        first.scatter_reduce_(0, inverse, torch.arange(key.numel(), device=dev), reduce="amin")
-        first = torch.sort(first).values
-        if limit is not None:
-            first = first[:limit]
-        qv, rv, sc = q_vid[first].cpu().numpy(), r_vid[first].cpu().numpy(), score[first].cpu().numpy()
+        q_vid = torch.from_numpy(np.repeat(np.arange(len(queries), dtype=np.int32), [len(q) for q in queries])).to(dev)
+        r_vid = torch.from_numpy(np.repeat(np.arange(len(self._ref_ids), dtype=np.int32), self._ref_lengths)).to(dev)
+        lib = _lib.load()
+        cap = n if limit is None else min(n, int(limit))
+        out_q = torch.empty((cap,), dtype=torch.int32, device=dev)
+        out_r = torch.empty((cap,), dtype=torch.int32, device=dev)
+        out_s = torch.empty((cap,), dtype=torch.float32, device=dev)
+        n_unique = torch.zeros((1,), dtype=torch.int64, device=dev)
+        scratch = torch.empty((int(lib.vsc_pair_max_scratch_bytes(n)),), dtype=torch.uint8, device=dev)
+        row, col, score = row.contiguous(), col.contiguous(), score.contiguous()
+        with torch.cuda.device(dev):
+            rc = lib.vsc_pair_max(row.data_ptr(), col.data_ptr(), score.data_ptr(), n, q_vid.data_ptr(), r_vid.data_ptr(),
+                                  len(self._ref_ids), cap, out_q.data_ptr(), out_r.data_ptr(), out_s.data_ptr(),
+                                  n_unique.data_ptr(), scratch.data_ptr(),
+                                  ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        _lib.check(rc, "vsc_pair_max")
+        k = min(cap, int(n_unique.item()))
+        qv, rv, sc = out_q[:k].cpu().numpy(), out_r[:k].cpu().numpy(), out_s[:k].cpu().numpy()
         return [CandidatePair(query_id=queries[a].video_id, ref_id=self._ref_ids[b], score=s)
                 for a, b, s in zip(qv, rv, sc)]

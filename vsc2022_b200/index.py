@@ -104,11 +104,15 @@ class FlatIndex:
         self._ntotal += x.shape[0]
         self._xb = None
 
-    def add_device(self, x):
-        """Append descriptors that already live on the device (float32 CUDA tensor [n, d])."""
+    def add_device(self, x, copy: bool = True):
+        """Append descriptors that already live on the device (float32 CUDA tensor [n, d]).  copy=False adopts the
+        tensor when the index is empty (the caller promises not to modify it)."""
         torch = _lib.require_cuda()
         base = self.database()
-        self._xb = x.clone() if base is None or base.shape[0] == 0 else torch.cat([base, x])
+        if base is None or base.shape[0] == 0:
+            self._xb = x.clone() if copy else x
+        else:
+            self._xb = torch.cat([base, x])
         self._host_chunks = []
         self._ntotal = self._xb.shape[0]
 
@@ -125,6 +129,9 @@ class FlatIndex:
     # ---- FAISS-style entry points ------------------------------------------------------------------------
     def _to_device(self, x):
         torch = _lib.require_cuda()
+        if isinstance(x, (list, tuple)):      # VideoFeatures: device tensors stay, row views of one array go up at once
+            from .device_features import features_matrix
+            return features_matrix(x, self.device())
         if isinstance(x, np.ndarray):
             return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(self.device())
         return x.to(self.device(), torch.float32)
@@ -371,12 +378,16 @@ class VideoIndex:
         self.video_metadata = {}
 
     def add(self, db: List[VideoFeature]):
-        for vf in db:
-            n = vf.feature.shape[0]
+        from .device_features import features_matrix
+        lens = [vf.feature.shape[0] for vf in db]
+        for vf, n in zip(db, lens):
             self.video_clip_idx.extend(range(n))
             self.video_clip_to_video_ids.extend([vf.video_id] * n)
             self.video_metadata[vf.video_id] = vf.metadata()
-            self.index.add(vf.feature)
+        if db:   # one upload (or none: device-resident descriptors) instead of a host copy per video
+            from .device_features import is_device_tensor
+            # FAISS semantics: the index owns a copy (an upload already is one)
+            self.index.add_device(features_matrix(db, self.index.device()), copy=is_device_tensor(db[0].feature))
 
     def search(self, queries: List[VideoFeature], global_k: int) -> List[PairMatches]:
         query_ids, query_indices = [], []
@@ -384,7 +395,7 @@ class VideoIndex:
             query_ids.extend([q.video_id] * len(q))
             query_indices.extend(range(len(q)))
         query_metadatas = {q.video_id: q.metadata() for q in queries}
-        query_features = np.concatenate([q.feature for q in queries])
+        query_features = queries   # stacked on the device by FlatIndex._to_device
         if global_k < 0:
             logging.warning(
                 "Using local k for KNN search. Warning: this is against the VSC rules, since predictions for a "
@@ -419,11 +430,11 @@ class VideoIndex:
         order = torch.sort(score, descending=keep_max, stable=True).indices[:global_k]
         return row[order], col[order], score[order]
 
-    def _global_threshold_knn_search(self, query_features: np.ndarray, global_k: int) -> Iterable[SearchIndices]:
+    def _global_threshold_knn_search(self, query_features, global_k: int) -> Iterable[SearchIndices]:
         row, col, score = self.global_topk_device(query_features, global_k)
         return list(zip(row.cpu().numpy().tolist(), col.cpu().numpy().tolist(), score.cpu().numpy()))
 
-    def _knn_search(self, query_features: np.ndarray, k: int) -> Iterable[SearchIndices]:
+    def _knn_search(self, query_features, k: int) -> Iterable[SearchIndices]:
         similarity, ids = self.index.search(query_features, k)
         for i in range(ids.shape[0]):
             for j in range(ids.shape[1]):

@@ -20,6 +20,7 @@ from typing import Dict, List
 import numpy as np
 
 from . import _lib, gemm
+from .device_features import features_matrix, is_device_tensor, root_of as _root_of
 from .index import VideoFeature
 from .metrics import CandidatePair, Match
 
@@ -46,29 +47,6 @@ class LocalizationWithMetadata(Localization):
         return np.matmul(self.queries[candidate.query_id].feature, self.refs[candidate.ref_id].feature.T)
 
 
-def _root_of(arr: np.ndarray, cache: dict = None):
-    """(root array, first row of `arr` inside it) if `arr` is a block of whole rows of a base array (1-D or 2-D,
-    C-contiguous), else None.  `cache` memoises the per-root facts (this runs once per video of a collection)."""
-    root = arr.base
-    if not isinstance(root, np.ndarray):
-        return None
-    while isinstance(root.base, np.ndarray):
-        root = root.base
-    info = cache.get(id(root)) if cache is not None else None
-    if info is None:
-        ok = root.ndim in (1, 2) and root.flags.c_contiguous and root.shape[0] > 0
-        info = (root, ok, root.__array_interface__["data"][0], root.strides, root.shape[1:], root.dtype, root.shape[0])
-        if cache is not None:
-            cache[id(root)] = info
-    _, ok, ptr, strides, tail, dtype, rows = info
-    if not ok or arr.dtype != dtype or arr.shape[1:] != tail or (arr.shape[0] and arr.strides != strides):
-        return None
-    row, rem = divmod(arr.__array_interface__["data"][0] - ptr, strides[0])
-    if rem or row < 0 or row + arr.shape[0] > rows:
-        return None
-    return root, row
-
-
 class _DeviceVideos:
     """Frame descriptors (and timestamps) of a video collection on the device, uploaded lazily.
 
@@ -91,15 +69,19 @@ class _DeviceVideos:
         self._root_cache = {}       # id(root) -> facts about that base array (keeps the array alive: ids stay unique)
         self.h2d_bytes = 0
 
-    def _upload(self, host: np.ndarray):
+    def _upload(self, host):
+        """Append rows: a host array (copied up) or a device matrix (adopted as it is)."""
         torch = _lib.require_cuda()
-        if host.dtype not in (np.float32, np.float16):
-            host = host.astype(np.float32)
-        t = torch.from_numpy(host)
-        self.h2d_bytes += t.numel() * t.element_size()
-        d = t.to(self.device, non_blocking=True)
-        if d.dtype != torch.float32:
-            d = d.float()           # --store_fp16 descriptors (inference_impl.py:230-231): widened on the device
+        if is_device_tensor(host):
+            d = host.to(self.device, torch.float32)
+        else:
+            if host.dtype not in (np.float32, np.float16):
+                host = host.astype(np.float32)
+            t = torch.from_numpy(host)
+            self.h2d_bytes += t.numel() * t.element_size()
+            d = t.to(self.device, non_blocking=True)
+            if d.dtype != torch.float32:
+                d = d.float()       # --store_fp16 descriptors (inference_impl.py:230-231): widened on the device
         first = self.rows
         self.segments.append(d)
         self.rows += d.shape[0]
@@ -127,7 +109,7 @@ class _DeviceVideos:
     def prefetch(self, vid):
         """Start the upload of the base array `vid`'s descriptors are a view of (asynchronous from pinned memory), so
         that the copy runs while the host walks the rest of the collection."""
-        if vid in self.start:
+        if vid in self.start or is_device_tensor(self.videos[vid].feature):
             return
         where = _root_of(self.videos[vid].feature, self._root_cache)
         if where is not None and id(where[0]) not in self._roots and where[0].shape[0] <= self.MAX_WASTE * (1 << 20):
@@ -140,6 +122,14 @@ class _DeviceVideos:
             return
         loose = []
         by_root = {}
+        on_device = [i for i in new if is_device_tensor(self.videos[i].feature)]
+        if on_device:   # descriptors that never left the GPU (score_normalize(on_device=True)): no copy over PCIe
+            first, seg = self._upload(features_matrix([self.videos[i] for i in on_device], self.device))
+            at = first
+            for i in on_device:
+                self._register(i, at, seg, first)
+                at += len(self.videos[i])
+            new = [i for i in new if not is_device_tensor(self.videos[i].feature)]
         for i in new:
             f = self.videos[i].feature
             if f.ndim != 2:

@@ -18,6 +18,7 @@ from .candidates import CandidateGeneration, MaxScoreAggregation
 from .index import VideoFeature
 from .localization import VCSLLocalizationCandidateScore, VCSLLocalizationMaxSim
 from .metrics import AveragePrecision, CandidatePair, Dataset, Match, average_precision, evaluate_matching_track
+from .device_features import to_host
 from .score_normalization import score_normalize, transform_features
 from .storage import load_features, store_features
 
@@ -101,11 +102,14 @@ def main(args):
     refs = load_features(args.ref_features, Dataset.REFS)
     score_normalization = False
     if args.score_norm_features:
-        queries, refs = score_normalize(queries, refs, load_features(args.score_norm_features, Dataset.REFS), beta=1.2)
+        # the normalised descriptors stay on the device for the search and the localization; the .npz copies the
+        # reference writes are taken from there
+        queries, refs = score_normalize(queries, refs, load_features(args.score_norm_features, Dataset.REFS), beta=1.2,
+                                        on_device=True)
         score_normalization = True
         os.makedirs(args.output_path, exist_ok=True)
-        store_features(os.path.join(args.output_path, "sn_queries.npz"), queries)
-        store_features(os.path.join(args.output_path, "sn_refs.npz"), refs)
+        store_features(os.path.join(args.output_path, "sn_queries.npz"), to_host(queries))
+        store_features(os.path.join(args.output_path, "sn_refs.npz"), to_host(refs))
     candidate_file, match_file = match(queries, refs, args.output_path, score_normalization=score_normalization)
     if not args.ground_truth:
         return
