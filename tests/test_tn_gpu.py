@@ -138,3 +138,16 @@ def test_compact_graph_variant_matches():
     for i, s in enumerate(sims[:96]):
         for k, (x1, y1, x2, y2) in enumerate(got[i]):
             assert maxsim[i, k] == s[x1:x2, y1:y2].max()
+
+
+def test_equal_distance_runs_stay_on_the_fast_pipeline():
+    """A chain whose edges were spent leaves a run of nodes with EQUAL distances (dist(v) = dist(u) + 0): ties at the
+    maximum between nodes of different Kahn generations, which the smallest generation resolves.  tests/golden/
+    tn_equal_distance_run.npz is such a matrix (pair 2618 of the bench workload, as the tensor-core GEMM produced it)."""
+    import os
+    s = np.load(os.path.join(os.path.dirname(__file__), "golden", "tn_equal_distance_run.npz"))["sims"]
+    sims = [s, np.ascontiguousarray(s[:, :296]), np.ascontiguousarray(s[:299])]
+    got, _, status = run_gpu(sims, **VSC_CFG)
+    want = tn_fast.tn_batch(sims, tn_max_step=5, tn_top_k=5, max_path=10, min_sim=0.2, min_length=4, max_iou=0.3)
+    assert got == want
+    assert (status == 0).all(), status

@@ -46,6 +46,8 @@ struct Workspace {
     int rec_bytes, sim_off;  // record size and byte offset of the similarity inside it
     int32_t *skip;      // [P] 1 = handed to the general kernel
     int32_t *cursor;    // T1 tile counter
+    // pairs whose end-node tie only the full Kahn order can break go straight to the exact-order kernel's work list
+    int32_t *exact_count, *exact_list;
 };
 
 template <typename MaskT>

@@ -439,7 +439,10 @@ __global__ void __launch_bounds__(32) tn_paths_kernel(const Batch b, const Works
     }
     if (lane == 0) {
         if (ambiguous) {
-            if (atomicExch(&w.skip[pair], 1) == 0) out.list[atomicAdd(out.count, 1)] = pair;
+            if (atomicExch(&w.skip[pair], 1) == 0) {
+                if (w.exact_list) w.exact_list[atomicAdd(w.exact_count, 1)] = pair;
+                else out.list[atomicAdd(out.count, 1)] = pair;
+            }
         } else {
             b.n_boxes[pair] = n_boxes;
             if (b.status) b.status[pair] = 0;

@@ -431,6 +431,45 @@ __device__ __forceinline__ void relax_node(MaskT pm, MaskT zm, float w, int q, i
     if (best_slot >= 0 && !(best >= 0.0f)) { best = 0.0f; best_slot = -1; }  // networkx: negative best -> (0, v)
 }
 
+// ---- exact order of two nodes of the SAME Kahn generation in networkx's topological order, without a Kahn pass.
+// networkx.topological_generations visits a generation in order and appends a child to the next one when its LAST parent
+// is processed, children of one parent in adjacency order (= node id order here).  So for two nodes of generation g:
+// the one whose last parent comes first in generation g-1 comes first; same last parent -> lower id first.  Generation 0
+// (zero in-degree) is in id order.  The last parent of a generation-1 node is its highest-id predecessor (the highest
+// slot: ascending slots are ascending predecessor ids).  For g >= 2 the last parent is known without recursion only if
+// exactly one predecessor lies in generation g-1; otherwise `undecided` is set and the pair goes to the exact-order kernel.
+template <typename MaskT, int K, int GS>
+__device__ __forceinline__ int parent_of_slot(int v, int sl, int step) {
+    const int grp = sl / GS;
+    return (v / K - (step - 1 - grp)) * K + (sl - grp * GS);
+}
+template <typename MaskT, int K, int GS>
+__device__ int topo_compare(int a, int b, int g, int step, const NodeRec<MaskT> *rec, const uint16_t *gen, bool &undecided) {
+    for (;;) {
+        if (a == b) return 0;
+        if (g <= 0) return a < b ? -1 : 1;
+        const MaskT ma = load_rec(&rec[a]).pred, mb = load_rec(&rec[b]).pred;
+        int pa = -1, pb = -1;
+        if (g == 1) {
+            pa = parent_of_slot<MaskT, K, GS>(a, sizeof(MaskT) == 8 ? 63 - __clzll((long long)ma) : 31 - __clz((int)ma), step);
+            pb = parent_of_slot<MaskT, K, GS>(b, sizeof(MaskT) == 8 ? 63 - __clzll((long long)mb) : 31 - __clz((int)mb), step);
+        } else {
+            int na = 0, nb = 0;
+            for (MaskT m = ma; m; m &= m - 1) {
+                const int u = parent_of_slot<MaskT, K, GS>(a, sizeof(MaskT) == 8 ? __ffsll((long long)m) - 1 : __ffs((int)m) - 1, step);
+                if (gen[u] == g - 1) { pa = u; ++na; }
+            }
+            for (MaskT m = mb; m; m &= m - 1) {
+                const int u = parent_of_slot<MaskT, K, GS>(b, sizeof(MaskT) == 8 ? __ffsll((long long)m) - 1 : __ffs((int)m) - 1, step);
+                if (gen[u] == g - 1) { pb = u; ++nb; }
+            }
+            if (na != 1 || nb != 1) { undecided = true; return a < b ? -1 : 1; }
+        }
+        if (pa == pb) return a < b ? -1 : 1;
+        a = pa; b = pb; --g;
+    }
+}
+
 template <typename MaskT, int K, int GS>
 __global__ void __launch_bounds__(kT2Threads, 16 / kT2Warps) tn_dp_kernel(const Batch b, const Workspace w, const WorkList out) {
     // WARP-SYNCHRONOUS: the four octets of a warp run every loop together (trip count = the longest of the
@@ -523,7 +562,10 @@ __global__ void __launch_bounds__(kT2Threads, 16 / kT2Warps) tn_dp_kernel(const 
         if (mk == 0u) searching = false;  // only zero-length paths left: networkx returns [source]
         const bool holds_max = searching && mine_max == mk;
         const int layers_at_max = oct_add(holds_max ? n_layers : 0, kFullMask);
+        // Ties at the maximum: the smallest generation wins.  Several nodes of that generation (rare): topo_compare gives
+        // networkx's order among them, or leaves the pair to the exact-order kernel.
         int bg = INT_MAX, bv = -1, cnt = 0;
+        bool undecided = false;
         if (holds_max) {
             const uint32_t m0 = lrank[q_first];
             if (layers_at_max == 1 && (m0 & (m0 - 1)) == 0u) {   // a single node: no tie to break
@@ -541,10 +583,33 @@ __global__ void __launch_bounds__(kT2Threads, 16 / kT2Warps) tn_dp_kernel(const 
             }
         }
         const int g_min = oct_min(bg, kFullMask);
-        const bool mine_best = searching && bg == g_min;
-        if (oct_add(mine_best ? cnt : 0, kFullMask) > 1 && searching) { ambiguous = true; searching = false; }
-        const unsigned who = __ballot_sync(kFullMask, mine_best && searching) & om;
-        const int end = __shfl_sync(kFullMask, bv, who ? __ffs(who) - 1 : lane);
+        const bool finalist = searching && bg == g_min;
+        const int tied = oct_add(finalist ? cnt : 0, kFullMask);
+        if (finalist && cnt > 1) {   // this lane's own candidates of the winning generation, in networkx order
+            for (int q = q_first; q < lq; q += 8) {
+                if (lbest[q] != mk) continue;
+                for (uint32_t m = lrank[q]; m; m &= m - 1) {
+                    const int v = q * K + __ffs((int)m) - 1;
+                    if (v != bv && gen[v] == g_min && topo_compare<MaskT, K, GS>(v, bv, g_min, step, rec, gen, undecided) < 0) bv = v;
+                }
+            }
+        }
+        int end = -1;
+        if (__any_sync(kFullMask, tied > 1)) {   // the octet's first lane decides between the lanes' winners
+            for (int k = 0; k < 8; ++k) {
+                const int cand = __shfl_sync(kFullMask, finalist ? bv : -1, oct * 8 + k);
+                if (sub == 0 && cand >= 0) {
+                    if (end < 0) end = cand;
+                    else if (topo_compare<MaskT, K, GS>(cand, end, g_min, step, rec, gen, undecided) < 0) end = cand;
+                }
+            }
+            undecided = (__ballot_sync(kFullMask, undecided) & om) != 0;
+            end = __shfl_sync(kFullMask, end, oct * 8);
+        } else {
+            const unsigned who = __ballot_sync(kFullMask, finalist) & om;
+            end = __shfl_sync(kFullMask, bv, who ? __ffs(who) - 1 : lane);
+        }
+        if (undecided && searching) { ambiguous = true; searching = false; }
 
         VSC_CLK(1);
         // ---- walk the chain back through the best-predecessor slots (shared memory only, one lane per octet)
@@ -678,7 +743,8 @@ __global__ void __launch_bounds__(kT2Threads, 16 / kT2Warps) tn_dp_kernel(const 
     if (sub == 0 && alive) {
         if (ambiguous) {
             w.skip[pair] = 1;
-            out.list[atomicAdd(out.count, 1)] = pair;
+            if (w.exact_list) w.exact_list[atomicAdd(w.exact_count, 1)] = pair;
+            else out.list[atomicAdd(out.count, 1)] = pair;
         } else {
             b.n_boxes[pair] = n_boxes;
             if (b.status) b.status[pair] = 0;
@@ -804,6 +870,7 @@ int workspace_alloc(const Batch &b, Workspace *w, void **base_out, cudaStream_t 
     w->rec = base + o_rec; w->rec_bytes = (int)rec_bytes; w->sim_off = wide ? 16 : 8;
     w->ref_of = reinterpret_cast<uint16_t *>(base + o_ref); w->gen = reinterpret_cast<uint16_t *>(base + o_gen);
     w->skip = reinterpret_cast<int32_t *>(base + o_skip); w->cursor = reinterpret_cast<int32_t *>(base + o_cursor);
+    w->exact_count = nullptr; w->exact_list = nullptr;
     VSC_CUDA_CHECK(cudaMemsetAsync(w->gen, 0, P * N * 2, stream));
     VSC_CUDA_CHECK(cudaMemsetAsync(w->skip, 0, (o_cursor - o_skip) + 4, stream));
     return VSC_OK;
@@ -990,6 +1057,7 @@ int run_tn(vsc::tn::Batch b, const vsc::tn::PairOperands *op, bool features_dire
             vsc::count_launch();
         } else if (op && features_direct && graph_supported(b) && pair_topk_supported(b)) {
             rc = workspace_alloc(b, &w, &ws_base, stream);
+            w.exact_count = B.count; w.exact_list = B.list;
             if (rc == VSC_OK) rc = launch_pipeline_from_features(*op, b, w, A, stream);
             if (rc == VSC_OK) {   // pairs handed back read their node records instead of a similarity matrix
                 Batch bn = b;
@@ -1002,6 +1070,7 @@ int run_tn(vsc::tn::Batch b, const vsc::tn::PairOperands *op, bool features_dire
             return rc;
         } else if (pipeline_supported(b)) {
             rc = workspace_alloc(b, &w, &ws_base, stream);
+            w.exact_count = B.count; w.exact_list = B.list;
             if (rc == VSC_OK) rc = launch_pipeline(b, w, A, stream);
             if (rc == VSC_OK) rc = launch_fused(b, false, &A, &B, 2, stream);
         } else {

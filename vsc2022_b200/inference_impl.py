@@ -63,11 +63,14 @@ def run_inference(dataloader: Iterable[dict], model: Callable, device=None, stor
 
 
 def infer_videos(videos: Sequence[Tuple[object, np.ndarray, object]], model: Callable, batch_size: int = 128,
-                 store_fp16: bool = False, device=None) -> List[VideoFeature]:
+                 store_fp16: bool = False, device=None, on_device: bool = False) -> List[VideoFeature]:
     """videos: (video_id, timestamps [n] or [n, 2], frames) with frames uint8 [n, H, W, 3] or normalised float32
     [n, 3, H, W] (numpy or torch).  Frames of all videos must share one geometry.  Returns one VideoFeature per video, in
-    order, identical to feeding every video on its own."""
+    order, identical to feeding every video on its own.  on_device=True (extension): the descriptors stay on the GPU --
+    every VideoFeature holds a row view of one device matrix, ready for score_normalize / CandidateGeneration."""
     import torch
+    if on_device:
+        return _infer_videos_device(videos, model, batch_size, store_fp16, device)
     counts = [int(len(f)) for _, _, f in videos]
     out: List[Optional[np.ndarray]] = [None] * len(videos)
     pending: List[Tuple[int, int, int]] = []      # (video, first frame, frames) of the batch being packed
@@ -107,6 +110,40 @@ def infer_videos(videos: Sequence[Tuple[object, np.ndarray, object]], model: Cal
         feat = np.concatenate(chunks[v], axis=0) if chunks[v] else np.zeros((0, dim), np.float16 if store_fp16 else np.float32)
         out[v] = VideoFeature(video_id=vid, timestamps=np.asarray(ts), feature=feat)
     return out  # type: ignore[return-value]
+
+
+def _infer_videos_device(videos, model, batch_size, store_fp16, device):
+    import torch
+    counts = [int(len(f)) for _, _, f in videos]
+    total = sum(counts)
+    out_mat = None
+    flat = [(v, s) for v, n in enumerate(counts) for s in range(0, n, 1)]   # frame -> (video, frame): packed batches
+    at = 0
+    while at < total:
+        take = min(batch_size, total - at)
+        parts, v, s = [], flat[at][0], flat[at][1]
+        left = take
+        while left:
+            n = min(left, counts[v] - s)
+            fr = videos[v][2][s:s + n]
+            parts.append(fr if isinstance(fr, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(fr)))
+            left -= n
+            v, s = v + 1, 0
+        frames = torch.cat(parts) if len(parts) > 1 else parts[0]
+        if device is not None:
+            frames = frames.to(device, non_blocking=True)
+        feats = model(frames)
+        if out_mat is None:
+            out_mat = torch.empty((total, feats.shape[1]), dtype=torch.float16 if store_fp16 else feats.dtype, device=feats.device)
+        out_mat[at:at + take] = feats
+        at += take
+    if out_mat is None:
+        out_mat = torch.zeros((0, 0), dtype=torch.float32, device=device)
+    out, at = [], 0
+    for (vid, ts, _), n in zip(videos, counts):
+        out.append(VideoFeature(video_id=vid, timestamps=np.asarray(ts), feature=out_mat[at:at + n]))
+        at += n
+    return out
 
 
 def merge_feature_files(filenames: List[str], output_filename: str) -> int:

@@ -66,8 +66,16 @@ def score_normalize(queries: List[VideoFeature], refs: List[VideoFeature], score
     torch = _lib.require_cuda()
     dev = torch.device("cuda", torch.cuda.current_device())
     q, r, noise = (features_matrix(f, dev) for f in (queries, refs, score_norm_refs))
+    qn, rn = score_normalize_device(q, r, noise, l2_normalize, replace_dim and score_norm_refs is not None, beta)
+    return split_rows(queries, qn, on_device), split_rows(refs, rn, on_device)
+
+
+def score_normalize_device(q, r, noise, l2_normalize: bool = True, replace_dim: bool = True, beta: float = 1.0):
+    """The arithmetic of score_normalize on float32 CUDA matrices [rows, d]; returns the widened (queries, refs)."""
+    torch = _lib.require_cuda()
+    dev = q.device
     drop = None
-    if score_norm_refs is not None and replace_dim:
+    if replace_dim:
         logger.info("Replacing dimension")
         drop = lowvar_dim(noise)                                       # lowest-variance dimension of the noise set
     if l2_normalize:
@@ -83,4 +91,4 @@ def score_normalize(queries: List[VideoFeature], refs: List[VideoFeature], score
         rc = _lib.load().vsc_fill_column(qn.data_ptr(), qn.shape[0], qn.shape[1], kept, nearest.data_ptr(), -float(beta),
                                          _stream(torch, dev))
     _lib.check(rc, "vsc_fill_column")
-    return split_rows(queries, qn, on_device), split_rows(refs, rn, on_device)
+    return qn, rn
