@@ -100,21 +100,42 @@ def build_graph(sims: np.ndarray, tn_max_step: int, tn_top_k: int, min_sim: floa
 
 
 def tn(sims: np.ndarray, tn_max_step: int = 10, tn_top_k: int = 5, max_path: int = 10,
-       min_sim: float = 0.2, min_length: int = 5, max_iou: float = 0.3,
+       min_sim: float = 0.2, min_length: int = 5, max_iou: float = 0.3, sink: str = "none",
        **_ignored) -> List[List[int]]:
     """Temporal-network alignment of one (Lq x Lr) similarity matrix.
 
     Returns up to ``max_path + 1`` boxes ``[q_min, r_min, q_max, r_max]``
-    (frame INDICES, inclusive).
+    (frame INDICES, inclusive).  ``sink``: see the module docstring.
     """
     graph, ref_of, top = build_graph(sims, tn_max_step, tn_top_k, min_sim)
+    n_real = sims.shape[0] * top
+    sink_node = None
+    if sink != "none" and n_real > 0:
+        def coords(node):
+            if node == 0:
+                return (-1, -1)
+            if node == n_real + 1:
+                return (sims.shape[0], sims.shape[1])
+            return ((node - 1) // top, int(ref_of[(node - 1) // top][(node - 1) % top]))
+        if sink == "dedicated":
+            sink_node = n_real + 1
+            graph.add_node(sink_node)
+        elif sink == "last_node":
+            sink_node = n_real
+        else:
+            raise ValueError(f"unknown sink variant {sink!r}")
+        jq, jr = coords(sink_node)
+        for i in range(0, sink_node):
+            iq, ir = coords(i)
+            if jq > iq and jr > ir and jq - iq <= tn_max_step and jr - ir <= tn_max_step:
+                graph.add_edge(i, sink_node, weight=0)
     boxes: List[List[int]] = []
     sweep = 0
     while sweep <= max_path:
         chain = dag_longest_path(graph)
         for u, v in zip(chain[:-1], chain[1:]):
             graph.add_edge(u, v, weight=0.0)  # spent: later sweeps gain nothing here
-        chain = [n for n in chain if n != 0]
+        chain = [n for n in chain if n != 0 and n != sink_node]
         if not chain:
             break
         qs = [(n - 1) // top for n in chain]
