@@ -43,6 +43,7 @@ struct Workspace {
     uint16_t *ref_of;   // [P][N] reference frame of node | kSimOk
     void *rec;          // [P][N] NodeRec: {predecessor mask, zeroed-edge mask, similarity, distance}
     uint16_t *gen;      // [P][N] Kahn generation
+    uint8_t *last_parent;  // [P][N] predecessor slot of the node's last parent in Kahn order (filled on demand by the DP)
     int rec_bytes, sim_off;  // record size and byte offset of the similarity inside it
     int32_t *skip;      // [P] 1 = handed to the general kernel
     int32_t *cursor;    // T1 tile counter

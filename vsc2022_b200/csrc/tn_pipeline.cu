@@ -470,6 +470,21 @@ __device__ int topo_compare(int a, int b, int g, int step, const NodeRec<MaskT> 
     }
 }
 
+// The exact order once the LAST PARENT of every ancestor is known (resolve pass in tn_dp_kernel): walk both last-parent
+// chains down the generations until they meet or reach generation 0.  Entries of nodes that are no ancestors of the
+// candidates may be stale; the clamp keeps their reads inside the pair.
+template <typename MaskT, int K, int GS>
+__device__ int topo_compare_exact(int a, int b, int g, int step, const uint8_t *last_parent) {
+    for (;;) {
+        if (a == b) return 0;
+        if (g <= 0) return a < b ? -1 : 1;
+        const int pa = max(0, parent_of_slot<MaskT, K, GS>(a, __ldcg(&last_parent[a]), step));
+        const int pb = max(0, parent_of_slot<MaskT, K, GS>(b, __ldcg(&last_parent[b]), step));
+        if (pa == pb) return a < b ? -1 : 1;
+        a = pa; b = pb; --g;
+    }
+}
+
 template <typename MaskT, int K, int GS>
 __global__ void __launch_bounds__(kT2Threads, 16 / kT2Warps) tn_dp_kernel(const Batch b, const Workspace w, const WorkList out) {
     // WARP-SYNCHRONOUS: the four octets of a warp run every loop together (trip count = the longest of the
@@ -609,7 +624,57 @@ __global__ void __launch_bounds__(kT2Threads, 16 / kT2Warps) tn_dp_kernel(const 
             const unsigned who = __ballot_sync(kFullMask, finalist) & om;
             end = __shfl_sync(kFullMask, bv, who ? __ffs(who) - 1 : lane);
         }
-        if (undecided && searching) { ambiguous = true; searching = false; }
+        // ---- ties topo_compare could not order (a node of generation >= 2 with several parents in the generation
+        // before): the octet computes the last parent of every possible ancestor of the tied nodes -- rows
+        // [first tied row - (step-1) * generation, last tied row], ascending, so that the order of a node's parents
+        // only needs entries that are already there -- and orders the tied nodes exactly.  Rare (about one pair in
+        // 10^4 on the bench workload); the other octets of the warp idle meanwhile.
+        if (__any_sync(kFullMask, undecided && searching)) {
+            const bool fix = undecided && searching;
+            uint8_t *last_parent = w.last_parent + nb;
+            int c_lo = INT_MAX, c_hi = -1;
+            if (fix) {
+                for (int q = sub; q < lq; q += 8)
+                    if (lbest[q] == mk) { c_lo = min(c_lo, q); c_hi = max(c_hi, q); }
+            }
+            c_lo = oct_min(c_lo, kFullMask);
+            c_hi = -oct_min(-c_hi, kFullMask);
+            int q = fix ? max(0, c_lo - (step - 1) * g_min) : 0;
+            const int q_end = fix ? c_hi : -1;
+            while (__any_sync(kFullMask, q <= q_end)) {
+                if (q <= q_end && ranked) {
+                    const int v = q * K + sub;
+                    const MaskT pm = load_rec(&rec[v]).pred;
+                    if (pm) {
+                        const int g = gen[v];
+                        int bu = -1, bsl = 0;
+                        for (MaskT m = pm; m; m &= m - 1) {
+                            const int sl = sizeof(MaskT) == 8 ? __ffsll((long long)m) - 1 : __ffs((int)m) - 1;
+                            const int u = parent_of_slot<MaskT, K, GS>(v, sl, step);
+                            if (gen[u] != g - 1) continue;
+                            if (bu < 0 || topo_compare_exact<MaskT, K, GS>(u, bu, g - 1, step, last_parent) > 0) { bu = u; bsl = sl; }
+                        }
+                        __stcg(&last_parent[v], (uint8_t)bsl);
+                    }
+                }
+                if (q <= q_end) ++q;
+                __syncwarp();   // the row's entries are visible to the octet before the next row reads them
+            }
+            int e2 = -1;
+            if (fix && sub == 0) {
+                for (int qq = c_lo; qq <= c_hi; ++qq) {
+                    if (lbest[qq] != mk) continue;
+                    for (uint32_t m = lrank[qq]; m; m &= m - 1) {
+                        const int v = qq * K + __ffs((int)m) - 1;
+                        if (gen[v] != g_min) continue;
+                        if (e2 < 0 || topo_compare_exact<MaskT, K, GS>(v, e2, g_min, step, last_parent) < 0) e2 = v;
+                    }
+                }
+            }
+            e2 = __shfl_sync(kFullMask, e2, oct * 8);
+            if (fix) { end = e2; undecided = false; }
+        }
+        if (undecided && searching) { ambiguous = true; searching = false; }   // unreachable; kept as a guard
 
         VSC_CLK(1);
         // ---- walk the chain back through the best-predecessor slots (shared memory only, one lane per octet)
@@ -862,13 +927,14 @@ int workspace_alloc(const Batch &b, Workspace *w, void **base_out, cudaStream_t 
     auto take = [&](size_t bytes) { size_t at = sz; sz += (bytes + 255) / 256 * 256; return at; };
     const size_t rec_bytes = wide ? sizeof(NodeRec<uint64_t>) : sizeof(NodeRec<uint32_t>);
     const size_t o_rec = take(P * N * rec_bytes);
-    const size_t o_ref = take(P * N * 2), o_gen = take(P * N * 2);
+    const size_t o_ref = take(P * N * 2), o_gen = take(P * N * 2), o_last = take(P * N);
     const size_t o_skip = take(P * 4), o_cursor = take(4);
     unsigned char *base = nullptr;
     VSC_CUDA_CHECK(cudaMallocAsync(&base, sz, stream));
     *base_out = base;
     w->rec = base + o_rec; w->rec_bytes = (int)rec_bytes; w->sim_off = wide ? 16 : 8;
     w->ref_of = reinterpret_cast<uint16_t *>(base + o_ref); w->gen = reinterpret_cast<uint16_t *>(base + o_gen);
+    w->last_parent = base + o_last;   // only written / read by the rare exact tie resolution: never initialised
     w->skip = reinterpret_cast<int32_t *>(base + o_skip); w->cursor = reinterpret_cast<int32_t *>(base + o_cursor);
     w->exact_count = nullptr; w->exact_list = nullptr;
     VSC_CUDA_CHECK(cudaMemsetAsync(w->gen, 0, P * N * 2, stream));
