@@ -42,7 +42,8 @@ BIAS = 0.5
 TN_CFG = dict(tn_max_step=5, tn_top_k=5, max_path=10, min_sim=0.2, min_length=4, max_iou=0.3)
 METRIC = "query-ref pairs localized/sec"
 UNIT = "pairs/s"
-CPU_SAMPLE = 96      # pairs per CPU step / cpu_baseline sample
+CPU_SAMPLE = 2048    # pairs of the cpu_baseline sample inside the GPU arm (about 10 s on 16 host cores)
+CPU_STEP_SAMPLE = 192  # pairs per step of `--impl reference` (about 1 s: 23 default steps stay within half a minute)
 
 
 def measured_peaks():
@@ -134,19 +135,20 @@ def run_reference(args, rank, world):
     wl = C4Workload(N_PAIRS, frames=FRAMES, dim=DIM)
     cores = os.cpu_count() or 1
     rates = []
+    sample = CPU_STEP_SAMPLE
     for step in range(args.warmup + args.steps):
-        lo = (step * CPU_SAMPLE) % (N_PAIRS - CPU_SAMPLE)
-        _, _, dt = cpu_localize(wl, lo, lo + CPU_SAMPLE, cores)
+        lo = (step * sample) % (N_PAIRS - sample)
+        _, _, dt = cpu_localize(wl, lo, lo + sample, cores)
         if step >= args.warmup:
-            rates.append(CPU_SAMPLE / dt)
+            rates.append(sample / dt)
     value = statistics.mean(rates)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * CPU_SAMPLE / value,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sample / value,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": _config(args.gpus, N_PAIRS // max(args.gpus, 1)),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{CPU_SAMPLE} consecutive pairs of the workload per step (different pairs each step): "
+                         "sample": f"{sample} consecutive pairs of the workload per step (different pairs each step): "
                                    f"numpy matmul + bias, VCSL TN restated on networkx (real VCSL/FAISS not installable "
                                    f"here) over multiprocessing.Pool({cores}), MaxSim scores"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -348,6 +350,90 @@ def stage_numbers(dev, peaks):
     return out
 
 
+def stage_numbers_sharded(dev, peaks, rank, world):
+    """The other two stages of the path on `world` GPUs (every rank calls this; device-timed, max over ranks):
+    configs[2] with the query frames sharded and FAISS's radius agreed across the ranks, configs[1] with the frames
+    sharded and the descriptors all-gathered over NCCL (what configs[4] does before its search)."""
+    import torch
+    import torch.distributed as dist
+    from vsc2022_b200.index import VideoIndex
+    from vsc2022_b200.score_normalization import score_normalize_device
+    out = {}
+
+    def timed(fn, n):
+        fn()
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([e0.elapsed_time(e1) / n], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- configs[2]: every rank generates the same 40k + 200k + 200k Gaussian descriptors (same seed)
+    g = torch.Generator(device=dev)
+    g.manual_seed(3)
+    nqv, nrv, frames, d, n_noise = 1250, 6250, 32, 512, 200_000
+    q = torch.randn((nqv * frames, d), generator=g, device=dev)
+    r = torch.randn((nrv * frames, d), generator=g, device=dev)
+    noise = torch.randn((n_noise, d), generator=g, device=dev)
+    for v in range(0, nqv, 20):
+        rv = (v * 7919) % nrv
+        q[v * frames + 8:v * frames + 24] = r[rv * frames + 4:rv * frames + 20] + 0.1 * torch.randn((16, d), generator=g, device=dev)
+    K = 1200 * nqv
+    lo, hi = rank * q.shape[0] // world, (rank + 1) * q.shape[0] // world
+    sn = {}
+
+    def normalise():   # the row maximum against the noise set is per query frame: each rank normalises its slice
+        mine, sn["r"] = score_normalize_device(q[lo:hi], r, noise, True, True, 1.2)
+        sn["q"] = torch.empty((q.shape[0], mine.shape[1]), dtype=mine.dtype, device=dev)
+        dist.all_gather_into_tensor(sn["q"], mine.contiguous())
+    ms_sn = timed(normalise, 2)
+    index = VideoIndex(d)
+    index.index.add_device(sn["r"], copy=False)
+    res = {}
+
+    def search():
+        res["out"] = index.global_topk_device(sn["q"], K, group=dist.group.WORLD)
+    ms_search = timed(search, 2)
+    flops = 2.0 * q.shape[0] * r.shape[0] * d
+    out["c3_descriptor_eval_sharded"] = {
+        "workload": "configs[2] on %d GPUs: query frames sharded (score normalisation per slice + all-gather of the normalised "
+                    "queries; search: every rank takes its slice of every FAISS batch, result counts all-reduced, radius by "
+                    "all-reduced radix histograms, survivors all-gathered); references and noise replicated" % world,
+        "score_normalize_ms": ms_sn, "search_ms": ms_search, "total_ms": ms_sn + ms_search,
+        "descriptors_per_s": (q.shape[0] + r.shape[0]) / (ms_sn + ms_search) * 1e3,
+        "pairs_returned": int(res["out"][0].numel()),
+        "search_tflops_algorithmic_whole_job": flops / ms_search / 1e9}
+    del q, r, noise, sn, index, res
+    torch.cuda.empty_cache()
+
+    # ---- configs[1]: 10 000 frames sharded over the ranks, descriptors all-gathered
+    from vsc2022_b200.sscd import SSCDResNet50, TorchReference
+    ref = TorchReference(seed=0, device=dev)
+    model = SSCDResNet50(ref.trunk, ref.head, device=dev)
+    n = 10_000
+    mine_n = n // world
+    g.manual_seed(100 + rank)
+    frames_u8 = torch.randint(0, 256, (mine_n, 288, 288, 3), generator=g, device=dev, dtype=torch.uint8)
+    everything = torch.empty((mine_n * world, 512), dtype=torch.float32, device=dev)
+
+    def infer():
+        desc = model.forward(frames_u8, batch=256)
+        dist.all_gather_into_tensor(everything, desc.float().contiguous())
+    ms = timed(infer, 2)
+    out["c2_sscd_sharded"] = {
+        "workload": "configs[1] on %d GPUs: %d synthetic 288x288 uint8 frames per rank (batch 256), descriptors all-gathered "
+                    "(NCCL) so that every rank holds all %d x 512" % (world, mine_n, mine_n * world),
+        "ms": ms, "frames_per_s_whole_job": mine_n * world / ms * 1e3,
+        "tflops_whole_job": mine_n * world * 13.513e9 / ms / 1e9}
+    return out
+
+
 def run_gpu(args, rank, local_rank, world):
     import ctypes
     import numpy as np
@@ -459,8 +545,8 @@ def run_gpu(args, rank, local_rank, world):
     same_boxes = bool((nb_ff == n_boxes).all()) and bool((bx_ff == boxes_v).all())
 
     # ---------------- e2e: the reference-facing call on host VideoFeatures, a fresh object per step
-    ts_q = np.tile(np.arange(f, dtype=np.float64), len(q_ids))
-    ts_r = np.tile(np.arange(f, dtype=np.float64), len(r_ids))
+    ts_q = np.tile(np.arange(f, dtype=np.float64), len(q_ids)).copy()     # frame timestamps of all videos, one array
+    ts_r = np.tile(np.arange(f, dtype=np.float64), len(r_ids)).copy()     # per side (what storage.load_features gives)
     qh, rh = q_host.numpy(), r_host.numpy()
     queries = [VideoFeature(video_id=f"Q{q:06d}", timestamps=ts_q[i * f:(i + 1) * f], feature=qh[i * f:(i + 1) * f])
                for i, q in enumerate(q_ids)]
@@ -482,7 +568,7 @@ def run_gpu(args, rank, local_rank, world):
     torch.cuda.synchronize(dev)
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     h2d = loc._dq.h2d_bytes + loc._dr.h2d_bytes + meta.nbytes
-    d2h = loc.model.last_result.buf.numel() * 4
+    d2h = loc.d2h_bytes
     matches_ok = len(matches) == int(n_boxes.sum())
 
     # ---------------- max over ranks
@@ -490,6 +576,11 @@ def run_gpu(args, rank, local_rank, world):
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     ms_max, e2e_ms_max, ms_ff_max, ms_ffb_max = times.tolist()
+    sharded = None
+    if world > 1 and not args.no_stages:
+        del sims, Qd, Rd, oq, orr, pairing, loc, matches, res, res_ff
+        torch.cuda.empty_cache()
+        sharded = stage_numbers_sharded(dev, measured_peaks()[0], rank, world)
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
@@ -540,6 +631,8 @@ def run_gpu(args, rank, local_rank, world):
             del sims, Qd, Rd, oq, orr, pairing
             torch.cuda.empty_cache()
             stages.update(stage_numbers(dev, peaks))
+        if sharded is not None:
+            stages.update(sharded)
         line = {
             "metric": METRIC, "value": N_PAIRS / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": warm, "ms_per_step": ms_max,

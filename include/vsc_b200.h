@@ -132,6 +132,13 @@ int vsc_tn_debug_counters(unsigned long long *out8);
 int vsc_prepare_operand_f16(const float *d_x, int64_t n, int32_t d, int64_t ld, int32_t kpad, int32_t side,
                             void *d_out_f16, float *d_inv_scale, int32_t *d_lo_flag, uint32_t *d_scratch,
                             vsc_stream_t stream);
+/* More rows of an operand whose scale is fixed: *d_scratch / *d_inv_scale as an earlier vsc_prepare_operand_f16 call on
+ * the same operand left them (no max|x| pass).  Lets a caller upload and convert a large descriptor collection piece by
+ * piece while earlier pieces are already being multiplied (localization.py:56-79 at configs[3] size).  Bit 1 of
+ * *d_lo_flag is set when a value does not fit the fp16 range under that scale: prepare the whole operand again. */
+int vsc_prepare_operand_f16_more(const float *d_x, int64_t n, int32_t d, int64_t ld, int32_t kpad, int32_t side,
+                                 void *d_out_f16, float *d_inv_scale, int32_t *d_lo_flag, uint32_t *d_scratch,
+                                 vsc_stream_t stream);
 int vsc_prepare_operand(const float *d_x, int64_t n, int32_t d, int64_t ld, int32_t kpad, int32_t mode,
                         void *d_out_bf16, int32_t *d_lo_flag, vsc_stream_t stream);
 int vsc_row_sqnorm(const float *d_x, int64_t n, int32_t d, int64_t ld, float *d_out, vsc_stream_t stream);

@@ -86,3 +86,86 @@ def test_ragged_batch_and_empty():
     flat = [(c.query_id, c.ref_id) + row[:5] for c, rows in zip(cands, want) for row in rows]
     assert [(m.query_id, m.ref_id, m.query_start, m.query_end, m.ref_start, m.ref_end, m.score) for m in got] == flat
     assert len(flat) >= 1
+
+
+@pytest.mark.parametrize("dtype,kind", [(np.float32, "grid"), (np.float16, "grid"), (np.float32, "gauss")])
+def test_chunked_localize_all_over_lazily_uploaded_base_arrays(dtype, kind):
+    """Large batches are aligned CHUNK pairs at a time while later descriptors are still going up (videos = row views
+    of one base array per side, what storage.load_features returns; --store_fp16 arrays included).  Same Match rows as
+    the oracle, as the unchunked call, and as a collection of loose arrays."""
+    from oracle import localize_numpy
+    from vsc2022_b200.index import VideoFeature
+    from vsc2022_b200.localization import VCSLLocalizationMaxSim
+    from vsc2022_b200.metrics import CandidatePair
+    rng = np.random.default_rng(9)
+    nq, nr, d = 24, 30, 64
+    lens_q, lens_r = rng.integers(20, 70, size=nq), rng.integers(20, 70, size=nr)
+    if kind == "grid":
+        draw = lambda n: (rng.integers(-16, 17, size=(n, d)) / 16.0).astype(dtype)
+    else:
+        draw = lambda n: unit(rng.normal(size=(n, d))).astype(dtype)
+    Q, R = draw(int(lens_q.sum())), draw(int(lens_r.sum()))
+    q_at, r_at = np.concatenate([[0], np.cumsum(lens_q)]), np.concatenate([[0], np.cumsum(lens_r)])
+    cand_ids = [(i, int(rng.integers(0, nr))) for i in range(nq) for _ in range(3)]
+    for i, j in cand_ids[::2]:          # planted copies
+        n = int(min(lens_q[i], lens_r[j], 30)) - 4
+        Q[q_at[i] + 2:q_at[i] + 2 + n] = R[r_at[j] + 1:r_at[j] + 1 + n]
+    tsq, tsr = np.arange(len(Q)) * 0.5, np.stack([np.arange(len(R)) * 1.0, np.arange(len(R)) * 1.0 + 0.75], axis=1)
+    views = lambda: ([VideoFeature(video_id=i, feature=Q[q_at[i]:q_at[i + 1]], timestamps=tsq[q_at[i]:q_at[i + 1]]) for i in range(nq)],
+                     [VideoFeature(video_id=100 + j, feature=R[r_at[j]:r_at[j + 1]], timestamps=tsr[r_at[j]:r_at[j + 1]]) for j in range(nr)])
+    cands = [CandidatePair(i, 100 + j, 1.0) for i, j in cand_ids]
+    cfg = dict(tn_max_step=5, min_length=4, similarity_bias=0.5)
+    rows = lambda ms: [(m.query_id, m.ref_id, m.query_start, m.query_end, m.ref_start, m.ref_end, float(m.score)) for m in ms]
+
+    qs, rs = views()
+    whole = VCSLLocalizationMaxSim(qs, rs, "TN", **cfg)
+    got_whole = whole.localize_all(cands)
+    assert whole._dq.lazy is not None and whole._dr.lazy is not None
+    assert whole._dr.h2d_bytes <= R.nbytes and whole._dq.h2d_bytes <= Q.nbytes
+
+    qs, rs = views()
+    chunked = VCSLLocalizationMaxSim(qs, rs, "TN", **cfg)
+    chunked.CHUNK = 8                    # 72 pairs -> 9 chunks; blocks of 16 rows -> many partial uploads
+    chunked._stores()[0].BLOCK = chunked._stores()[1].BLOCK = 16
+    got_chunked = chunked.localize_all(cands)
+    assert rows(got_chunked) == rows(got_whole)
+    assert chunked._dq.h2d_bytes <= Q.nbytes and chunked._dr.h2d_bytes <= R.nbytes   # nothing crosses PCIe twice
+    assert rows(chunked.localize_all(cands[5:40])) == rows(whole.localize_all(cands[5:40]))   # everything resident now
+
+    loose_q = [VideoFeature(video_id=v.video_id, feature=np.array(v.feature), timestamps=np.array(v.timestamps)) for v in qs]
+    loose_r = [VideoFeature(video_id=v.video_id, feature=np.array(v.feature), timestamps=np.array(v.timestamps)) for v in rs]
+    assert rows(VCSLLocalizationMaxSim(loose_q, loose_r, "TN", **cfg).localize_all(cands)) == rows(got_whole)
+
+    if kind == "grid":                   # every product exact: the oracle's rows, bit for bit
+        pairs = [(Q[q_at[i]:q_at[i + 1]].astype(np.float32), tsq[q_at[i]:q_at[i + 1]], R[r_at[j]:r_at[j + 1]].astype(np.float32),
+                  tsr[r_at[j]:r_at[j + 1]], 1.0) for i, j in cand_ids]
+        want = localize_numpy.localize_all(pairs, 0.5, "max_sim", tn_max_step=5, min_length=4)
+        flat = [(i, 100 + j) + tuple(row[:4]) + (float(row[4]),) for (i, j), rws in zip(cand_ids, want) for row in rws]
+        assert rows(got_whole) == flat
+    assert len(got_whole) >= 10
+
+
+def test_growing_operand_scale_overflow_starts_over():
+    """A later chunk with values far outside the first chunk's range (fp16 overflow under its scale): detected, the
+    collection is prepared again as a whole and the rows equal the unchunked result."""
+    from vsc2022_b200.index import VideoFeature
+    from vsc2022_b200.localization import VCSLLocalizationMaxSim
+    from vsc2022_b200.metrics import CandidatePair
+    rng = np.random.default_rng(10)
+    n, f, d = 12, 40, 32
+    Q = (rng.integers(-16, 17, size=(n * f, d)) / 16.0).astype(np.float32)
+    R = (rng.integers(-16, 17, size=(n * f, d)) / 16.0).astype(np.float32)
+    Q[6 * f:] *= 64.0                    # the second half of the queries is 64x larger (first-chunk scale has 16x headroom)
+    for i in range(n):
+        R[i * f + 3:i * f + 33] = Q[i * f + 5:i * f + 35] / (64.0 if i >= 6 else 1.0)
+    ts = np.arange(n * f) * 1.0
+    mk = lambda X, base: [VideoFeature(video_id=base + i, feature=X[i * f:(i + 1) * f], timestamps=ts[i * f:(i + 1) * f]) for i in range(n)]
+    cands = [CandidatePair(i, 100 + i, 1.0) for i in range(n)]
+    cfg = dict(tn_max_step=5, min_length=4, similarity_bias=0.5)
+    want = VCSLLocalizationMaxSim(mk(Q, 0), mk(R, 100), "TN", **cfg).localize_all(cands)
+    loc = VCSLLocalizationMaxSim(mk(Q, 0), mk(R, 100), "TN", **cfg)
+    loc.CHUNK = 3
+    loc._stores()[0].BLOCK = loc._stores()[1].BLOCK = 8
+    got = loc.localize_all(cands)
+    assert got == want and len(want) >= n
+    assert loc._dq.lazy is None          # settled after the overflow

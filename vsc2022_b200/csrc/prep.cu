@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(256) prepare_f16_kernel(const float *__restric
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t row = idx / quads;
     const int k = (int)(idx - row * quads) * 4;
-    bool any_lo = false;
+    bool any_lo = false, too_big = false;
     if (row < n) {
         float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         const float *src = x + row * ld + k;
@@ -111,6 +111,7 @@ __global__ void __launch_bounds__(256) prepare_f16_kernel(const float *__restric
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float xs = v[j] * s;                                   // exact: power of two
+            too_big = too_big || (fabsf(xs) > 65504.0f && fabsf(v[j]) < INFINITY);   // only with a scale from earlier rows
             hi[j] = __float2half_rn(xs);
             const float r = xs - __half2float(hi[j]);                    // exact in fp32
             lo[j] = __float2half_rn(r * 2048.0f);
@@ -128,6 +129,7 @@ __global__ void __launch_bounds__(256) prepare_f16_kernel(const float *__restric
         *reinterpret_cast<uint2 *>(o + 2 * kpad) = hi2;
     }
     if (lo_flag && __any_sync(vsc::kFullMask, any_lo) && (threadIdx.x & 31) == 0) atomicOr(lo_flag, 1);
+    if (lo_flag && __any_sync(vsc::kFullMask, too_big) && (threadIdx.x & 31) == 0) atomicOr(lo_flag, 2);
 }
 
 // squared L2 norm per row (float32, sequential-in-k per warp lane then warp reduce): for the L2 metric
@@ -175,27 +177,29 @@ extern "C" int vsc_row_sqnorm(const float *d_x, int64_t n, int32_t d, int64_t ld
     return VSC_OK;
 }
 
-extern "C" int vsc_prepare_operand_f16(const float *d_x, int64_t n, int32_t d, int64_t ld, int32_t kpad, int32_t side,
-                                       void *d_out_f16, float *d_inv_scale, int32_t *d_lo_flag, uint32_t *d_scratch,
-                                       vsc_stream_t stream_) {
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+static int prepare_f16(const float *d_x, int64_t n, int32_t d, int64_t ld, int32_t kpad, int32_t side,
+                       void *d_out_f16, float *d_inv_scale, int32_t *d_lo_flag, uint32_t *d_scratch, bool keep_scale,
+                       cudaStream_t stream) {
     if (kpad < d || kpad % 64 != 0 || side < 0 || side > 1 || !d_inv_scale || !d_scratch) {
         vsc::set_error("vsc_prepare_operand_f16: kpad=%d must be a multiple of 64 and >= d=%d; side in 0..1", kpad, d);
         return VSC_ERR_INVALID;
     }
-    VSC_CUDA_CHECK(cudaMemsetAsync(d_scratch, 0, sizeof(uint32_t), stream));
+    if (!keep_scale) VSC_CUDA_CHECK(cudaMemsetAsync(d_scratch, 0, sizeof(uint32_t), stream));
     if (n <= 0) {   // the scale of an empty operand is 1
+        if (keep_scale) return VSC_OK;
         const float one = 1.0f;
         VSC_CUDA_CHECK(cudaMemcpyAsync(d_inv_scale, &one, sizeof(float), cudaMemcpyHostToDevice, stream));
         return VSC_OK;
     }
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int64_t elems = n * d;
-    const int64_t want = (elems + 255) / 256;
-    absmax_kernel<<<(unsigned)(want < sms * 16 ? want : sms * 16), 256, 0, stream>>>(d_x, n, d, ld, d_scratch);
-    vsc::count_launch();
+    if (!keep_scale) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int64_t elems = n * d;
+        const int64_t want = (elems + 255) / 256;
+        absmax_kernel<<<(unsigned)(want < sms * 16 ? want : sms * 16), 256, 0, stream>>>(d_x, n, d, ld, d_scratch);
+        vsc::count_launch();
+    }
     const int64_t total = n * (kpad / 4);
     const bool vec = (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(d_x) & 15u) == 0;
     if (vec)
@@ -207,4 +211,21 @@ extern "C" int vsc_prepare_operand_f16(const float *d_x, int64_t n, int32_t d, i
     VSC_CUDA_CHECK(cudaGetLastError());
     vsc::count_launch();
     return VSC_OK;
+}
+
+extern "C" int vsc_prepare_operand_f16(const float *d_x, int64_t n, int32_t d, int64_t ld, int32_t kpad, int32_t side,
+                                       void *d_out_f16, float *d_inv_scale, int32_t *d_lo_flag, uint32_t *d_scratch,
+                                       vsc_stream_t stream_) {
+    return prepare_f16(d_x, n, d, ld, kpad, side, d_out_f16, d_inv_scale, d_lo_flag, d_scratch, false,
+                       static_cast<cudaStream_t>(stream_));
+}
+
+// More rows of an operand whose scale is already fixed (*d_scratch as an earlier vsc_prepare_operand_f16 call on the
+// same operand left it): no max|x| pass.  Bit 1 of *d_lo_flag is set when a value does not fit the fp16 range under
+// that scale (the caller then prepares the operand again as a whole).
+extern "C" int vsc_prepare_operand_f16_more(const float *d_x, int64_t n, int32_t d, int64_t ld, int32_t kpad,
+                                            int32_t side, void *d_out_f16, float *d_inv_scale, int32_t *d_lo_flag,
+                                            uint32_t *d_scratch, vsc_stream_t stream_) {
+    return prepare_f16(d_x, n, d, ld, kpad, side, d_out_f16, d_inv_scale, d_lo_flag, d_scratch, true,
+                       static_cast<cudaStream_t>(stream_));
 }

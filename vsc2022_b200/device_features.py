@@ -22,10 +22,11 @@ def root_of(arr: np.ndarray, cache: dict = None):
     """(root array, first row of `arr` inside it) if `arr` is a block of whole rows of a base array (1-D or 2-D,
     C-contiguous), else None.  `cache` memoises the per-root facts (this runs once per video of a collection)."""
     root = arr.base
-    if not isinstance(root, np.ndarray):
+    if root.__class__ is not np.ndarray and not isinstance(root, np.ndarray):
         return None
-    while isinstance(root.base, np.ndarray):
-        root = root.base
+    base = root.base
+    while base is not None and isinstance(base, np.ndarray):
+        root, base = base, base.base
     info = cache.get(id(root)) if cache is not None else None
     if info is None:
         ok = root.ndim in (1, 2) and root.flags.c_contiguous and root.shape[0] > 0

@@ -48,13 +48,59 @@ class Operand:
         return sub
 
 
+class GrowingOperand(Operand):
+    """An operand converted piece by piece (vsc_prepare_operand_f16 for the first piece, which fixes the power-of-two
+    scale, vsc_prepare_operand_f16_more for the rest): the panel covers `rows` rows from the start, rows that were never
+    prepared hold garbage and must not be multiplied."""
+
+    def __init__(self, rows: int, d: int, side: int, device):
+        torch = _lib.require_cuda()
+        kpad = pad_k(d)
+        self.meta = torch.zeros((4,), dtype=torch.int32, device=device)
+        panel = torch.empty((max(rows, 1), 3 * kpad), dtype=torch.float16, device=device)
+        super().__init__(panel, rows, kpad, self.meta[0:1].view(torch.float32), self.meta[1:2], side)
+        self.d, self.started = d, False
+
+    def prepare_rows(self, x, r0: int, n: Optional[int] = None):
+        """Convert rows [r0, r0 + n) of the collection (asynchronous).  x: the float32 CUDA matrix [rows, d] the panel
+        mirrors (n given: only its address and row stride are used, no tensor slicing per call), or just the rows to
+        convert."""
+        torch = _lib.require_cuda()
+        if n is None:
+            n, src = x.shape[0], x.data_ptr()
+        else:
+            src = x.data_ptr() + r0 * x.stride(0) * 4
+        assert x.is_cuda and x.dtype == torch.float32 and x.shape[1] == self.d and 0 <= r0 and r0 + n <= max(self.rows, 1)
+        if n == 0:
+            return
+        lib = _lib.load()
+        fn = lib.vsc_prepare_operand_f16_more if self.started else lib.vsc_prepare_operand_f16
+        base = self.meta.data_ptr()
+        with torch.cuda.device(x.device):
+            rc = fn(src, n, self.d, x.stride(0), self.kpad, self.side, self.panel.data_ptr() + r0 * self.ld * 2,
+                    base, base + 4, base + 8, _stream_ptr(torch, x.device))
+        _lib.check(rc, "vsc_prepare_operand_f16(_more)")
+        self.started = True
+
+    def needs_split(self) -> bool:
+        if not self._needs_split:          # the flag only ever goes up: once set, no more read-backs
+            self._needs_split = bool(int(self.lo_flag.item()) & 1)
+        return self._needs_split
+
+    def overflowed(self) -> bool:
+        """True when a later piece held a value outside the fp16 range under the first piece's scale (one read back)."""
+        return bool(int(self.lo_flag.item()) & 2)
+
+
 class Pairing:
     """How two operands multiply: inner dimension, the format struct of the C ABI (kept alive with its scale)."""
 
-    def __init__(self, a: Operand, b: Operand, precise: bool = True):
+    def __init__(self, a: Operand, b: Operand, precise: bool = True, split: Optional[bool] = None):
+        """`split`: None = decide from the operands' flags (a 4-byte read back the first time: waits for their
+        preparation); True = all three partial products without asking (always exact, 3x the work when one would do)."""
         assert a.kpad == b.kpad, "operands of different dimensions"
         assert a.side == SIDE_A and b.side == SIDE_B, "first operand must be prepared as SIDE_A, second as SIDE_B"
-        self.split = precise and (a.needs_split() or b.needs_split())
+        self.split = (precise and (a.needs_split() or b.needs_split())) if split is None else bool(split)
         self.k = 3 * a.kpad if self.split else a.kpad
         key = id(b.inv_scale)
         if key not in a._scales:

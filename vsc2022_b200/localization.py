@@ -14,7 +14,9 @@ Same classes and signatures as the reference.  `VCSLLocalization.localize_all` i
   operations (no per-pair Python work for pairs without a match).
 """
 import abc
+import collections
 import gc
+import time
 from typing import Dict, List
 
 import numpy as np
@@ -54,6 +56,8 @@ class _DeviceVideos:
     shared base array are uploaded with that array in one copy; anything else is concatenated on the host first."""
 
     MAX_WASTE = 8   # upload a shared base whole unless it is this many times larger than what the batch needs
+    BLOCK = 512     # rows per residency block of a lazily mirrored base array
+    BRIDGE = 4      # blocks nobody asked for that a copy may take along to join two runs
 
     def __init__(self, videos: Dict[object, VideoFeature], device):
         self.videos, self.device = videos, device
@@ -68,6 +72,12 @@ class _DeviceVideos:
         self._ts_cat = None
         self._root_cache = {}       # id(root) -> facts about that base array (keeps the array alive: ids stay unique)
         self.h2d_bytes = 0
+        # A collection that is row views of ONE base array (storage.load_features) is mirrored lazily: the device matrix
+        # is allocated whole, rows go up in blocks when a batch first needs them, and the GEMM panels grow with them --
+        # so a large localize_all can multiply its first pairs while the descriptors of the later ones are still on
+        # their way.  {root, dev, first, resident (per block), fresh [(row0, row1) uploaded, not yet prepared]}
+        self.lazy = None
+        self._operand = None        # (key, gemm.Operand)
 
     def _upload(self, host):
         """Append rows: a host array (copied up) or a device matrix (adopted as it is)."""
@@ -91,6 +101,110 @@ class _DeviceVideos:
         self.version += 1
         return first, len(self.segments) - 1
 
+    def _mirror(self, root):
+        """Device matrix for all rows of `root`, nothing copied yet."""
+        torch = _lib.require_cuda()
+        d = torch.empty(root.shape, dtype=torch.float32, device=self.device)
+        first = self.rows
+        self.segments.append(d)
+        self.rows += d.shape[0]
+        self._ts[0].append(np.zeros(d.shape[0]))
+        self._ts[1].append(np.zeros(d.shape[0]))
+        self._cat = self._ts_cat = None
+        self.version += 1
+        blocks = (root.shape[0] + self.BLOCK - 1) // self.BLOCK
+        # the blocks go up on a stream of their own, so that the copy of the next batch's rows overlaps the kernels of
+        # this one; `events` = copies the compute stream has to wait for before it converts the `fresh` rows
+        copier = torch.cuda.Stream(device=self.device)
+        copier.wait_stream(torch.cuda.current_stream(self.device))   # the block may have been another tensor's a moment ago
+        self.lazy = {"root": root, "dev": d, "first": first, "resident": np.zeros(blocks, dtype=bool), "fresh": [],
+                     "copier": copier, "events": []}
+        return first, len(self.segments) - 1
+
+    def _touch(self, lo: np.ndarray, hi: np.ndarray):
+        """Rows [lo_i, hi_i) of the lazily mirrored base array must be on the device: copy the missing blocks
+        (consecutive blocks in one asynchronous copy)."""
+        torch = _lib.require_cuda()
+        lz = self.lazy
+        root, dev, resident = lz["root"], lz["dev"], lz["resident"]
+        keep = hi > lo
+        lo, hi = lo[keep], hi[keep]
+        if len(lo) == 0:
+            return
+        edge = np.zeros(len(resident) + 1, dtype=np.int64)
+        np.add.at(edge, lo // self.BLOCK, 1)
+        np.add.at(edge, (hi - 1) // self.BLOCK + 1, -1)
+        todo = (np.cumsum(edge[:-1]) > 0) & ~resident
+        idx = np.flatnonzero(todo)
+        if len(idx) == 0:
+            return
+        # few large copies instead of many small ones: a gap of up to BRIDGE blocks between two needed blocks goes along
+        # when none of it is resident yet (every row still crosses PCIe at most once)
+        gaps = np.flatnonzero((np.diff(idx) > 1) & (np.diff(idx) <= self.BRIDGE + 1))
+        for g in gaps:
+            if not resident[idx[g] + 1:idx[g + 1]].any():
+                todo[idx[g] + 1:idx[g + 1]] = True
+        idx = np.flatnonzero(todo)
+        with torch.cuda.stream(lz["copier"]):
+            for run in np.split(idx, np.flatnonzero(np.diff(idx) > 1) + 1):
+                r0, r1 = int(run[0]) * self.BLOCK, min((int(run[-1]) + 1) * self.BLOCK, root.shape[0])
+                src = torch.from_numpy(root[r0:r1])
+                self.h2d_bytes += src.numel() * src.element_size()
+                if src.dtype == torch.float32:
+                    dev[r0:r1].copy_(src, non_blocking=True)
+                else:                       # --store_fp16 descriptors: half the bytes over PCIe, widened on the device
+                    dev[r0:r1].copy_(src.to(self.device, non_blocking=True))
+                lz["fresh"].append((r0, r1))
+            done = torch.cuda.Event()
+            done.record(lz["copier"])
+        lz["events"].append(done)
+        resident |= todo
+
+    def _settle(self):
+        """Another segment is about to join: the lazily mirrored array goes up whole and becomes an ordinary segment."""
+        if self.lazy is not None:
+            self._touch(np.array([0]), np.array([self.lazy["root"].shape[0]]))
+            self._await_copies()
+            self.lazy = None
+            self._operand = None
+
+    def __del__(self):
+        # block copies nobody waited for (a batch that was prepared but never multiplied) must finish before the
+        # allocator hands the mirror's memory to a tensor of the compute stream
+        try:
+            if self.lazy is not None and self.lazy["events"]:
+                self._await_copies()
+        except Exception:
+            pass
+
+    def _await_copies(self):
+        """The compute stream waits for the block copies issued so far."""
+        torch = _lib.require_cuda()
+        stream = torch.cuda.current_stream(self.device)
+        for ev in self.lazy["events"]:
+            stream.wait_event(ev)
+        self.lazy["events"] = []
+
+    def dim(self) -> int:
+        return self.segments[0].shape[1]
+
+    def operand(self, side: int):
+        """The fp16 split panels of the collection (gemm.Operand); with a lazy mirror only resident rows are valid."""
+        if self.lazy is not None:
+            lz = self.lazy
+            if self._operand is None or self._operand[0] != ("lazy", id(lz)):
+                self._operand = (("lazy", id(lz)), gemm.GrowingOperand(self.rows, lz["dev"].shape[1], side, self.device))
+            op = self._operand[1]
+            self._await_copies()
+            for r0, r1 in lz["fresh"]:          # (a lazy mirror is the store's only segment: first == 0)
+                op.prepare_rows(lz["dev"], r0, r1 - r0)
+            lz["fresh"] = []
+            return op
+        key = ("full", self.version)
+        if self._operand is None or self._operand[0] != key:
+            self._operand = (key, gemm.prepare(self.matrix(), side))
+        return self._operand[1]
+
     def _stamp(self, seg: int, lo: int, ts: np.ndarray):
         n = ts.shape[0]
         if ts.ndim == 1:          # VideoMetadata.get_timestamps: (t, t) for instants, (t[0], t[1]) for intervals
@@ -109,21 +223,75 @@ class _DeviceVideos:
     def prefetch(self, vid):
         """Start the upload of the base array `vid`'s descriptors are a view of (asynchronous from pinned memory), so
         that the copy runs while the host walks the rest of the collection."""
-        if vid in self.start or is_device_tensor(self.videos[vid].feature):
-            return
+        if vid in self.start or is_device_tensor(self.videos[vid].feature) or not self.segments:
+            return      # (an empty store mirrors its first base array lazily: ensure() decides)
         where = _root_of(self.videos[vid].feature, self._root_cache)
         if where is not None and id(where[0]) not in self._roots and where[0].shape[0] <= self.MAX_WASTE * (1 << 20):
             first, seg = self._upload(where[0])
             self._roots[id(where[0])] = (where[0], first, seg)
 
+    def _ensure_views_of_one_array(self, new) -> bool:
+        """Fast path of ensure(): every new video's descriptors are whole rows of ONE base array that this store mirrors
+        lazily (or is empty and about to), timestamps likewise rows of one array laid out the same way -- what
+        storage.load_features returns.  One tight loop per video; nothing is changed unless everything fits."""
+        videos, nd = self.videos, np.ndarray
+        v0 = videos[new[0]]
+        root, troot = getattr(v0.feature, "base", None), getattr(v0.timestamps, "base", None)
+        if root.__class__ is not nd or troot.__class__ is not nd or isinstance(root.base, nd) or isinstance(troot.base, nd):
+            return False
+        if (root.ndim != 2 or troot.ndim not in (1, 2) or troot.shape[0] != root.shape[0] or troot.dtype != np.float64
+                or root.dtype not in (np.float32, np.float16) or not root.flags.c_contiguous or not troot.flags.c_contiguous):
+            return False
+        key = id(root)
+        known = self._roots.get(key)
+        if known is None and self.segments:
+            return False
+        if known is not None and (self.lazy is None or self.lazy["root"] is not root or self._roots.get(("ts", key)) is not troot):
+            return False
+        rptr, rstride, tptr, tstride = root.ctypes.data, root.strides[0], troot.ctypes.data, troot.strides[0]
+        fshape, fstrides, tshape, tstrides = root.shape[1:], root.strides, troot.shape[1:], troot.strides
+        rows, lens = [], []
+        for i in new:
+            v = videos[i]
+            f, t = v.feature, v.timestamps
+            if f.__class__ is not nd or t.__class__ is not nd or f.base is not root or t.base is not troot:
+                return False
+            n = f.shape[0]
+            if (n == 0 or f.shape[1:] != fshape or f.strides != fstrides or t.shape[0] != n or t.shape[1:] != tshape
+                    or t.strides != tstrides):
+                return False
+            row, rem = divmod(f.__array_interface__["data"][0] - rptr, rstride)
+            if rem or t.__array_interface__["data"][0] - tptr != row * tstride:
+                return False
+            rows.append(row)
+            lens.append(n)
+        rows, lens = np.array(rows, dtype=np.int64), np.array(lens, dtype=np.int64)
+        if known is None:
+            if root.shape[0] > self.MAX_WASTE * max(int(lens.sum()), 1) and root.nbytes > (1 << 28):
+                return False
+            first, seg = self._mirror(root)
+            self._roots[key] = (root, first, seg)
+            self._ts[0][seg], self._ts[1][seg] = (troot, troot) if troot.ndim == 1 else (troot[:, 0], troot[:, 1])
+            self._roots[("ts", key)] = troot
+        else:
+            first = known[1]
+        self._touch(rows, rows + lens)
+        self.start.update(zip(new, (rows + first).tolist()))
+        self.length.update(zip(new, lens.tolist()))
+        self._ts_cat = None
+        return True
+
     def ensure(self, ids):
         new = [i for i in dict.fromkeys(ids) if i not in self.start]
-        if not new:
+        if not new or self._ensure_views_of_one_array(new):
             return
         loose = []
         by_root = {}
-        on_device = [i for i in new if is_device_tensor(self.videos[i].feature)]
+        videos, nd = self.videos, np.ndarray
+        on_device = [] if all(videos[i].feature.__class__ is nd for i in new) else \
+            [i for i in new if is_device_tensor(videos[i].feature)]
         if on_device:   # descriptors that never left the GPU (score_normalize(on_device=True)): no copy over PCIe
+            self._settle()
             first, seg = self._upload(features_matrix([self.videos[i] for i in on_device], self.device))
             at = first
             for i in on_device:
@@ -139,15 +307,24 @@ class _DeviceVideos:
                 loose.append(i)
             else:
                 by_root.setdefault(id(where[0]), (where[0], []))[1].append((i, where[1]))
+        lazy_ok = not self.segments and len(by_root) == 1 and not loose
         for key, (root, members) in by_root.items():
             if key not in self._roots:
                 need = sum(len(self.videos[i]) for i, _ in members)
                 if root.shape[0] > self.MAX_WASTE * max(need, 1) and root.nbytes > (1 << 28):
                     loose.extend(i for i, _ in members)
                     continue
-                first, seg = self._upload(root)
+                if lazy_ok and root.ndim == 2 and root.dtype in (np.float32, np.float16):
+                    first, seg = self._mirror(root)
+                else:
+                    self._settle()
+                    first, seg = self._upload(root)
                 self._roots[key] = (root, first, seg)
             _, first, seg = self._roots[key]
+            if self.lazy is not None and self.lazy["root"] is root:
+                rows = np.fromiter((row for _, row in members), dtype=np.int64, count=len(members))
+                lens = np.fromiter((len(self.videos[i]) for i, _ in members), dtype=np.int64, count=len(members))
+                self._touch(rows, rows + lens)
             # timestamps: when they are row views of one array laid out like the descriptors (storage.load_features),
             # one bulk copy; otherwise video by video
             ts_where = [_root_of(self.videos[i].timestamps, self._root_cache) for i, _ in members]
@@ -156,7 +333,11 @@ class _DeviceVideos:
                 w is not None and w[0] is ts_root and w[1] == row for w, (_, row) in zip(ts_where, members))
             if bulk:
                 if ("ts", key) not in self._roots:
-                    self._stamp(seg, 0, ts_root)
+                    if ts_root.dtype == np.float64 and self._ts[0][seg].shape[0] == ts_root.shape[0]:
+                        # the segment is this base array: its timestamp array serves as it is (read only), no copy
+                        self._ts[0][seg], self._ts[1][seg] = (ts_root, ts_root) if ts_root.ndim == 1 else (ts_root[:, 0], ts_root[:, 1])
+                    else:
+                        self._stamp(seg, 0, ts_root)
                     self._roots[("ts", key)] = ts_root
                 self.start.update((i, first + row) for i, row in members)
                 self.length.update((i, len(self.videos[i])) for i, _ in members)
@@ -165,6 +346,7 @@ class _DeviceVideos:
                 for i, row in members:
                     self._register(i, first + row, seg, first)
         if loose:
+            self._settle()
             host = np.concatenate([np.asarray(self.videos[i].feature, dtype=np.float32) for i in loose])
             first, seg = self._upload(host)
             at = first
@@ -183,7 +365,8 @@ class _DeviceVideos:
 
     def timestamps(self):
         if self._ts_cat is None:
-            self._ts_cat = (np.concatenate(self._ts[0]), np.concatenate(self._ts[1]))
+            one = len(self._ts[0]) == 1     # a single segment: its arrays as they are, no copy per batch
+            self._ts_cat = (self._ts[0][0], self._ts[1][0]) if one else (np.concatenate(self._ts[0]), np.concatenate(self._ts[1]))
         return self._ts_cat
 
 
@@ -198,7 +381,9 @@ class VCSLLocalization(LocalizationWithMetadata):
         self.model = build_vta_model(model_type, **kwargs)
         self.similarity_bias = similarity_bias
         self._dq = self._dr = None
-        self._panels = None
+        self.d2h_bytes = 0
+        self._no_sync = False
+        self.profile = None          # set to a dict to collect the host-side phase times of localize_all (tools/probe_e2e.py)
 
     def similarity(self, candidate: CandidatePair):
         """Add an optional similarity bias (some aligners do not tolerate negative values well)."""
@@ -212,35 +397,76 @@ class VCSLLocalization(LocalizationWithMetadata):
         return self._dq, self._dr
 
     def _operands(self):
-        """bf16 panels of all uploaded query / reference rows; the split is chosen for both sides together."""
+        """fp16 split panels of the uploaded query / reference rows (prepared piece by piece while a lazily mirrored
+        collection is still going up); the split is chosen for both sides together."""
         dq, dr = self._stores()
-        key = (dq.version, dr.version)
-        if self._panels is None or self._panels[0] != key:
-            Q, R = dq.matrix(), dr.matrix()
-            if Q.shape[1] != R.shape[1]:
-                raise ValueError(f"query descriptors have {Q.shape[1]} dimensions, reference descriptors {R.shape[1]}")
-            oq, orr = gemm.prepare_pair(Q, R)
-            self._panels = (key, oq, orr, gemm.Pairing(oq, orr, precise=True))
-        return self._panels[1], self._panels[2], self._panels[3]
+        if dq.dim() != dr.dim():
+            raise ValueError(f"query descriptors have {dq.dim()} dimensions, reference descriptors {dr.dim()}")
+        oq, orr = dq.operand(gemm.SIDE_A), dr.operand(gemm.SIDE_B)
+        return oq, orr, gemm.Pairing(oq, orr, precise=True, split=True if self._no_sync else None)
 
     def _similarity_use(self):
         known = (VCSLLocalization.score, VCSLLocalizationMaxSim.score, VCSLLocalizationCandidateScore.score)
         return self.similarity_use if type(self).score in known else "full"
 
+    # Batches of at least 2 * CHUNK pairs are aligned CHUNK pairs at a time: the descriptors of chunk c+1 cross PCIe and
+    # its pairs are multiplied while the host turns the boxes of chunk c into Match rows.
+    CHUNK = 1024
+
     def localize_all(self, candidates: List[CandidatePair]) -> List[Match]:
         if not candidates:
             return []
-        torch = _lib.require_cuda()
-        from .vta import tn_batch_from_features
+        self.d2h_bytes = 0
+        n = len(candidates)
+        if self.profile is not None:
+            self.profile["t_start"] = time.perf_counter()
+        self._no_sync = n >= 2 * self.CHUNK   # chunked: all three partial products without waiting for the operands' flags
+        if n < 2 * self.CHUNK:
+            matches = self._rows(self._launch(candidates))
+        else:
+            # Launch chunks ahead while the oldest outstanding one is still on the device, build its Match rows as soon
+            # as its boxes have landed: the host never idles while descriptors are crossing PCIe.
+            chunks = [candidates[at:at + self.CHUNK] for at in range(0, n, self.CHUNK)]
+            depth = 2 if self._similarity_use() == "full" else len(chunks)    # whole matrices per job: keep few alive
+            matches, pending, c = [], collections.deque(), 0
+            while c < len(chunks) or pending:
+                if pending and (c >= len(chunks) or len(pending) >= depth or pending[0][5].ready()):
+                    matches.extend(self._rows(pending.popleft()))
+                else:
+                    pending.append(self._launch(chunks[c]))
+                    c += 1
+        for store in self._stores():   # a later piece outside the fp16 range of the first piece's scale: start over, whole
+            op = store._operand[1] if store._operand is not None else None
+            if isinstance(op, gemm.GrowingOperand) and op.overflowed():
+                for st in self._stores():
+                    st._settle()
+                return self.localize_all(candidates)
+        return matches
+
+    def _ensure(self, candidates: List[CandidatePair]):
         dq, dr = self._stores()
-        dev = dq.device
         q_ids = [c.query_id for c in candidates]
         r_ids = [c.ref_id for c in candidates]
         dq.prefetch(q_ids[0])
         dr.prefetch(r_ids[0])
         dq.ensure(q_ids)
         dr.ensure(r_ids)
+        return q_ids, r_ids
+
+    def _launch(self, candidates: List[CandidatePair]):
+        """Upload what is missing, enqueue the per-pair GEMM + temporal network and the copy of the result."""
+        torch = _lib.require_cuda()
+        from .vta import tn_batch_from_features
+        prof = self.profile
+        t0 = time.perf_counter() if prof is not None else 0.0
+        dq, dr = self._stores()
+        dev = dq.device
+        q_ids, r_ids = self._ensure(candidates)
+        if prof is not None:
+            t1 = time.perf_counter(); prof["ensure"] = prof.get("ensure", 0.0) + t1 - t0; t0 = t1
         oq, orr, pairing = self._operands()
+        if prof is not None:
+            t1 = time.perf_counter(); prof["operands"] = prof.get("operands", 0.0) + t1 - t0; t0 = t1
         n = len(candidates)
         meta = np.empty((4, n), dtype=np.int32)      # q_start, lq, r_start, lr
         meta[0] = [dq.start[i] for i in q_ids]
@@ -263,9 +489,23 @@ class VCSLLocalization(LocalizationWithMetadata):
             want_maxsim=(use == "boxmax"), sims_out=sims, d_off=d_off, force_exact_order=self.model.force_exact_order,
             fmt=pairing)
         self.model.last_result = res
-        boxes, n_boxes, maxsim, _ = res.to_host()
+        self.d2h_bytes += res.buf.numel() * 4
+        job = candidates, q_ids, r_ids, meta, res, res.to_host_async(), sims, off, pairing
+        if prof is not None:
+            prof["launch"] = prof.get("launch", 0.0) + time.perf_counter() - t0
+        return job
 
-        # ---- boxes -> Match rows (localization.py:61-78), vectorised over all boxes of the batch
+    def _rows(self, job) -> List[Match]:
+        """boxes -> Match rows (localization.py:61-78), vectorised over all boxes of the batch."""
+        candidates, q_ids, r_ids, meta, res, wait, sims, off, _pairing = job
+        dq, dr = self._stores()
+        n = len(candidates)
+        prof = self.profile
+        t0 = time.perf_counter() if prof is not None else 0.0
+        boxes, n_boxes, maxsim, _ = wait()
+        if prof is not None:
+            t1 = time.perf_counter(); prof["wait_for_results"] = prof.get("wait_for_results", 0.0) + t1 - t0; t0 = t1
+            prof.setdefault("results_at_ms", []).append(round(1e3 * (t1 - prof.get("t_start", t1)), 2))
         pair_of = np.repeat(np.arange(n), n_boxes)
         if len(pair_of) == 0:
             return []
@@ -277,7 +517,8 @@ class VCSLLocalization(LocalizationWithMetadata):
         q_start, q_end = tq0[qs + bx[:, 0]].tolist(), tq1[qs + bx[:, 2]].tolist()
         r_start, r_end = tr0[rs + bx[:, 1]].tolist(), tr1[rs + bx[:, 3]].tolist()
         pairs_l = pair_of.tolist()
-        qid, rid = [q_ids[p] for p in pairs_l], [r_ids[p] for p in pairs_l]
+        qid = np.fromiter(q_ids, dtype=object, count=n)[pair_of].tolist()     # ids pass through untouched (int, str, ...)
+        rid = np.fromiter(r_ids, dtype=object, count=n)[pair_of].tolist()
         scorer = type(self).score
         if scorer is VCSLLocalizationMaxSim.score:        # similarity[x1:x2, y1:y2].max() - bias, float32 like numpy's
             scores = list(maxsim[pair_of, slot] - self.similarity_bias)
@@ -304,6 +545,8 @@ class VCSLLocalization(LocalizationWithMetadata):
         finally:
             if was_on:
                 gc.enable()
+            if prof is not None:
+                prof["match_rows"] = prof.get("match_rows", 0.0) + time.perf_counter() - t0
 
     def localize(self, candidate: CandidatePair) -> List[Match]:
         return self.localize_all([candidate])

@@ -49,8 +49,24 @@ class TnResult:
     def status(self):
         return self.buf[self._o_st:][:self.n_pairs]
 
+    def to_host_async(self):
+        """Start the device-to-host copy into pinned memory; returns wait() -> the tuple to_host() gives."""
+        torch = _lib.require_cuda()
+        host = torch.empty(self.buf.shape, dtype=self.buf.dtype, pin_memory=True)
+        host.copy_(self.buf, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream(self.buf.device))
+
+        def wait():
+            done.synchronize()
+            return self._split(host.numpy())
+        wait.ready = done.query     # non-blocking: has the copy landed?
+        return wait
+
     def to_host(self):
-        h = self.buf.cpu().numpy()
+        return self._split(self.buf.cpu().numpy())
+
+    def _split(self, h):
         n, cap = self.n_pairs, self.box_cap
         bx = h[self._o_boxes:self._o_nb].reshape(-1, cap, 4)[:n]
         nb = h[self._o_nb:self._o_ms][:n]
