@@ -576,6 +576,7 @@ def run_gpu(args, rank, local_rank, world):
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     ms_max, e2e_ms_max, ms_ff_max, ms_ffb_max = times.tolist()
+    split_k = pairing.k
     sharded = None
     if world > 1 and not args.no_stages:
         del sims, Qd, Rd, oq, orr, pairing, loc, matches, res, res_ff
@@ -619,14 +620,14 @@ def run_gpu(args, rank, local_rank, world):
             "c1_c4_from_descriptors": {
                 "what": "vcsl_tn_batch_from_features on the shard, descriptor panels resident: per-pair tcgen05 GEMM "
                         "(fp16 split, three partial products, K'=%d) with the TN row top-K out of tensor memory, matrices written for the "
-                        "MaxSim scores, graph stage" % pairing.k,
+                        "MaxSim scores, graph stage" % split_k,
                 "ms_with_maxsim": ms_ff_max, "pairs_per_s_with_maxsim": N_PAIRS / (ms_ff_max * 1e-3),
                 "ms_boxes_only": ms_ffb_max, "pairs_per_s_boxes_only": N_PAIRS / (ms_ffb_max * 1e-3),
                 "stages_ms": {"pair_gemm_topk_kernel": st_ff[0], "tn_edges_kernel": st_ff[1], "tn_dp_kernel": st_ff[2],
                               "tn_maxsim_kernel": st_ff[3]},
                 "prepare_panels_ms": ms_prep, "pair_similarity_only_ms": ms_sim,
                 "gemm_tflops_algorithmic": 2.0 * n * f * f * DIM / (st_ff[0] * 1e-3) / 1e12 if st_ff[0] > 0 else None,
-                "gemm_tflops_issued": 2.0 * n * f * f * pairing.k / (st_ff[0] * 1e-3) / 1e12 if st_ff[0] > 0 else None}}
+                "gemm_tflops_issued": 2.0 * n * f * f * split_k / (st_ff[0] * 1e-3) / 1e12 if st_ff[0] > 0 else None}}
         if world == 1 and not args.no_stages:
             del sims, Qd, Rd, oq, orr, pairing
             torch.cuda.empty_cache()

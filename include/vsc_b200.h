@@ -264,6 +264,21 @@ int vsc_gem_pool(const void *d_in, int32_t n, int32_t hw, int32_t c, float p, fl
 /* Number of kernel launches issued by this library since load (all entry points). */
 int64_t vsc_launch_count(void);
 
+/* -------------------------------------------------------------------------
+ * Stage A, ahead of the model: the PIL bilinear resize of torchvision.transforms.Resize (+ CenterCrop) in the
+ * reference's transforms, vsc/baseline/inference_impl.py:39-69, on decoded uint8 RGB frames [n][h][w][3].
+ * The frame is resized to rh x rw and the window [top, top+oh) x [left, left+ow) of it is written to d_out
+ * [n][oh][ow][3].  d_xbounds / d_xk ([rw][2] / [rw][xksize]) and d_ybounds / d_yk ([rh][2] / [rh][yksize]) are Pillow's
+ * (first input pixel, count) windows and 22-bit fixed-point weights (libImaging/Resample.c precompute_coeffs +
+ * normalize_coeffs_8bpc; vsc2022_b200/preprocess.py computes them).  d_tmp: n*h*ow*3 bytes of scratch.
+ * The result equals PIL's Image.resize(..., BILINEAR) bit for bit.
+ * ------------------------------------------------------------------------- */
+int vsc_resize_u8(const uint8_t *d_in, int32_t n, int32_t h, int32_t w, int32_t rh, int32_t rw,
+                  int32_t top, int32_t left, int32_t oh, int32_t ow,
+                  const int32_t *d_xbounds, const int32_t *d_xk, int32_t xksize,
+                  const int32_t *d_ybounds, const int32_t *d_yk, int32_t yksize,
+                  uint8_t *d_tmp, uint8_t *d_out, vsc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -65,3 +65,13 @@ def test_store_fp16_and_merge(tmp_path):
     for f in feats:
         assert np.array_equal(back[f.video_id].feature, f.feature)
         assert np.array_equal(back[f.video_id].timestamps, f.timestamps)
+
+
+def test_frame_timestamps_quirk():
+    """ffmpeg_video_reader.py:54 with original_fps == 1 (video_reader.py:18, FFMpegVideoReader.fps is None)."""
+    from vsc2022_b200.inference_impl import frame_timestamps
+    ts = frame_timestamps(4)
+    assert ts.tolist() == [[0.0, 1.0], [1.0, 2.0], [2.0, 3.0], [3.0, 4.0]]
+    assert frame_timestamps(2, original_fps=0.5).tolist() == [[0.0, 1.0], [1.0, 2.0]]      # max(1, fps)
+    assert frame_timestamps(2, original_fps=4).tolist() == [[0.0, 0.25], [0.25, 0.5]]
+    assert frame_timestamps(0).shape == (0, 2)

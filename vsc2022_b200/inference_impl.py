@@ -18,6 +18,17 @@ from .index import VideoFeature
 from .storage import load_features, store_features
 
 
+def frame_timestamps(n_frames: int, original_fps=None) -> np.ndarray:
+    """The [start, end] timestamps the reference attaches to decoded frame i: ((i) / original_fps, (i + 1) / original_fps)
+    with original_fps = max(1, reader.fps) if reader.fps else 1 (video_reader/video_reader.py:18) -- and since
+    FFMpegVideoReader.fps is always None (ffmpeg_video_reader.py:28-30), every frame extracted at `--fps` gets the
+    interval [i, i + 1] whatever the sampling rate.  Reproduced as it is: downstream timestamps (Match rows, metrics)
+    depend on it."""
+    fps = max(1, original_fps) if original_fps else 1
+    i = np.arange(n_frames, dtype=np.float64)
+    return np.stack([i / fps, (i + 1) / fps], axis=1)
+
+
 def select_videos(videos: Sequence, rank: int = 0, world_size: int = 1) -> List[Tuple[int, object]]:
     """`VideoDataset.selected_videos` (inference_impl.py:103-109): video i belongs to rank i % world_size."""
     assert rank < world_size
@@ -63,12 +74,16 @@ def run_inference(dataloader: Iterable[dict], model: Callable, device=None, stor
 
 
 def infer_videos(videos: Sequence[Tuple[object, np.ndarray, object]], model: Callable, batch_size: int = 128,
-                 store_fp16: bool = False, device=None, on_device: bool = False) -> List[VideoFeature]:
+                 store_fp16: bool = False, device=None, on_device: bool = False, transform=None) -> List[VideoFeature]:
     """videos: (video_id, timestamps [n] or [n, 2], frames) with frames uint8 [n, H, W, 3] or normalised float32
-    [n, 3, H, W] (numpy or torch).  Frames of all videos must share one geometry.  Returns one VideoFeature per video, in
-    order, identical to feeding every video on its own.  on_device=True (extension): the descriptors stay on the GPU --
-    every VideoFeature holds a row view of one device matrix, ready for score_normalize / CandidateGeneration."""
+    [n, 3, H, W] (numpy or torch).  Frames of all videos must share one geometry (after `transform`).  Returns one
+    VideoFeature per video, in order, identical to feeding every video on its own.  on_device=True (extension): the
+    descriptors stay on the GPU -- every VideoFeature holds a row view of one device matrix, ready for score_normalize /
+    CandidateGeneration.  transform: a preprocess.GpuTransform (build_transforms, inference_impl.py:39-69) applied to the
+    decoded uint8 frames of every video on the device before they are packed into batches."""
     import torch
+    if transform is not None:
+        model = _TransformedModel(model, transform)
     if on_device:
         return _infer_videos_device(videos, model, batch_size, store_fp16, device)
     counts = [int(len(f)) for _, _, f in videos]
@@ -110,6 +125,17 @@ def infer_videos(videos: Sequence[Tuple[object, np.ndarray, object]], model: Cal
         feat = np.concatenate(chunks[v], axis=0) if chunks[v] else np.zeros((0, dim), np.float16 if store_fp16 else np.float32)
         out[v] = VideoFeature(video_id=vid, timestamps=np.asarray(ts), feature=feat)
     return out  # type: ignore[return-value]
+
+
+class _TransformedModel:
+    """model(transform(frames)).  Packed batches hold frames of ONE source geometry (the caller's contract), so the
+    whole batch is resized in one launch pair."""
+
+    def __init__(self, model, transform):
+        self.model, self.transform = model, transform
+
+    def __call__(self, frames):
+        return self.model(self.transform(frames))
 
 
 def _infer_videos_device(videos, model, batch_size, store_fp16, device):
