@@ -431,6 +431,66 @@ def stage_numbers_sharded(dev, peaks, rank, world):
                     "(NCCL) so that every rank holds all %d x 512" % (world, mine_n, mine_n * world),
         "ms": ms, "frames_per_s_whole_job": mine_n * world / ms * 1e3,
         "tflops_whole_job": mine_n * world * 13.513e9 / ms / 1e9}
+    del frames_u8, everything
+    torch.cuda.empty_cache()
+
+    # ---- configs[4] at the N=1 miniature's size, over the ranks: videos i % world per rank (the reference's rule) ->
+    # SSCD -> NCCL all-gather of the descriptors -> score normalisation + query-sharded search -> candidate pairs
+    # sharded contiguously -> TN localization -> matches gathered.  Wall clock per stage, max over ranks.
+    import numpy as np
+    from vsc2022_b200 import distributed as D, inference_impl
+    from vsc2022_b200.candidates import CandidateGeneration, MaxScoreAggregation
+    from vsc2022_b200.localization import VCSLLocalizationMaxSim
+    from vsc2022_b200.score_normalization import score_normalize
+    nq, nr, nn, fr = 50, 400, 50, 40
+    ts = np.stack([np.arange(fr) * 1.0, np.arange(fr) * 1.0 + 1.0], axis=1)
+
+    def frames_of(kind, i):       # every video has its own seed: a rank generates only what it owns (+ planted sources)
+        gv = torch.Generator(device=dev)
+        gv.manual_seed({"R": 1_000_000, "Q": 2_000_000, "N": 3_000_000}[kind] + i)
+        x = torch.randint(0, 256, (fr, 288, 288, 3), generator=gv, device=dev, dtype=torch.uint8)
+        if kind == "Q" and i % 2 == 0:
+            x[8:28] = frames_of("R", (i * 37) % nr)[4:24]
+        return x
+    sets = {k: [(f"{k}{i:06d}", ts, frames_of(k, i)) for i in range(cnt) if i % world == rank]
+            for k, cnt in (("Q", nq), ("R", nr), ("N", nn))}
+
+    def stamp():
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        return time.perf_counter()
+
+    def pipeline():
+        t0 = stamp()
+        local = {k: inference_impl.infer_videos(v, model, batch_size=128, device=dev, on_device=True) for k, v in sets.items()}
+        t1 = stamp()
+        feats = {k: D.all_gather_video_features(local[k], cnt, device=dev, on_device=True)
+                 for k, cnt in (("Q", nq), ("R", nr), ("N", nn))}
+        t2 = stamp()
+        sn_q, sn_r = score_normalize(feats["Q"], feats["R"], feats["N"], beta=1.2, on_device=True)
+        cg = CandidateGeneration(sn_r, MaxScoreAggregation())
+        cands = cg.query(sn_q, global_k=1200 * nq, limit=25 * nq, group=dist.group.WORLD)
+        t3 = stamp()
+        todo = cands[:5 * nq]
+        lo_, hi_ = D.shard_bounds(len(todo), rank, world)
+        loc = VCSLLocalizationMaxSim(sn_q, sn_r, model_type="TN", tn_max_step=5, min_length=4, concurrency=16, similarity_bias=0.5)
+        matches = D.gather_lists(loc.localize_all(todo[lo_:hi_]))
+        t4 = stamp()
+        return (t0, t1, t2, t3, t4), cands, matches
+    pipeline()
+    (t0, t1, t2, t3, t4), cands, matches = pipeline()
+    planted = {(f"Q{i:06d}", f"R{(i * 37) % nr:06d}") for i in range(0, nq, 2)}
+    found = {(m.query_id, m.ref_id) for m in matches}
+    n_frames = (nq + nr + nn) * fr
+    out["c5_pipeline_sharded"] = {
+        "workload": f"configs[4] at test size on {world} GPUs: {nq} query + {nr} ref + {nn} noise videos x {fr} frames of 288x288, "
+                    "videos i % world per rank -> SSCD -> NCCL all-gather of the descriptors -> score-norm + query-sharded global "
+                    "top-K -> TN localization of contiguous candidate shards -> matches gathered (second pass timed)",
+        "seconds": {"descriptors": t1 - t0, "all_gather": t2 - t1, "score_norm_and_search": t3 - t2, "localize": t4 - t3,
+                    "total": t4 - t0},
+        "frames_per_s_descriptors": n_frames / (t1 - t0), "frames_per_s_total": n_frames / (t4 - t0),
+        "candidates": len(cands), "pairs_localized": min(len(cands), 5 * nq), "matches": len(matches),
+        "planted_pairs_found": len(planted & found), "planted_pairs": len(planted)}
     return out
 
 

@@ -133,12 +133,13 @@ def all_gather_rows(t: torch.Tensor, group=None) -> List[torch.Tensor]:
     return out
 
 
-def all_gather_video_features(local, n_videos: int, device=None, group=None):
+def all_gather_video_features(local, n_videos: int, device=None, group=None, on_device: bool = False):
     """Stage A runs video i on rank i % world_size (inference_impl.select_videos, the reference's VideoDataset rule);
     the search stage wants every rank to hold ALL reference descriptors (BASELINE.json configs[4]: "ref descriptors
     NCCL all-gathered over NVLink").  `local`: this rank's VideoFeatures in its own order.  Returns the VideoFeatures of
     all n_videos videos in global video order on every rank: ids and timestamps travel as small objects, the
-    descriptor rows in one all-gather of device tensors."""
+    descriptor rows in one all-gather of device tensors.  `local` features may be CUDA tensors (inference with
+    on_device=True); on_device=True leaves the gathered descriptors on the GPU as row views of the gathered matrices."""
     import numpy as np
     from .index import VideoFeature
     rank, ws = world(group)
@@ -148,17 +149,23 @@ def all_gather_video_features(local, n_videos: int, device=None, group=None):
     dims = [None] * ws
     dist.all_gather_object(dims, dim, group=group)
     dim = max(dims)
-    dtype = np.result_type(*[v.feature.dtype for v in local]) if local else np.float32
-    rows = np.concatenate([v.feature for v in local]) if local else np.zeros((0, dim), dtype)
     dev = device if device is not None else ("cuda" if dist.get_backend(group) == "nccl" else "cpu")
-    parts = all_gather_rows(torch.from_numpy(np.ascontiguousarray(rows, dtype=np.float32)).to(dev), group)
+    if local and isinstance(local[0].feature, torch.Tensor):
+        dtype = np.float32
+        rows_t = torch.cat([v.feature for v in local]).to(dev, torch.float32)
+    else:
+        dtype = np.result_type(*[v.feature.dtype for v in local]) if local else np.float32
+        rows = np.concatenate([v.feature for v in local]) if local else np.zeros((0, dim), dtype)
+        rows_t = torch.from_numpy(np.ascontiguousarray(rows, dtype=np.float32)).to(dev)
+    parts = all_gather_rows(rows_t.contiguous(), group)
     meta = [None] * ws
     dist.all_gather_object(meta, [(v.video_id, v.timestamps, len(v)) for v in local], group=group)
     out = [None] * n_videos
     for r in range(ws):
-        feats, at = parts[r].cpu().numpy(), 0
+        feats, at = parts[r] if on_device else parts[r].cpu().numpy(), 0
         for slot, (vid, ts, n) in zip(range(r, n_videos, ws), meta[r]):
-            out[slot] = VideoFeature(video_id=vid, timestamps=ts, feature=feats[at:at + n].astype(dtype, copy=False))
+            rows_v = feats[at:at + n] if on_device else feats[at:at + n].astype(dtype, copy=False)
+            out[slot] = VideoFeature(video_id=vid, timestamps=ts, feature=rows_v)
             at += n
     assert all(v is not None for v in out), "every video must be owned by exactly one rank"
     return out
