@@ -376,9 +376,17 @@ __device__ __forceinline__ int oct_add(int v, unsigned m) {
     return v + __shfl_xor_sync(m, v, 4);
 }
 
-__host__ __device__ inline int window_depth(int step) {  // power of two >= step
+// The per-layer maxima are taken once per kAhead layers from the window (layer_max) instead of with three shuffles and a
+// ballot per layer (measured: see profiles/r02_tn_summary.md); VSC_DP_DEFER_MAX=0 restores the per-layer form.
+#ifndef VSC_DP_DEFER_MAX
+#define VSC_DP_DEFER_MAX 1
+#endif
+constexpr bool kDeferMax = VSC_DP_DEFER_MAX != 0;
+static_assert(kAhead <= 8, "one lane of the octet per deferred layer");
+
+__host__ __device__ inline int window_depth(int step) {  // power of two >= step (and >= kAhead: deferred layer maxima)
     int d = 1;
-    while (d < step) d <<= 1;  // > step-1, so the slot being written is never one being read
+    while (d < step || (kDeferMax && d < kAhead)) d <<= 1;  // > step-1, so the slot being written is never one being read
     return d;
 }
 
@@ -403,6 +411,21 @@ __device__ __forceinline__ Rec load_rec(const Rec *p) {
     d[0] = __ldcg(s);
     if (sizeof(Rec) == 32) d[1] = __ldcg(s + 1);
     return r;
+}
+
+// Layer maximum and the ranks that attain it, read back from the window by ONE lane (distances are >= +0: their bit
+// patterns are ordered as unsigned integers).
+template <int K>
+__device__ __forceinline__ void layer_max(const float2 *win, int base, uint32_t &best, uint8_t &ranks) {
+    uint32_t v[K], m = 0;
+#pragma unroll
+    for (int r = 0; r < K; ++r) { v[r] = __float_as_uint(win[base + r].x); m = max(m, v[r]); }
+    uint32_t at = 0;
+#pragma unroll
+    for (int r = 0; r < K; ++r) at |= (v[r] == m ? 1u : 0u) << r;
+    // ranks >= K of the octet hold distance 0 in the window: they tie with an all-zero layer exactly as in the shuffle form
+    if (m == 0u) at = 0xFFu;
+    best = m; ranks = (uint8_t)at;
 }
 
 // One lane relaxes its own node against the distance window: FIRST maximal predecessor in
@@ -550,10 +573,19 @@ __global__ void __launch_bounds__(kT2Threads, 16 / kT2Warps) tn_dp_kernel(const 
                 }
                 // window slot q & wmask held layer q-depth, which nobody reads any more
                 win[(q & wmask) * 8 + sub] = make_float2(d, __int_as_float(g));
-                const uint32_t db = __float_as_uint(d);
-                const uint32_t lm = oct_max(db, kFullMask);  // dist >= +0: bits are ordered
-                const uint32_t at_max = (__ballot_sync(kFullMask, db == lm) >> (oct * 8)) & 0xFFu;
-                if (sub == 0 && q < lq) { lbest[q] = lm; lrank[q] = (uint8_t)at_max; }
+                if (!kDeferMax) {
+                    const uint32_t db = __float_as_uint(d);
+                    const uint32_t lm = oct_max(db, kFullMask);  // dist >= +0: bits are ordered
+                    const uint32_t at_max = (__ballot_sync(kFullMask, db == lm) >> (oct * 8)) & 0xFFu;
+                    if (sub == 0 && q < lq) { lbest[q] = lm; lrank[q] = (uint8_t)at_max; }
+                }
+                __syncwarp();
+            }
+            // (maximum, ranks that attain it) of the kAhead layers just relaxed: lane `sub` takes layer q0 + sub straight
+            // from the window -- no shuffles on the layer-to-layer chain
+            if (kDeferMax) {
+                const int q = q0 + sub;
+                if (sub < kAhead && q < lq) layer_max<K>(win, (q & wmask) * 8, lbest[q], lrank[q]);
                 __syncwarp();
             }
         }
@@ -775,6 +807,7 @@ __global__ void __launch_bounds__(kT2Threads, 16 / kT2Warps) tn_dp_kernel(const 
             // the exit test runs once per kAhead steps (an early exit inside the unrolled body brings back the
             // register moves behind the prefetch loads); the few extra steps are predicated off
             if (!__any_sync(kFullMask, sweeping && q < lq && (q <= q_last || q <= last_changed + step - 1))) break;
+            const int q_group = q;
 #pragma unroll
             for (int u = 0; u < kAhead; ++u) {
                 // once `on` turns false for an octet it stays false (nothing can update last_changed), so the
@@ -793,12 +826,19 @@ __global__ void __launch_bounds__(kT2Threads, 16 / kT2Warps) tn_dp_kernel(const 
                 }
                 if (on) win[(q & wmask) * 8 + sub].x = d;
                 if (__ballot_sync(kFullMask, changed) & om) last_changed = q;
-                const uint32_t db = __float_as_uint(d);
-                const uint32_t lm = oct_max(db, kFullMask);
-                const uint32_t at_max = (__ballot_sync(kFullMask, db == lm) >> (oct * 8)) & 0xFFu;
-                if (sub == 0 && on) { lbest[q] = lm; lrank[q] = (uint8_t)at_max; }
+                if (!kDeferMax) {
+                    const uint32_t db = __float_as_uint(d);
+                    const uint32_t lm = oct_max(db, kFullMask);
+                    const uint32_t at_max = (__ballot_sync(kFullMask, db == lm) >> (oct * 8)) & 0xFFu;
+                    if (sub == 0 && on) { lbest[q] = lm; lrank[q] = (uint8_t)at_max; }
+                }
                 if (on) ++q;
                 VSC_CLK_ADD(6, 1);
+                __syncwarp();
+            }
+            if (kDeferMax) {   // the layers [q_group, q) this octet has just relaxed
+                const int ql = q_group + sub;
+                if (sub < kAhead && ql < q) layer_max<K>(win, (ql & wmask) * 8, lbest[ql], lrank[ql]);
                 __syncwarp();
             }
         }
