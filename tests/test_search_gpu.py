@@ -330,3 +330,54 @@ def test_score_normalize_device_handoff_and_small_kernels(golden_c1):
     assert (out[:, 299] == 1.0).all()
     raw, _ = l2norm_dropdim(d_x, None, False, extra_column=False)
     assert np.array_equal(raw.cpu().numpy(), x)
+
+
+def test_reference_index_code_over_the_faiss_stand_in():
+    """The statements of the reference's VideoIndex (vsc/index.py:82,94,142-165,167-177) executed against
+    `vsc2022_b200.compat`'s faiss module -- the engine behind the unmodified file -- and against the oracle's numpy
+    faiss shim: same radius, limits, distances, ids; same global top-K list; same kNN result."""
+    import importlib
+    import importlib.util
+    import os
+    import sys
+    from vsc2022_b200 import compat
+    gpu_faiss = compat.faiss_module()
+    # the oracle's numpy faiss, loaded under a private package name (sys.modules["faiss"] may be the stand-in already)
+    shim = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "shims", "faiss")
+    spec = importlib.util.spec_from_file_location("oracle_faiss_shim", os.path.join(shim, "__init__.py"),
+                                                  submodule_search_locations=[shim])
+    cpu_faiss = importlib.util.module_from_spec(spec)
+    sys.modules["oracle_faiss_shim"] = cpu_faiss
+    spec.loader.exec_module(cpu_faiss)
+    cpu_es = importlib.import_module("oracle_faiss_shim.contrib.exhaustive_search")
+    rng = np.random.default_rng(21)
+    grid = lambda n, d: (rng.integers(-16, 17, size=(n, d)) / 16.0).astype(np.float32)
+    for metric_name in ("METRIC_INNER_PRODUCT", "METRIC_L2"):
+        db, xq = [grid(37, 64) for _ in range(9)], grid(700, 64)
+        results = []
+        for faiss, es in ((gpu_faiss, gpu_faiss.contrib.exhaustive_search), (cpu_faiss, cpu_es)):
+            metric = getattr(faiss, metric_name)
+            index = faiss.index_factory(64, "Flat", metric)                       # index.py:82
+            for x in db:
+                index.add(x)                                                      # index.py:94
+            use_similarity = index.metric_type == faiss.METRIC_INNER_PRODUCT      # index.py:145
+            global_k = 3000
+            radius, limits, similarity, indices = es.range_search_max_results(    # index.py:147-154
+                index, es.exponential_query_iterator(xq), -1e10 if use_similarity else 1e10,
+                max_results=2 * global_k, min_results=global_k, ngpu=-1)
+            search_indices = [(i, int(indices[j]), similarity[j]) for i in range(len(xq)) for j in range(limits[i], limits[i + 1])]
+            search_indices.sort(key=lambda t: t[2], reverse=use_similarity)       # index.py:162-164
+            search_indices = search_indices[:global_k]
+            D, I = index.search(xq[:50], 3)                                       # index.py:172
+            lims_r, D_r, I_r = index.range_search(xq[:40], 2.0 if use_similarity else 36.0)
+            results.append((float(radius), np.asarray(limits), np.asarray(similarity), np.asarray(indices), search_indices,
+                            D, I, lims_r, D_r, I_r))
+        got, want = results
+        assert got[0] == want[0]
+        for a, b in zip(got[1:4], want[1:4]):
+            assert np.array_equal(a, b)
+        assert got[4] == want[4] and len(got[4]) == 3000
+        assert np.array_equal(got[5], want[5]) and np.array_equal(got[6], want[6])
+        for a, b in zip(got[7:], want[7:]):
+            assert np.array_equal(a, b)
+        assert len(got[8]) > 20

@@ -157,6 +157,36 @@ class FlatIndex:
         D[:, :kk], I[:, :kk] = d, i
         return D, I
 
+    def range_search(self, x, radius: float):
+        """faiss IndexFlat.range_search: (lims [nq+1], D, I) -- per query row, in database order, every entry whose score
+        beats `radius` STRICTLY (> for inner product, < for squared L2).  Two launches of the threshold-emit GEMM: the
+        first only counts, the second stores into a buffer of exactly that size."""
+        torch = _lib.require_cuda()
+        xq = self._to_device(x)
+        xb = self.database()
+        nq, nb = xq.shape[0], xb.shape[0]
+        lims = np.zeros(nq + 1, dtype=np.int64)
+        if nq == 0 or nb == 0:
+            return lims, np.zeros(0, np.float32), np.zeros(0, np.int64)
+        keep_max = self.metric_type == METRIC_INNER_PRODUCT
+        oa, ob = gemm.prepare_pair(xq, xb, self.precise)
+        pairing = gemm.Pairing(oa, ob, self.precise)
+        qn = bn = None
+        if not keep_max:
+            qn, bn = gemm.row_sqnorm(xq), gemm.row_sqnorm(xb)
+        never = float("inf") if keep_max else float("-inf")
+        probe = gemm.HitBuffer(EMIT_PAD, xq.device)
+        gemm.gemm_emit(oa, ob, probe, radius, never, metric_l2=not keep_max, a_norm=qn, b_norm=bn, pairing=pairing)
+        counted = probe.read_counters()[1]
+        hits = gemm.HitBuffer(counted + EMIT_PAD, xq.device)
+        gemm.gemm_emit(oa, ob, hits, radius, radius, metric_l2=not keep_max, a_norm=qn, b_norm=bn, pairing=pairing)
+        held = self._refilter(hits, hits.read_counters()[0], radius, keep_max)      # drops the per-warp block fillers
+        row, col, score = hits.row[:held].long(), hits.col[:held].long(), hits.score[:held]
+        order = torch.argsort(row * nb + col)
+        row, col, score = row[order], col[order], score[order]
+        lims[1:] = np.cumsum(np.bincount(row.cpu().numpy(), minlength=nq))
+        return lims, score.cpu().numpy(), col.cpu().numpy()
+
     def max_similarity(self, x):
         """max_j <x_i, db_j> per row as a device tensor -- all score normalisation needs from search(x, 1)."""
         assert self.metric_type == METRIC_INNER_PRODUCT
