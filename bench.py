@@ -713,7 +713,10 @@ def run_gpu(args, rank, local_rank, world):
                          "traffic": TRAFFIC_BYTES_PER_CALL * n / 8000.0,
                          "stages_ms": {"tn_topk_kernel": stage[0], "tn_edges_kernel": stage[1],
                                        "tn_dp_kernel": stage[2], "tn_maxsim_kernel": stage[3]},
-                         "tn_topk_frac": algo_bytes / (stage[0] * 1e-3) / 1e9 / peaks["hbm_gbs"] if stage[0] > 0 else None},
+                         "dominant_kernel": "tn_topk_kernel (the only HBM-bound stage: reads every matrix once)",
+                         "dominant_kernel_frac": algo_bytes / (stage[0] * 1e-3) / 1e9 / peaks["hbm_gbs"] if stage[0] > 0 else None,
+                         "note": "frac is quoted on the WHOLE call (row top-K + edges + longest-path sweeps + MaxSim); edges and "
+                                 "sweeps are instruction- / latency-bound and move 0.6 GB, see profiles/r02_tn_summary.md"},
             "cpu_baseline": cpu,
             "stages": stages,
             "result_check": check,
@@ -724,8 +727,8 @@ def run_gpu(args, rank, local_rank, world):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum over the kernels of one 8000-pair call, from the ncu capture
-# committed under profiles/ (per-launch table: profiles/r01_tn_launches_final.txt).
-TRAFFIC_BYTES_PER_CALL = 3.88e9  # tn_topk 3.014+0.213, tn_edges 0.152+0.058, tn_dp 0.326+0.116 GB (profiles/r01_tn_summary.md)
+# committed under profiles/ (per-launch table: profiles/r02_bench_launches_by_kernel.txt).
+TRAFFIC_BYTES_PER_CALL = 4.01e9  # tn_topk 3.014+0.207, tn_edges 0.149+0.052, tn_dp 0.323+0.105, tn_maxsim 0.158 GB (profiles/r02_bench_launches_by_kernel.txt)
 
 
 def main():
