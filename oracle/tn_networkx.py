@@ -33,10 +33,21 @@ Numerical contract (what runs in THIS image: numpy 2.x, networkx 3.6.1):
       topological order = Kahn generations (zero-in-degree nodes in insertion
       order, children in adjacency order); per node the FIRST maximal
       predecessor wins; the end node is the FIRST maximum in topological order.
-    * no "sink" node: VCSL may link a zero-weight sink; with first-max
-      tie-breaking a sink can never be selected as the end node (its distance
-      ties with a predecessor that precedes it), so both variants give the same
-      boxes.
+    * "sink" node (``tn(..., sink=...)``): upstream VCSL has a "link sink node"
+      step that could not be read here (source missing).  Contract = "none".
+      The two possible readings are implemented as a switch so that their
+      effect is measured, not argued (tests/test_oracle_cpu.py::
+      test_vcsl_sink_node_variants):
+        "dedicated"  an extra node (Lq, Lr) after all real nodes, zero-weight
+                     edges from every node within tn_max_step of it, stripped
+                     from the path.  With first-max tie-breaking it is never the
+                     end node and never lies inside a path: boxes are identical
+                     to "none" on every golden and random fixture.
+        "last_node"  the LAST REAL node (last query row, lowest top-k rank)
+                     plays the sink: its incoming edges weigh 0 and it is
+                     stripped from paths.  This changes the boxes of 13 of the
+                     186 test matrices (paths that end in the last row).
+      Which reading the pinned VCSL commit implements stays UNVERIFIED.
 """
 from typing import List, Sequence, Tuple
 

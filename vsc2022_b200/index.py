@@ -8,6 +8,7 @@ csrc/gemm_tc.cu (tcgen05 GEMM with fused threshold-emit and row-max epilogues); 
 faiss.contrib.exhaustive_search.range_search_max_results is followed step by step so ties behave identically.
 """
 import collections
+import functools
 import logging
 from dataclasses import dataclass
 from typing import Iterable, List, NamedTuple, Optional, Sequence, Tuple
@@ -175,10 +176,10 @@ class FlatIndex:
         if not keep_max:
             qn, bn = gemm.row_sqnorm(xq), gemm.row_sqnorm(xb)
         never = float("inf") if keep_max else float("-inf")
-        probe = gemm.HitBuffer(EMIT_PAD, xq.device)
+        probe = gemm.HitBuffer(emit_pad(), xq.device)
         gemm.gemm_emit(oa, ob, probe, radius, never, metric_l2=not keep_max, a_norm=qn, b_norm=bn, pairing=pairing)
         counted = probe.read_counters()[1]
-        hits = gemm.HitBuffer(counted + EMIT_PAD, xq.device)
+        hits = gemm.HitBuffer(counted + emit_pad(), xq.device)
         gemm.gemm_emit(oa, ob, hits, radius, radius, metric_l2=not keep_max, a_norm=qn, b_norm=bn, pairing=pairing)
         held = self._refilter(hits, hits.read_counters()[0], radius, keep_max)      # drops the per-warp block fillers
         row, col, score = hits.row[:held].long(), hits.col[:held].long(), hits.score[:held]
@@ -256,7 +257,7 @@ class FlatIndex:
         if not keep_max:
             qn, bn = gemm.row_sqnorm(xq), gemm.row_sqnorm(xb)
         if capacity is None:
-            capacity = max(4 * max_results, min(32 * nb, 1 << 26)) + EMIT_PAD + 65536   # the first 32-row batch fits
+            capacity = max(4 * max_results, min(32 * nb, 1 << 26)) + emit_pad() + 65536   # the first 32-row batch fits
         hits = gemm.HitBuffer(int(capacity), dev)
         pairing = gemm.Pairing(oa, ob, self.precise)
         if ws == 1 and self.device_schedule:
@@ -276,8 +277,8 @@ class FlatIndex:
             while r0 < b1:
                 rows = max(1, min(rows, b1 - r0))
                 room = hits.capacity - held
-                if unbounded and prune == radius and rows * nb > room - EMIT_PAD:
-                    rows = max(room - EMIT_PAD, 0) // nb   # known emission: size the slice instead of trying
+                if unbounded and prune == radius and rows * nb > room - emit_pad():
+                    rows = max(room - emit_pad(), 0) // nb   # known emission: size the slice instead of trying
                 if rows >= 1:
                     hits.counters[0] = held
                     hits.counters[1] = 0
@@ -389,8 +390,22 @@ class FlatIndex:
         return new
 
 
-# upper bound of the filler slots one emit launch can add (every warp of the grid retires one partly used block)
-EMIT_PAD = 148 * 8 * 256
+# upper bound of the filler slots one emit launch can add: every epilogue warp of the persistent grid (one CTA per SM,
+# 8 epilogue warps: gemm_tc.cu) retires one partly used block of 256 slots.  Sized for the largest SM count in the process
+# (148 on B200); the buffer writes themselves are guarded by the capacity, this only sizes margins.
+@functools.lru_cache(maxsize=1)
+def emit_pad() -> int:
+    sms = 148
+    try:
+        import torch
+        if torch.cuda.is_available():
+            sms = max(torch.cuda.get_device_properties(i).multi_processor_count for i in range(torch.cuda.device_count()))
+    except Exception:
+        pass
+    return sms * 8 * 256
+
+
+EMIT_PAD = 148 * 8 * 256     # the B200 value; code paths use emit_pad() once a device is in play
 
 
 def index_factory(d: int, description: str = "Flat", metric: int = METRIC_L2) -> FlatIndex:
