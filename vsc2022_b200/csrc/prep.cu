@@ -1,11 +1,13 @@
-// Operand preparation for the descriptor GEMM: fp32 descriptors -> K-major bf16 panels.
+// Operand preparation for the descriptor GEMMs: fp32 descriptors -> K-major 16-bit panels.
 //
-// Tensor cores multiply bf16; the reference multiplies fp32 (FAISS sgemm).  Descriptors whose values
-// are bf16-representable lose nothing (mode HI).  For arbitrary fp32 descriptors the split
-// x = hi + lo (hi = bf16(x), lo = bf16(x - hi)) recovers fp32-class products with three partial
-// GEMMs  hi.hi + hi.lo + lo.hi,  laid out as ONE GEMM with K' = 3K:
-//     A' = [hi | hi | lo]      B' = [hi | lo | hi]
-// (the dropped lo.lo term is < 2^-16 relative per product).  HBM-bound elementwise kernel.
+// Tensor cores multiply 16-bit values; the reference multiplies fp32 (FAISS sgemm, np.matmul).  The product path is
+// prepare_f16_kernel (vsc_prepare_operand_f16 / _more): x * 2^e is split into hi = fp16(x 2^e) and
+// lo = fp16((x 2^e - hi) 2^11), 22 significant bits per value, laid out so that ONE GEMM over K' = 3K adds the three
+// partial products hi.lo + lo.hi + hi.hi (include/vsc_b200.h, vsc_gemm_format); every product is exact in the fp32
+// accumulator, the dropped lo.lo term is < 2^-22 relative.  Values that fit the hi part leave the lo flag clear and the
+// last third of the panel alone is exact (grid / test data).
+// prepare_kernel (vsc_prepare_operand) is the older bf16 form ([hi | hi | lo] / [hi | lo | hi], 16 significant bits); it
+// stays for bf16 consumers (tests of the GEMM core).  HBM-bound elementwise kernels.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 

@@ -2,9 +2,11 @@
 // (vsc/baseline/inference_impl.py:210-239 runs the TorchScript model; its shape contract is documented in
 // vsc/baseline/adapt_sscd_model.py:56-70: ResNet-50 trunk -> GeM pooling -> Linear(2048 -> 512), no L2 norm).
 //
-// Activations are NHWC bf16, so a 1x1 convolution is a GEMM on the activation tensor itself; 3x3 / 7x7
-// convolutions go through an explicit im2col panel (first version; the implicit-GEMM TMA-im2col load is the
-// planned replacement).  All kernels here are HBM-bound copies with 16-byte accesses.
+// Activations are NHWC bf16, so a 1x1 convolution is a GEMM on the activation tensor itself; 3x3 convolutions are
+// implicit GEMMs (TMA im2col loads inside gemm_tc.cu) and the 7x7 stem reads the space-to-depth image written here.
+// What lives in this file: that space-to-depth / normalisation kernel, the pooling kernels, and two explicit
+// data-movement kernels (im2col3x3, subsample2) that only the tests use, as the independent statement the implicit
+// paths are compared with.  All kernels here are HBM-bound copies with 16-byte accesses.
 #include <cuda_bf16.h>
 
 #include "common.cuh"

@@ -1,7 +1,7 @@
 """`vsc.metrics` mirror: ids, candidate / match records, micro-AP and the segment-level matching metric.
 
 Behavioural contract: vsc/metrics.py of the reference (cited per function); the numbers are the yardstick the
-parity tests use (tests/test_metrics_parity.py replays the reference's 13 known-answer cases).  This module is
+parity tests use (tests/test_mirror_cpu.py runs the reference's own 13 known-answer cases against this module).  This module is
 host-side bookkeeping -- nothing here is on the GPU path -- but it is written independently: interval unions are
 computed with numpy sweeps instead of rebuilding Python interval lists for every prediction.
 """

@@ -4,7 +4,7 @@ The reference runs a downloaded TorchScript file (`vsc/baseline/inference_impl.p
 documented in `vsc/baseline/adapt_sscd_model.py:56-70`.  Here every convolution is a tensor-core GEMM
 (`vsc_gemm_conv` / `vsc_conv3x3`: tcgen05 MMA, TMA-staged operands, folded BatchNorm bias + residual + ReLU in the
 epilogue, NHWC bf16 activations); 1x1 convolutions read the activation tensor directly, 3x3 convolutions are implicit
-GEMMs (TMA im2col loads, no patch matrix), the 7x7 stem goes through a space-to-depth patch panel.
+GEMMs (TMA im2col loads, no patch matrix), the 7x7 stem is a 4x4 convolution over a 2x2 space-to-depth image (no patch matrix either).
 Weights come from any torch module with the torchvision ResNet-50 layout (random init in tests and the bench:
 the SSCD checkpoint is a download the sandbox does not have).
 """
@@ -83,14 +83,6 @@ class SSCDResNet50:
         _lib.check(self.lib.vsc_conv3x3(x.data_ptr(), n, h, w, c, stride, conv.weight.data_ptr(), conv.cout,
                                         conv.bias.data_ptr(), None, 1 if relu else 0, out.data_ptr(),
                                         _sp(torch, self.device)), "vsc_conv3x3")
-        return out, ho, wo
-
-    def _im2col3x3(self, x, n, h, w, c, stride):
-        torch = _lib.require_cuda()
-        ho, wo = (h + 2 - 3) // stride + 1, (w + 2 - 3) // stride + 1
-        out = torch.empty((n * ho * wo, 9 * c), dtype=torch.bfloat16, device=self.device)
-        _lib.check(self.lib.vsc_im2col3x3(x.data_ptr(), n, h, w, c, stride, out.data_ptr(), _sp(torch, self.device)),
-                   "vsc_im2col3x3")
         return out, ho, wo
 
     # ---- forward -----------------------------------------------------------------------------------------------
