@@ -146,6 +146,43 @@ class SSCDResNet50:
         return out
 
 
+def load_torchscript(path: str, device=None, gem_p: float = 3.0, gem_eps: float = 1e-6) -> "SSCDResNet50":
+    """The model `worker_process` loads with torch.jit.load (inference_impl.py:173), as an SSCDResNet50: the TorchScript
+    file is read for its WEIGHTS only.  Accepts the adapted SSCD layout of adapt_sscd_model.py:56-70
+    (`backbone` = children[:-2] of a torchvision ResNet-50, `pool`, `project` = Linear(2048, 512)) and the unadapted
+    torchvision SSCD layout (`backbone`, `embeddings.1` = Linear; its trailing L2 norm is then NOT applied -- the vsc
+    baseline runs the adapted file).  GeM exponent: `pool.p` if the file carries it as a tensor, else `gem_p`."""
+    import torch
+    import torchvision
+    script = torch.jit.load(path, map_location="cpu")
+    state = script.state_dict()
+    child_names = {"0": "conv1", "1": "bn1", "4": "layer1", "5": "layer2", "6": "layer3", "7": "layer4"}
+    trunk_state = {}
+    for key, value in state.items():
+        if key.startswith("backbone."):
+            head, _, tail = key[len("backbone."):].partition(".")
+            trunk_state[f"{child_names.get(head, head)}.{tail}"] = value
+    trunk = torchvision.models.resnet50(weights=None)
+    missing, unexpected = trunk.load_state_dict(trunk_state, strict=False)
+    missing = [k for k in missing if not k.startswith("fc.")]
+    if missing or unexpected:
+        raise ValueError(f"{path}: not a ResNet-50 SSCD model (missing {missing[:4]}, unexpected {list(unexpected)[:4]})")
+    for prefix in ("project", "embeddings.1"):
+        if f"{prefix}.weight" in state:
+            w, b = state[f"{prefix}.weight"], state.get(f"{prefix}.bias")
+            break
+    else:
+        raise ValueError(f"{path}: no projection layer (project / embeddings.1) found")
+    head = torch.nn.Linear(w.shape[1], w.shape[0], bias=True)
+    with torch.no_grad():
+        head.weight.copy_(w)
+        head.bias.copy_(b if b is not None else torch.zeros(w.shape[0]))
+    for name in ("pool.p", "embeddings.0.p"):
+        if name in state and state[name].numel() == 1:
+            gem_p = float(state[name].reshape(()).item())
+    return SSCDResNet50(trunk.eval(), head.eval(), gem_p=gem_p, gem_eps=gem_eps, device=device)
+
+
 class TorchReference:
     """Plain PyTorch fp32 statement of the same model (parity oracle for this floating-point stage)."""
 
