@@ -124,3 +124,33 @@ def test_descriptors_match_cpu_golden():
         assert _cos(got, want).min() >= 0.999, _cos(got, want)
         rel = np.linalg.norm(got - want, axis=1) / np.linalg.norm(want, axis=1)
         assert rel.max() <= 3e-2, rel
+
+
+def test_cuda_graph_replay_is_bit_identical(models):
+    """Full batches of <= graph_max_batch frames replay a captured graph of the forward's launches: same descriptors as the
+    eager launches, for uint8 frames and for normalised float32 input, and across replays with new data."""
+    import torch
+    ours, _ = models
+    g = torch.Generator(device="cuda"); g.manual_seed(6)
+    frames = torch.randint(0, 256, (25, 64, 96, 3), generator=g, device="cuda", dtype=torch.uint8)
+    ours._graphs.clear()
+    graphed = ours.forward(frames, batch=8).cpu().numpy()                # 3 replays + one eager remainder
+    assert len(ours._graphs) == 1
+    again = ours.forward(torch.flip(frames, dims=[0]), batch=8).cpu().numpy()
+    keep, ours.graph_max_batch = ours.graph_max_batch, 0
+    try:
+        eager = ours.forward(frames, batch=8).cpu().numpy()
+    finally:
+        ours.graph_max_batch = keep
+    assert np.array_equal(graphed, eager)
+    assert np.array_equal(again[::-1], eager)
+    from vsc2022_b200.sscd import normalize_pixels
+    x = normalize_pixels(frames[:16])
+    a = ours.forward(x, batch=8).cpu().numpy()
+    assert len(ours._graphs) == 2
+    ours.graph_max_batch = 0
+    try:
+        b = ours.forward(x, batch=8).cpu().numpy()
+    finally:
+        ours.graph_max_batch = keep
+    assert np.array_equal(a, b)

@@ -63,6 +63,10 @@ class SSCDResNet50:
         self.head_b = head.bias.detach().to(dev, torch.float32).contiguous()
         self.gem_p, self.gem_eps = float(gem_p), float(gem_eps)
         self.lib = _lib.load()
+        # Full batches of at most `graph_max_batch` frames replay a captured CUDA graph of the 57 launches (the forward of a
+        # 32-frame batch -- the reference's default -- takes 1.4 ms on the device, the launches ~0.5 ms of host time).
+        self.graph_max_batch = 64
+        self._graphs = {}
 
     # ---- primitive launches ------------------------------------------------------------------------------------
     def _conv(self, a, m, conv: _Conv, relu: bool, residual=None):
@@ -91,8 +95,38 @@ class SSCDResNet50:
         [N, 3, H, W] already normalised (what the reference model receives).  Returns float32 [N, 512] descriptors."""
         torch = _lib.require_cuda()
         frames = frames.to(self.device)
-        outs = [self._forward_batch(frames[i:i + batch]) for i in range(0, frames.shape[0], batch)]
+        outs = []
+        for i in range(0, frames.shape[0], batch):
+            part = frames[i:i + batch]
+            graphed = part.shape[0] == batch and batch <= self.graph_max_batch and frames.shape[0] >= 2 * batch
+            outs.append(self._forward_batch_graphed(part) if graphed else self._forward_batch(part))
         return torch.cat(outs) if outs else torch.empty((0, self.head_w.shape[0]), device=self.device)
+
+    def _forward_batch_graphed(self, frames):
+        """_forward_batch through a CUDA graph captured once per (shape, dtype): same kernels, same arithmetic."""
+        torch = _lib.require_cuda()
+        key = (tuple(frames.shape), frames.dtype)
+        entry = self._graphs.get(key)
+        if entry is None:
+            if len(self._graphs) >= 4:          # a few geometries at most: every graph keeps its activations alive
+                return self._forward_batch(frames)
+            dev = self.device
+            static_in = frames.contiguous().clone()
+            cur = torch.cuda.current_stream(dev)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):       # first run outside the capture: function attributes, module loading
+                self._forward_batch(static_in)
+            cur.wait_stream(side)
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = self._forward_batch(static_in)
+            entry = self._graphs[key] = (graph, static_in, static_out)
+        graph, static_in, static_out = entry
+        static_in.copy_(frames)
+        graph.replay()
+        return static_out.clone()
 
     __call__ = forward
 
