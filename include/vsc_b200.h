@@ -98,6 +98,8 @@ int vcsl_tn_batch_from_features(const void *d_q_panel, int64_t q_rows, const voi
 int vsc_tn_set_profiling(int on);
 /* Graph stage of the fast pipeline: 0 = layer-by-layer sweeps (default), 1 = compact graph relaxed by Kahn generation
  * (csrc/tn_graph.cu; parameter sets with (tn_max_step-1)*tn_top_k <= 32).  Identical results. */
+/* Pairs per warp of the longest-path kernel: 0 = chosen from the batch size (default), 1 / 2 / 4 forced (tests, tuning). */
+int vsc_tn_set_dp_pairs_per_warp(int pairs);
 int vsc_tn_set_graph_variant(int variant);
 int vsc_tn_last_stage_ms(float *out4);
 

@@ -151,3 +151,25 @@ def test_equal_distance_runs_stay_on_the_fast_pipeline():
     want = tn_fast.tn_batch(sims, tn_max_step=5, tn_top_k=5, max_path=10, min_sim=0.2, min_length=4, max_iou=0.3)
     assert got == want
     assert (status == 0).all(), status
+
+
+@pytest.mark.parametrize("pairs_per_warp", [1, 2, 4])
+def test_dp_pairs_per_warp_variants(golden_tn, pairs_per_warp):
+    """The longest-path kernel packs 1, 2 or 4 pairs into a warp depending on the batch size (small batches: a warp runs as long
+    as its slowest pair).  Every packing against the oracle: goldens, tie-heavy grids (in-kernel exact tie order), ragged
+    random shapes and full-size pairs."""
+    from vsc2022_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(17)
+    sims = [golden_tn[f"sims_{i}"] for i in range(int(golden_tn["n"]))]
+    sims += [synth.sim_matrix(rng, 40, 40, quant=4.0) for _ in range(24)] + _random_cases(seed=13, count=90, max_len=90)
+    sims += [synth.sim_matrix(rng, 300, 300) for _ in range(40)]
+    cfg = dict(tn_max_step=5, tn_top_k=5, max_path=10, min_sim=0.2, min_length=4, max_iou=0.3)
+    want = tn_fast.tn_batch(sims, **cfg)
+    try:
+        _lib.check(lib.vsc_tn_set_dp_pairs_per_warp(pairs_per_warp), "vsc_tn_set_dp_pairs_per_warp")
+        got, _, status = run_gpu(sims, **VSC_CFG)
+    finally:
+        lib.vsc_tn_set_dp_pairs_per_warp(0)
+    assert got == want
+    assert (status == 0).sum() >= 40      # the 40 full-size pairs at least stay on the fast pipeline

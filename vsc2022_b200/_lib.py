@@ -44,6 +44,7 @@ EXPORTS = {
     "vsc_tn_debug_counters": (ctypes.c_int, [ctypes.c_void_p]),
     "vsc_tn_set_profiling": (ctypes.c_int, [ctypes.c_int]),
     "vsc_tn_set_graph_variant": (ctypes.c_int, [ctypes.c_int]),
+    "vsc_tn_set_dp_pairs_per_warp": (ctypes.c_int, [ctypes.c_int]),
     "vsc_tn_last_stage_ms": (ctypes.c_int, [ctypes.c_void_p]),
     "vsc_prepare_operand": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int64,
                                            ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,

@@ -509,7 +509,8 @@ __device__ int topo_compare_exact(int a, int b, int g, int step, const uint8_t *
 }
 
 template <typename MaskT, int K, int GS>
-__global__ void __launch_bounds__(kT2Threads, 16 / kT2Warps) tn_dp_kernel(const Batch b, const Workspace w, const WorkList out) {
+__global__ void __launch_bounds__(kT2Threads, 16 / kT2Warps) tn_dp_kernel(const Batch b, const Workspace w, const WorkList out,
+                                                                          const int pairs_per_warp) {
     // WARP-SYNCHRONOUS: the four octets of a warp run every loop together (trip count = the longest of the
     // four, shorter ones are predicated off) and all shuffles use the full mask, so the warp never splits into
     // four serially executed instruction streams.
@@ -517,8 +518,10 @@ __global__ void __launch_bounds__(kT2Threads, 16 / kT2Warps) tn_dp_kernel(const 
     const int step = b.step;
     const int lane = threadIdx.x & 31, sub = lane & 7, oct = lane >> 3;
     const unsigned om = 0xFFu << (oct * 8);
-    const int pair = (blockIdx.x * kT2Warps + (threadIdx.x >> 5)) * 4 + oct;
-    const bool alive = pair < b.n_pairs && !w.skip[pair < b.n_pairs ? pair : 0];
+    // pairs_per_warp < 4 (small batches): the warp's loops run as long as the LONGEST of its pairs needs, so with few
+    // pairs per GPU a pair is faster in a warp of its own; the unused octets are dead (see below)
+    const int pair = (blockIdx.x * kT2Warps + (threadIdx.x >> 5)) * pairs_per_warp + oct;
+    const bool alive = oct < pairs_per_warp && pair < b.n_pairs && !w.skip[pair < b.n_pairs ? pair : 0];
     if (!__any_sync(kFullMask, alive)) return;
     const int p = alive ? pair : 0;   // dead octets shadow pair 0 read-only and never store
 
@@ -859,26 +862,26 @@ __global__ void __launch_bounds__(kT2Threads, 16 / kT2Warps) tn_dp_kernel(const 
 
 template <typename MaskT, int K, int GS>
 cudaError_t launch_dp_k(const Batch &b, const Workspace &w, const WorkList &out, int grid, size_t smem,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, int pairs_per_warp) {
     cudaError_t e = cudaFuncSetAttribute(tn_dp_kernel<MaskT, K, GS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(tn_dp_kernel<MaskT, K, GS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (e != cudaSuccess) return e;
-    tn_dp_kernel<MaskT, K, GS><<<grid, kT2Threads, smem, stream>>>(b, w, out);
+    tn_dp_kernel<MaskT, K, GS><<<grid, kT2Threads, smem, stream>>>(b, w, out, pairs_per_warp);
     return cudaGetLastError();
 }
 template <typename MaskT, int GS8>
 cudaError_t launch_dp(const Batch &b, const Workspace &w, const WorkList &out, int grid, size_t smem,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, int ppw) {
     switch (b.topk) {
-        case 1: return launch_dp_k<MaskT, 1, GS8 ? 8 : 1>(b, w, out, grid, smem, stream);
-        case 2: return launch_dp_k<MaskT, 2, GS8 ? 8 : 2>(b, w, out, grid, smem, stream);
-        case 3: return launch_dp_k<MaskT, 3, GS8 ? 8 : 3>(b, w, out, grid, smem, stream);
-        case 4: return launch_dp_k<MaskT, 4, GS8 ? 8 : 4>(b, w, out, grid, smem, stream);
-        case 5: return launch_dp_k<MaskT, 5, GS8 ? 8 : 5>(b, w, out, grid, smem, stream);
-        case 6: return launch_dp_k<MaskT, 6, GS8 ? 8 : 6>(b, w, out, grid, smem, stream);
-        case 7: return launch_dp_k<MaskT, 7, GS8 ? 8 : 7>(b, w, out, grid, smem, stream);
-        default: return launch_dp_k<MaskT, 8, 8>(b, w, out, grid, smem, stream);
+        case 1: return launch_dp_k<MaskT, 1, GS8 ? 8 : 1>(b, w, out, grid, smem, stream, ppw);
+        case 2: return launch_dp_k<MaskT, 2, GS8 ? 8 : 2>(b, w, out, grid, smem, stream, ppw);
+        case 3: return launch_dp_k<MaskT, 3, GS8 ? 8 : 3>(b, w, out, grid, smem, stream, ppw);
+        case 4: return launch_dp_k<MaskT, 4, GS8 ? 8 : 4>(b, w, out, grid, smem, stream, ppw);
+        case 5: return launch_dp_k<MaskT, 5, GS8 ? 8 : 5>(b, w, out, grid, smem, stream, ppw);
+        case 6: return launch_dp_k<MaskT, 6, GS8 ? 8 : 6>(b, w, out, grid, smem, stream, ppw);
+        case 7: return launch_dp_k<MaskT, 7, GS8 ? 8 : 7>(b, w, out, grid, smem, stream, ppw);
+        default: return launch_dp_k<MaskT, 8, 8>(b, w, out, grid, smem, stream, ppw);
     }
 }
 
@@ -1012,6 +1015,10 @@ static int launch_row_topk(const Batch &b, const Workspace &w, const WorkList &o
 // Graph-stage variant: 0 = layer-by-layer kernels (default: fewer warp instructions at batch sizes that fill the GPU),
 // 1 = compact graph by Kahn generation (tn_graph.cu; profiles/r02_tn_graph_variants.md).  VSC_TN_GRAPH=compact or
 // vsc_tn_set_graph_variant(1) selects the latter.
+// pairs per SM up to which the DP runs one / two pairs per warp (see launch_graph)
+// (measured, 300x300 pairs: one pair per warp wins up to ~4 pairs per SM, two up to ~8, four beyond)
+static int g_dp_ppw1_per_sm = 4, g_dp_ppw2_per_sm = 8;
+static int g_dp_ppw_forced = [] { const char *e = getenv("VSC_DP_PPW"); return e ? atoi(e) : 0; }();
 static int g_graph_variant = [] { const char *e = getenv("VSC_TN_GRAPH"); return e && e[0] == 'c' ? 1 : 0; }();
 static bool use_graph_v2() { return g_graph_variant == 1; }
 
@@ -1037,11 +1044,18 @@ static int launch_graph(const Batch &b, const Workspace &w, const WorkList &out,
     }
     mark(2, stream);
     if (rc == VSC_OK) {
-        const int pairs_per_cta = kT2Warps * 4;
+        // pairs per warp: four when the batch fills the GPU (fewest warp instructions), fewer for small batches (a warp
+        // runs as long as its slowest pair; measured in profiles/r02_tn_summary.md).  VSC_DP_PPW / vsc_tn_set_dp_pairs_per_warp override.
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        int ppw = b.n_pairs <= sms * g_dp_ppw1_per_sm ? 1 : (b.n_pairs <= sms * g_dp_ppw2_per_sm ? 2 : 4);
+        if (g_dp_ppw_forced == 1 || g_dp_ppw_forced == 2 || g_dp_ppw_forced == 4) ppw = g_dp_ppw_forced;
+        const int pairs_per_cta = kT2Warps * ppw;
         const int grid = (b.n_pairs + pairs_per_cta - 1) / pairs_per_cta;
-        const size_t smem = t2_pair_bytes(b.max_nodes, b.max_lq, b.step) * pairs_per_cta;
-        fail(wide ? launch_dp<uint64_t, 0>(b, w, out, grid, smem, stream)
-                  : launch_dp<uint32_t, 1>(b, w, out, grid, smem, stream), "tn_dp_kernel");
+        const size_t smem = t2_pair_bytes(b.max_nodes, b.max_lq, b.step) * kT2Warps * 4;
+        fail(wide ? launch_dp<uint64_t, 0>(b, w, out, grid, smem, stream, ppw)
+                  : launch_dp<uint32_t, 1>(b, w, out, grid, smem, stream, ppw), "tn_dp_kernel");
         fail(cudaGetLastError(), "tn_dp_kernel");
         vsc::count_launch();
     }
@@ -1079,6 +1093,12 @@ int launch_pipeline_from_features(const PairOperands &op, const Batch &b, const 
 extern "C" int vsc_tn_set_graph_variant(int variant) {
     if (variant != 0 && variant != 1) { vsc::set_error("vsc_tn_set_graph_variant: 0 (layers) or 1 (compact)"); return VSC_ERR_INVALID; }
     vsc::tn::g_graph_variant = variant;
+    return VSC_OK;
+}
+
+extern "C" int vsc_tn_set_dp_pairs_per_warp(int pairs) {
+    if (pairs != 0 && pairs != 1 && pairs != 2 && pairs != 4) { vsc::set_error("vsc_tn_set_dp_pairs_per_warp: 0 (auto), 1, 2 or 4"); return VSC_ERR_INVALID; }
+    vsc::tn::g_dp_ppw_forced = pairs;
     return VSC_OK;
 }
 
