@@ -141,6 +141,11 @@ int vsc_prepare_operand_f16(const float *d_x, int64_t n, int32_t d, int64_t ld, 
 int vsc_prepare_operand_f16_more(const float *d_x, int64_t n, int32_t d, int64_t ld, int32_t kpad, int32_t side,
                                  void *d_out_f16, float *d_inv_scale, int32_t *d_lo_flag, uint32_t *d_scratch,
                                  vsc_stream_t stream);
+/* The same for a list of rows: d_x / d_out_f16 address the WHOLE matrix / panel, d_rows[0..n) (device) are the absolute rows to
+ * convert, in one launch; keep_scale != 0 behaves like _more, 0 like vsc_prepare_operand_f16 restricted to these rows. */
+int vsc_prepare_operand_f16_rows(const float *d_x, const int32_t *d_rows, int64_t n, int32_t d, int64_t ld, int32_t kpad,
+                                 int32_t side, void *d_out_f16, float *d_inv_scale, int32_t *d_lo_flag, uint32_t *d_scratch,
+                                 int32_t keep_scale, vsc_stream_t stream);
 int vsc_prepare_operand(const float *d_x, int64_t n, int32_t d, int64_t ld, int32_t kpad, int32_t mode,
                         void *d_out_bf16, int32_t *d_lo_flag, vsc_stream_t stream);
 int vsc_row_sqnorm(const float *d_x, int64_t n, int32_t d, int64_t ld, float *d_out, vsc_stream_t stream);
@@ -262,6 +267,12 @@ int vsc_maxpool3x3s2(const void *d_in, int32_t n, int32_t h, int32_t w, int32_t 
                      void *d_out, vsc_stream_t stream);
 /* GeM pooling over hw pixels: (mean clamp(x, eps)^p)^(1/p), bf16 [n][c] out */
 int vsc_gem_pool(const void *d_in, int32_t n, int32_t hw, int32_t c, float p, float eps, void *d_out, vsc_stream_t stream);
+
+/* Host -> device copies of n_ranges row ranges ([first_row, n_rows] pairs, int64) of one array, same offsets on both sides,
+ * one cudaMemcpyAsync each, in one call: the block-wise descriptor upload of localize_all (localization.py:56-79 keeps all
+ * descriptors in host dicts; here only the rows a batch of candidates needs cross PCIe, once). */
+int vsc_upload_rows(void *d_dst, const void *h_src, int64_t row_bytes, const int64_t *ranges, int32_t n_ranges,
+                    vsc_stream_t stream);
 
 /* Number of kernel launches issued by this library since load (all entry points). */
 int64_t vsc_launch_count(void);

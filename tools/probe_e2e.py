@@ -18,6 +18,15 @@ from vsc2022_b200.metrics import CandidatePair  # noqa: E402
 from vsc2022_b200.workloads import C4Workload  # noqa: E402
 
 n_pairs = int(sys.argv[1]) if len(sys.argv) > 1 else 8000
+import os  # noqa: E402
+from vsc2022_b200 import localization as _loc  # noqa: E402
+if os.environ.get("VSC_E2E_BLOCK"):     # sweep of the upload granularity
+    _loc._DeviceVideos.BLOCK = int(os.environ["VSC_E2E_BLOCK"])
+if os.environ.get("VSC_E2E_BRIDGE"):
+    _loc._DeviceVideos.BRIDGE = int(os.environ["VSC_E2E_BRIDGE"])
+if os.environ.get("VSC_E2E_CHUNK"):
+    _loc.VCSLLocalization.CHUNK = int(os.environ["VSC_E2E_CHUNK"])
+print("BLOCK", _loc._DeviceVideos.BLOCK, "BRIDGE", _loc._DeviceVideos.BRIDGE, "CHUNK", _loc.VCSLLocalization.CHUNK)
 f, dim = 300, 512
 wl = C4Workload(n_pairs, frames=f, dim=dim)
 q_ids = sorted(set(wl.pair_query.tolist()))
@@ -42,7 +51,7 @@ def whole():
 for _ in range(2):
     whole()
 sync()
-for rep in range(2):
+for rep in range(0 if os.environ.get('VSC_E2E_QUICK') else 2):
     t = [time.perf_counter()]
     loc = VCSLLocalizationMaxSim(queries, refs, "TN", tn_max_step=5, min_length=4, concurrency=16, similarity_bias=0.5)
     t.append(time.perf_counter())
@@ -77,6 +86,8 @@ print("un-instrumented localize_all, fresh object: ms", [round(1e3 * x, 2) for x
 sync(); t0 = time.perf_counter(); a = q_host.to("cuda", non_blocking=True); b = r_host.to("cuda", non_blocking=True); sync()
 dt = time.perf_counter() - t0
 print(f"raw pinned H2D of the same arrays: {1e3 * dt:.2f} ms = {(q_host.numel() + r_host.numel()) * 4 / dt / 1e9:.1f} GB/s")
+if os.environ.get('VSC_E2E_QUICK'):
+    sys.exit(0)
 import cProfile, pstats
 pr = cProfile.Profile(); pr.enable(); whole(); sync(); pr.disable()
 pstats.Stats(pr).sort_stats("cumulative").print_stats(18)

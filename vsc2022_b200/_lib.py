@@ -45,6 +45,8 @@ EXPORTS = {
     "vsc_tn_set_profiling": (ctypes.c_int, [ctypes.c_int]),
     "vsc_tn_set_graph_variant": (ctypes.c_int, [ctypes.c_int]),
     "vsc_tn_set_dp_pairs_per_warp": (ctypes.c_int, [ctypes.c_int]),
+    "vsc_upload_rows": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int32,
+                                        ctypes.c_void_p]),
     "vsc_tn_last_stage_ms": (ctypes.c_int, [ctypes.c_void_p]),
     "vsc_prepare_operand": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int64,
                                            ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
@@ -58,6 +60,10 @@ EXPORTS = {
     "vsc_resize_u8": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_int32] * 9 + [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
                                       ctypes.c_void_p]),
+    "vsc_prepare_operand_f16_rows": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32,
+                                                    ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
+                                                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
+                                                    ctypes.c_void_p]),
     "vsc_row_sqnorm": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int64,
                                       ctypes.c_void_p, ctypes.c_void_p]),
     "vsc_gemm_store": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,

@@ -35,3 +35,23 @@ void keep_pool_cached() {
 extern "C" const char *vsc_last_error(void) { return vsc::g_error; }
 extern "C" int vsc_abi_version(void) { return 1; }
 extern "C" int64_t vsc_launch_count(void) { return vsc::g_launches.load(); }
+
+// Host -> device copies of many row ranges of one array in ONE call (localization.py's block-wise descriptor upload: a
+// chunk of candidate pairs touches hundreds of scattered reference videos; a Python-level copy per range costs more
+// host time than the copies take).  ranges = [first_row, n_rows] pairs; every range is one cudaMemcpyAsync of
+// n_rows * row_bytes bytes at the same offset of both arrays.  Pinned host memory makes them asynchronous.
+extern "C" int vsc_upload_rows(void *d_dst, const void *h_src, int64_t row_bytes, const int64_t *ranges, int32_t n_ranges,
+                               vsc_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (n_ranges <= 0) return VSC_OK;
+    if (!d_dst || !h_src || !ranges || row_bytes <= 0) { vsc::set_error("vsc_upload_rows: bad arguments"); return VSC_ERR_INVALID; }
+    for (int32_t i = 0; i < n_ranges; ++i) {
+        const int64_t first = ranges[2 * i], rows = ranges[2 * i + 1];
+        if (first < 0 || rows < 0) { vsc::set_error("vsc_upload_rows: negative range"); return VSC_ERR_INVALID; }
+        if (rows == 0) continue;
+        VSC_CUDA_CHECK(cudaMemcpyAsync(static_cast<char *>(d_dst) + first * row_bytes,
+                                       static_cast<const char *>(h_src) + first * row_bytes, (size_t)(rows * row_bytes),
+                                       cudaMemcpyHostToDevice, stream));
+    }
+    return VSC_OK;
+}

@@ -63,12 +63,13 @@ __global__ void __launch_bounds__(256) prepare_kernel(const float *__restrict__ 
 // ---- fp16 split panels (see include/vsc_b200.h, vsc_gemm_format).  Pass 1: max |x| (float bits are monotone for
 // non-negative values); pass 2 derives the power-of-two scale from it on the device and writes the panels.
 __global__ void __launch_bounds__(256) absmax_kernel(const float *__restrict__ x, int64_t n, int d, int64_t ld,
-                                                     unsigned int *__restrict__ out) {
+                                                     unsigned int *__restrict__ out, const int32_t *__restrict__ rows) {
     unsigned int m = 0;
     const int64_t total = n * d;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t row = i / d;
-        const float v = fabsf(x[row * ld + (i - row * d)]);
+        const int64_t vrow = i / d;
+        const int64_t row = rows ? rows[vrow] : vrow;     // optional row list: only these rows of x take part
+        const float v = fabsf(x[row * ld + (i - vrow * d)]);
         if (v < INFINITY) m = max(m, __float_as_uint(v));     // NaN / inf do not take part
     }
 #pragma unroll
@@ -89,16 +90,18 @@ template <bool VEC>
 __global__ void __launch_bounds__(256) prepare_f16_kernel(const float *__restrict__ x, int64_t n, int d, int64_t ld,
                                                           int kpad, int side, __half *__restrict__ out,
                                                           const unsigned int *__restrict__ absmax,
-                                                          float *__restrict__ inv_scale, int *__restrict__ lo_flag) {
+                                                          float *__restrict__ inv_scale, int *__restrict__ lo_flag,
+                                                          const int32_t *__restrict__ rows) {
     const int e = scale_exponent(*absmax);
     const float s = pow2f(e);
     if (blockIdx.x == 0 && threadIdx.x == 0) *inv_scale = pow2f(-e);
     const int quads = kpad >> 2;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t row = idx / quads;
-    const int k = (int)(idx - row * quads) * 4;
+    const int64_t vrow = idx / quads;
+    const int k = (int)(idx - vrow * quads) * 4;
     bool any_lo = false, too_big = false;
-    if (row < n) {
+    const int64_t row = (rows && vrow < n) ? rows[vrow] : vrow;   // optional row list (rows of x and of the panel alike)
+    if (vrow < n) {
         float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         const float *src = x + row * ld + k;
         if (VEC && k + 3 < d) {
@@ -181,7 +184,7 @@ extern "C" int vsc_row_sqnorm(const float *d_x, int64_t n, int32_t d, int64_t ld
 
 static int prepare_f16(const float *d_x, int64_t n, int32_t d, int64_t ld, int32_t kpad, int32_t side,
                        void *d_out_f16, float *d_inv_scale, int32_t *d_lo_flag, uint32_t *d_scratch, bool keep_scale,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, const int32_t *d_rows = nullptr) {
     if (kpad < d || kpad % 64 != 0 || side < 0 || side > 1 || !d_inv_scale || !d_scratch) {
         vsc::set_error("vsc_prepare_operand_f16: kpad=%d must be a multiple of 64 and >= d=%d; side in 0..1", kpad, d);
         return VSC_ERR_INVALID;
@@ -199,17 +202,17 @@ static int prepare_f16(const float *d_x, int64_t n, int32_t d, int64_t ld, int32
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const int64_t elems = n * d;
         const int64_t want = (elems + 255) / 256;
-        absmax_kernel<<<(unsigned)(want < sms * 16 ? want : sms * 16), 256, 0, stream>>>(d_x, n, d, ld, d_scratch);
+        absmax_kernel<<<(unsigned)(want < sms * 16 ? want : sms * 16), 256, 0, stream>>>(d_x, n, d, ld, d_scratch, d_rows);
         vsc::count_launch();
     }
     const int64_t total = n * (kpad / 4);
     const bool vec = (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(d_x) & 15u) == 0;
     if (vec)
         prepare_f16_kernel<true><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
-            d_x, n, d, ld, kpad, side, static_cast<__half *>(d_out_f16), d_scratch, d_inv_scale, d_lo_flag);
+            d_x, n, d, ld, kpad, side, static_cast<__half *>(d_out_f16), d_scratch, d_inv_scale, d_lo_flag, d_rows);
     else
         prepare_f16_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
-            d_x, n, d, ld, kpad, side, static_cast<__half *>(d_out_f16), d_scratch, d_inv_scale, d_lo_flag);
+            d_x, n, d, ld, kpad, side, static_cast<__half *>(d_out_f16), d_scratch, d_inv_scale, d_lo_flag, d_rows);
     VSC_CUDA_CHECK(cudaGetLastError());
     vsc::count_launch();
     return VSC_OK;
@@ -230,4 +233,16 @@ extern "C" int vsc_prepare_operand_f16_more(const float *d_x, int64_t n, int32_t
                                             uint32_t *d_scratch, vsc_stream_t stream_) {
     return prepare_f16(d_x, n, d, ld, kpad, side, d_out_f16, d_inv_scale, d_lo_flag, d_scratch, true,
                        static_cast<cudaStream_t>(stream_));
+}
+
+// The same for a LIST of rows: d_x / d_out_f16 are the whole matrix and the whole panel, d_rows[0..n) the (absolute) rows to
+// convert -- one launch for the hundreds of scattered videos a chunk of candidate pairs brings in.  keep_scale != 0: the
+// scale of an earlier call on this operand is kept (vsc_prepare_operand_f16_more), else it is chosen from these rows.
+extern "C" int vsc_prepare_operand_f16_rows(const float *d_x, const int32_t *d_rows, int64_t n, int32_t d, int64_t ld,
+                                            int32_t kpad, int32_t side, void *d_out_f16, float *d_inv_scale,
+                                            int32_t *d_lo_flag, uint32_t *d_scratch, int32_t keep_scale,
+                                            vsc_stream_t stream_) {
+    if (n > 0 && !d_rows) { vsc::set_error("vsc_prepare_operand_f16_rows: null row list"); return VSC_ERR_INVALID; }
+    return prepare_f16(d_x, n, d, ld, kpad, side, d_out_f16, d_inv_scale, d_lo_flag, d_scratch, keep_scale != 0,
+                       static_cast<cudaStream_t>(stream_), d_rows);
 }

@@ -82,6 +82,36 @@ class GrowingOperand(Operand):
         _lib.check(rc, "vsc_prepare_operand_f16(_more)")
         self.started = True
 
+    def prepare_ranges(self, x, ranges):
+        """Convert the row ranges [(r0, r1), ...] of the float32 CUDA matrix `x` the panel mirrors, in ONE launch
+        (vsc_prepare_operand_f16_rows over a row list built here)."""
+        torch = _lib.require_cuda()
+        if not ranges:
+            return
+        if len(ranges) <= 64:       # a launch per range is cheaper than staging a row list (a pinned allocation + a copy)
+            for r0, r1 in ranges:
+                self.prepare_rows(x, r0, r1 - r0)
+            return
+        r = np.asarray(ranges, dtype=np.int64)
+        lens = r[:, 1] - r[:, 0]
+        total = int(lens.sum())
+        if total == 0:
+            return
+        # row list: for every range its rows in order (start of the range + position inside it)
+        starts = np.repeat(r[:, 0] - np.concatenate([[0], np.cumsum(lens)[:-1]]), lens)
+        rows = starts + np.arange(total, dtype=np.int64)
+        assert x.is_cuda and x.dtype == torch.float32 and x.shape[1] == self.d and int(r[:, 1].max()) <= max(self.rows, 1)
+        staged = torch.empty((total,), dtype=torch.int32, pin_memory=True)   # pinned: the copy must not block the host, which
+        staged.numpy()[:] = rows                                                # is running ahead of the descriptor uploads
+        d_rows = staged.to(x.device, non_blocking=True)
+        base = self.meta.data_ptr()
+        with torch.cuda.device(x.device):
+            rc = _lib.load().vsc_prepare_operand_f16_rows(x.data_ptr(), d_rows.data_ptr(), total, self.d, x.stride(0), self.kpad,
+                                                          self.side, self.panel.data_ptr(), base, base + 4, base + 8,
+                                                          1 if self.started else 0, _stream_ptr(torch, x.device))
+        _lib.check(rc, "vsc_prepare_operand_f16_rows")
+        self.started = True
+
     def needs_split(self) -> bool:
         if not self._needs_split:          # the flag only ever goes up: once set, no more read-backs
             self._needs_split = bool(int(self.lo_flag.item()) & 1)

@@ -15,6 +15,7 @@ Same classes and signatures as the reference.  `VCSLLocalization.localize_all` i
 """
 import abc
 import collections
+import ctypes
 import gc
 import time
 from typing import Dict, List
@@ -56,8 +57,8 @@ class _DeviceVideos:
     shared base array are uploaded with that array in one copy; anything else is concatenated on the host first."""
 
     MAX_WASTE = 8   # upload a shared base whole unless it is this many times larger than what the batch needs
-    BLOCK = 512     # rows per residency block of a lazily mirrored base array
-    BRIDGE = 4      # blocks nobody asked for that a copy may take along to join two runs
+    BLOCK = 512     # rows per residency block of a lazily mirrored base array (1 MB at 512-d: PCIe-efficient copies)
+    BRIDGE = 4      # blocks nobody asked for that a copy may take along to join two runs (few, large copies)
 
     def __init__(self, videos: Dict[object, VideoFeature], device):
         self.videos, self.device = videos, device
@@ -104,7 +105,9 @@ class _DeviceVideos:
     def _mirror(self, root):
         """Device matrix for all rows of `root`, nothing copied yet."""
         torch = _lib.require_cuda()
-        d = torch.empty(root.shape, dtype=torch.float32, device=self.device)
+        # zero-filled: rows that have not been uploaded yet read as zeros, so the panel conversion may cover a span that
+        # contains some (zeros change neither the scale nor the flags) instead of one launch per uploaded run
+        d = torch.zeros(root.shape, dtype=torch.float32, device=self.device)
         first = self.rows
         self.segments.append(d)
         self.rows += d.shape[0]
@@ -145,16 +148,23 @@ class _DeviceVideos:
             if not resident[idx[g] + 1:idx[g + 1]].any():
                 todo[idx[g] + 1:idx[g + 1]] = True
         idx = np.flatnonzero(todo)
+        cuts = np.flatnonzero(np.diff(idx) > 1) + 1
+        first = idx[np.concatenate([[0], cuts])] * self.BLOCK                                     # runs of consecutive blocks
+        last = np.minimum((idx[np.concatenate([cuts, [len(idx)]]) - 1] + 1) * self.BLOCK, root.shape[0])
+        ranges = np.ascontiguousarray(np.stack([first, last - first], axis=1), dtype=np.int64)
         with torch.cuda.stream(lz["copier"]):
-            for run in np.split(idx, np.flatnonzero(np.diff(idx) > 1) + 1):
-                r0, r1 = int(run[0]) * self.BLOCK, min((int(run[-1]) + 1) * self.BLOCK, root.shape[0])
-                src = torch.from_numpy(root[r0:r1])
-                self.h2d_bytes += src.numel() * src.element_size()
-                if src.dtype == torch.float32:
-                    dev[r0:r1].copy_(src, non_blocking=True)
-                else:                       # --store_fp16 descriptors: half the bytes over PCIe, widened on the device
-                    dev[r0:r1].copy_(src.to(self.device, non_blocking=True))
-                lz["fresh"].append((r0, r1))
+            if root.dtype == np.float32:    # all runs in one engine call (a Python-level copy per run costs more than the copy)
+                with torch.cuda.device(self.device):
+                    rc = _lib.load().vsc_upload_rows(dev.data_ptr(), root.ctypes.data, root.strides[0], ranges.ctypes.data,
+                                                     len(ranges), ctypes.c_void_p(lz["copier"].cuda_stream))
+                _lib.check(rc, "vsc_upload_rows")
+                self.h2d_bytes += int(ranges[:, 1].sum()) * root.strides[0]
+            else:                           # --store_fp16 descriptors: half the bytes over PCIe, widened on the device
+                for r0, n in ranges.tolist():
+                    src = torch.from_numpy(root[r0:r0 + n])
+                    self.h2d_bytes += src.numel() * src.element_size()
+                    dev[r0:r0 + n].copy_(src.to(self.device, non_blocking=True))
+            lz["fresh"].extend((int(r0), int(r0 + n)) for r0, n in ranges.tolist())
             done = torch.cuda.Event()
             done.record(lz["copier"])
         lz["events"].append(done)
@@ -196,7 +206,10 @@ class _DeviceVideos:
                 self._operand = (("lazy", id(lz)), gemm.GrowingOperand(self.rows, lz["dev"].shape[1], side, self.device))
             op = self._operand[1]
             self._await_copies()
-            for r0, r1 in lz["fresh"]:          # (a lazy mirror is the store's only segment: first == 0)
+            fresh = lz["fresh"]                         # (a lazy mirror is the store's only segment: first == 0)
+            if len(fresh) > 8:                          # many runs: one launch over the span they cover (see _mirror)
+                fresh = [(min(r0 for r0, _ in fresh), max(r1 for _, r1 in fresh))]
+            for r0, r1 in fresh:
                 op.prepare_rows(lz["dev"], r0, r1 - r0)
             lz["fresh"] = []
             return op
