@@ -117,3 +117,33 @@ def test_emit_capacity_overflow_is_counted_not_written():
     gemm.gemm_emit(oa, ob, hits, -1e10, -1e10)
     stored, counted = hits.read_counters()
     assert stored >= 256 * 512 and counted == 256 * 512   # claimed slots (incl. block fillers) / true hits
+
+
+def test_growing_operand_pieces_equal_whole():
+    """fp16 split panels converted piece by piece (first piece fixes the scale: vsc_prepare_operand_f16, then _more and the
+    row-list form _rows) are bit-identical to the panel of one whole-matrix conversion when the first piece holds max|x|."""
+    import torch
+    from vsc2022_b200 import gemm
+    g = torch.Generator(device="cuda"); g.manual_seed(11)
+    x = torch.randn((1500, 96), generator=g, device="cuda")
+    x[0, 0] = 9.0                                                   # the largest value sits in the first piece
+    whole = gemm.prepare(x, gemm.SIDE_B)
+    grow = gemm.GrowingOperand(1500, 96, gemm.SIDE_B, x.device)
+    grow.prepare_rows(x, 0, 100)                                    # vsc_prepare_operand_f16
+    grow.prepare_rows(x[100:260], 100)                              # _more, rows given directly
+    ranges = [(260 + 12 * i, 260 + 12 * i + 7) for i in range(80)]  # > 64 runs: one launch over a row list
+    grow.prepare_ranges(x, ranges)
+    grow.prepare_ranges(x, [(1220, 1500)])
+    torch.cuda.synchronize()
+    assert float(grow.inv_scale.item()) == float(whole.inv_scale.item())
+    done = torch.zeros(1500, dtype=torch.bool, device="cuda")
+    done[:260] = True
+    done[1220:] = True
+    for r0, r1 in ranges:
+        done[r0:r1] = True
+    assert torch.equal(grow.panel[done], whole.panel[done])
+    assert grow.needs_split() and not grow.overflowed()
+    late = gemm.GrowingOperand(64, 96, gemm.SIDE_A, x.device)
+    late.prepare_rows(x[:32] * 1e-3, 0)
+    late.prepare_rows(x[32:64] * 1e3, 32)                           # far outside the first piece's fp16 range
+    assert late.overflowed()
