@@ -274,6 +274,19 @@ int vsc_gem_pool(const void *d_in, int32_t n, int32_t hw, int32_t c, float p, fl
 int vsc_upload_rows(void *d_dst, const void *h_src, int64_t row_bytes, const int64_t *ranges, int32_t n_ranges,
                     vsc_stream_t stream);
 
+/* Filtered row maximum (FAISS index.search(x, 1) of score_normalization.py:93-96 at one tensor-core product per value pair
+ * instead of three).  vsc_gemm_emit_rows: inner-product range search with one threshold per query row -- appends every
+ * (score, i, j) with score > d_row_thr[i] (counters as vsc_gemm_emit).  vsc_rowmax_rescore: float32 inner products of the
+ * candidate (row, column) pairs from the ORIGINAL float32 matrices (fused multiply-adds, fixed order) and their maximum
+ * per row into d_out[m] (-inf for a row without candidate); d_scratch_keys: m uint32.  With thresholds = single-product
+ * row maxima minus twice the single-product error bound the candidates contain the true arg max of every row. */
+int vsc_gemm_emit_rows(const void *d_a, int64_t m, const void *d_b, int64_t n, int32_t k, const float *d_row_thr,
+                       float *d_score, int32_t *d_row, int32_t *d_col, uint64_t capacity, unsigned long long *d_counters,
+                       const vsc_gemm_format *fmt, vsc_stream_t stream);
+int vsc_rowmax_rescore(const float *d_a, int64_t m, int64_t lda, const float *d_b, int64_t n, int64_t ldb, int32_t d,
+                       const float *d_cand_score, const int32_t *d_cand_row, const int32_t *d_cand_col, int64_t n_cand,
+                       uint32_t *d_scratch_keys, float *d_out, vsc_stream_t stream);
+
 /* Number of kernel launches issued by this library since load (all entry points). */
 int64_t vsc_launch_count(void);
 

@@ -147,3 +147,41 @@ def test_growing_operand_pieces_equal_whole():
     late.prepare_rows(x[:32] * 1e-3, 0)
     late.prepare_rows(x[32:64] * 1e3, 32)                           # far outside the first piece's fp16 range
     assert late.overflowed()
+
+
+def test_filtered_rowmax_is_float32_exact():
+    """index.max_similarity on float32 descriptors: two single-product passes + exact re-score (gemm.rowmax_filtered).
+    Against the float64 row maximum: float32-dot accuracy, on unit rows, on rows of very different norms, and with
+    near-tied columns (several candidates per row); a row of identical columns overflows the candidate buffer and falls back."""
+    import torch
+    from vsc2022_b200 import gemm
+    from vsc2022_b200.index import METRIC_INNER_PRODUCT, FlatIndex
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    unit = lambda n, d: torch.nn.functional.normalize(torch.randn((n, d), generator=g, device="cuda"), dim=1)
+    q, b = unit(3000, 511), unit(20000, 511)
+    b[5000:5040] = b[100] + 1e-4 * torch.randn((40, 511), generator=g, device="cuda")   # near ties around column 100
+    q[7] = b[100]
+    for scale_q, scale_b in ((1.0, 1.0), (37.0, 0.02)):
+        xq, xb = q * scale_q, b * scale_b
+        idx = FlatIndex(511, METRIC_INNER_PRODUCT)
+        idx.add_device(xb, copy=False)
+        got = idx.max_similarity(xq)
+        want = (xq.double() @ xb.double().T).max(dim=1).values
+        err = (got.double() - want).abs().max().item()
+        assert err <= 4e-7 * scale_q * scale_b, err
+        idx.filtered_rowmax = False
+        split = idx.max_similarity(xq)
+        assert (split.double() - want).abs().max().item() <= 4e-6 * scale_q * scale_b   # identical rows: the accumulator truncates
+    # the filter really ran, found few candidates, and saw the planted near-ties
+    oa, ob = gemm.prepare_pair(q, b)
+    assert gemm.Pairing(oa, ob).split
+    assert gemm.rowmax_filtered(q, b, oa, ob) is not None
+    # every column identical: every column is a candidate -> buffer overflow -> fallback to the three-product GEMM
+    same = unit(1, 511).repeat(4000, 1).contiguous()
+    oa, ob = gemm.prepare_pair(q[:256].contiguous(), same)
+    assert gemm.rowmax_filtered(q[:256].contiguous(), same, oa, ob) is None
+    idx = FlatIndex(511, METRIC_INNER_PRODUCT)
+    idx.add_device(same, copy=False)
+    got = idx.max_similarity(q[:256].contiguous())
+    want = (q[:256].double() @ same.double().T).max(dim=1).values
+    assert (got.double() - want).abs().max().item() <= 2e-6

@@ -59,6 +59,7 @@ struct GemmArgs {
     int metric_l2;
     float count_thr, emit_thr;
     const float *thr_ptr;            // when set: {count_thr, emit_thr} are read from device memory (device-driven search)
+    const float *row_thr;            // when set (inner product only): row i emits (and counts) the scores beyond row_thr[i]
     int64_t row_offset, col_offset;  // added to the emitted indices
     float *out_score; int32_t *out_row, *out_col;
     unsigned long long capacity;
@@ -145,8 +146,9 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs &g, float &best, i
         // inner product: the comparisons run on the raw accumulators against thresholds divided by the (power-of-two,
         // hence exact) output scale; only the emitted scores are scaled
         const float inv = g.metric_l2 ? 1.0f : 1.0f / osc;
-        const float emit_thr = (g.thr_ptr ? g.thr_ptr[1] : g.emit_thr) * inv, count_thr = (g.thr_ptr ? g.thr_ptr[0] : g.count_thr) * inv;
-        const bool two = emit_thr != count_thr;  // uniform: the common case has one threshold
+        float emit_thr = (g.thr_ptr ? g.thr_ptr[1] : g.emit_thr) * inv, count_thr = (g.thr_ptr ? g.thr_ptr[0] : g.count_thr) * inv;
+        const bool two = !g.row_thr && emit_thr != count_thr;  // uniform: the common case has one threshold
+        if (g.row_thr) emit_thr = count_thr = (row_ok ? g.row_thr[row] : INFINITY) * inv;   // one threshold per query row
         float an = 0.0f;
         if (!g.metric_l2) {
 #pragma unroll
@@ -760,6 +762,21 @@ int launch_emit_device(const void *d_a, int64_t m, const void *d_b, int64_t n, i
     return launch<EPI_EMIT, 256>(d_a, d_b, g, stream);
 }
 }  // namespace vsc
+
+// Inner-product range search with one threshold PER QUERY ROW: appends every (score, i, j) with score > d_row_thr[i].
+// The second pass of the filtered row maximum (vsc_rowmax_rescore below / index.py max_similarity): thresholds are the
+// single-product row maxima minus the error margin, so the few columns that can hold the true maximum come out.
+extern "C" int vsc_gemm_emit_rows(const void *d_a, int64_t m, const void *d_b, int64_t n, int32_t k, const float *d_row_thr,
+                                  float *d_score, int32_t *d_row, int32_t *d_col, uint64_t capacity,
+                                  unsigned long long *d_counters, const vsc_gemm_format *fmt, vsc_stream_t stream) {
+    if (!d_row_thr) { vsc::set_error("vsc_gemm_emit_rows: null thresholds"); return VSC_ERR_INVALID; }
+    GemmArgs g = {};
+    apply_format(g, fmt);
+    g.M = m; g.N = n; g.K = k;
+    g.row_thr = d_row_thr;
+    g.out_score = d_score; g.out_row = d_row; g.out_col = d_col; g.capacity = capacity; g.counters = d_counters;
+    return launch<EPI_EMIT, 256>(d_a, d_b, g, static_cast<cudaStream_t>(stream));
+}
 
 extern "C" int vsc_gemm_emit(const void *d_a, int64_t m, const void *d_b, int64_t n, int32_t k, const float *d_a_norm,
                              const float *d_b_norm, int32_t metric_l2, float count_thr, float emit_thr,

@@ -274,3 +274,58 @@ extern "C" int vsc_pair_max(const int64_t *d_row, const int64_t *d_col, const fl
     vsc::count_launch(5);
     return VSC_OK;
 }
+
+// ------------------------------------------------------------------ exact re-score of row-maximum candidates
+// vsc_rowmax_rescore: for every candidate (row i, column j) the float32 inner product <a_i, b_j> over d dimensions -- one
+// warp per candidate, lane l accumulates k = l, l+32, ... with fused multiply-adds in ascending k, then a fixed xor-shuffle
+// tree: deterministic, independent of the batch -- and out[i] = max over the row's candidates (order-preserving integer
+// keys + atomicMax).  Fillers of the emit epilogue (score = -inf, row = col = -1 or stale) are skipped by their score.
+namespace {
+__global__ void rowmax_init_kernel(uint32_t *__restrict__ key, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) key[i] = vsc::float_to_key(-INFINITY);
+}
+__global__ void __launch_bounds__(256) rowmax_rescore_kernel(const float *__restrict__ a, int64_t lda, const float *__restrict__ b,
+                                                             int64_t ldb, int d, const float *__restrict__ cand_score,
+                                                             const int32_t *__restrict__ cand_row,
+                                                             const int32_t *__restrict__ cand_col, int64_t n_cand,
+                                                             int64_t m, int64_t n, uint32_t *__restrict__ key) {
+    const int64_t c = (int64_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (c >= n_cand) return;
+    if (!(cand_score[c] > -INFINITY)) return;                 // filler slot of a per-warp emit block
+    const int64_t i = cand_row[c], j = cand_col[c];
+    if (i < 0 || i >= m || j < 0 || j >= n) return;
+    const float *x = a + i * lda, *y = b + j * ldb;
+    float acc = 0.0f;
+    for (int k = lane; k < d; k += 32) acc = __fmaf_rn(x[k], y[k], acc);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(kFullMask, acc, s);
+    if (lane == 0) atomicMax(&key[i], vsc::float_to_key(acc));
+}
+__global__ void rowmax_finish_kernel(const uint32_t *__restrict__ key, int64_t n, float *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = vsc::key_to_float(key[i]);
+}
+}  // namespace
+
+extern "C" int vsc_rowmax_rescore(const float *d_a, int64_t m, int64_t lda, const float *d_b, int64_t n, int64_t ldb, int32_t d,
+                                  const float *d_cand_score, const int32_t *d_cand_row, const int32_t *d_cand_col,
+                                  int64_t n_cand, uint32_t *d_scratch_keys, float *d_out, vsc_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (m <= 0) return VSC_OK;
+    if (!d_a || !d_b || !d_scratch_keys || !d_out || (n_cand > 0 && (!d_cand_score || !d_cand_row || !d_cand_col))) {
+        vsc::set_error("vsc_rowmax_rescore: null pointer"); return VSC_ERR_INVALID;
+    }
+    rowmax_init_kernel<<<(unsigned)((m + 255) / 256), 256, 0, stream>>>(d_scratch_keys, m);
+    vsc::count_launch();
+    if (n_cand > 0) {
+        rowmax_rescore_kernel<<<(unsigned)((n_cand + 7) / 8), 256, 0, stream>>>(d_a, lda, d_b, ldb, d, d_cand_score, d_cand_row,
+                                                                                 d_cand_col, n_cand, m, n, d_scratch_keys);
+        vsc::count_launch();
+    }
+    rowmax_finish_kernel<<<(unsigned)((m + 255) / 256), 256, 0, stream>>>(d_scratch_keys, m, d_out);
+    VSC_CUDA_CHECK(cudaGetLastError());
+    vsc::count_launch();
+    return VSC_OK;
+}

@@ -254,3 +254,47 @@ def gemm_emit(a: Operand, b: Operand, hits: HitBuffer, count_thr: float, emit_th
             hits.score.data_ptr(), hits.row.data_ptr(), hits.col.data_ptr(), hits.capacity,
             hits.counters.data_ptr(), p.ref(), _stream_ptr(torch, hits.score.device))
     _lib.check(rc, "vsc_gemm_emit")
+
+
+def gemm_emit_rows(a: Operand, b: Operand, hits: HitBuffer, row_thr, pairing: Pairing):
+    """Append every inner product of a x b beyond its ROW's threshold (row_thr: float32 CUDA [a.rows]) to `hits`."""
+    torch = _lib.require_cuda()
+    with torch.cuda.device(hits.score.device):
+        rc = _lib.load().vsc_gemm_emit_rows(
+            a.panel.data_ptr() + pairing.col_off, a.rows, b.ptr(pairing.split), b.rows, pairing.k, row_thr.data_ptr(),
+            hits.score.data_ptr(), hits.row.data_ptr(), hits.col.data_ptr(), hits.capacity, hits.counters.data_ptr(),
+            pairing.ref(), _stream_ptr(torch, hits.score.device))
+    _lib.check(rc, "vsc_gemm_emit_rows")
+
+
+# |single-product score - exact score| <= SINGLE_PASS_EPS * |a| * |b|: both hi parts carry a relative rounding error of at
+# most 2^-11 (fp16, round to nearest), so every product is off by at most (2^-10 + 2^-22) |a_k b_k|, Cauchy-Schwarz bounds
+# the sum; the rest (fp32 accumulation in the tensor core, measured <= 2e-6 on unit rows) is covered by the slack.
+SINGLE_PASS_EPS = 2.0 ** -10 * 1.02 + 1e-5
+
+
+def rowmax_filtered(xq, xb, a: Operand, b: Operand):
+    """max_j <xq_i, xb_j> per row in float32 from TWO single-product GEMMs instead of one three-product GEMM: pass 1 gives the
+    approximate row maxima, pass 2 lists, per row, the columns within twice the error bound of it (a superset of the true
+    arg max: ~1.3 columns per row on Gaussian descriptors), vsc_rowmax_rescore takes their exact float32 inner products
+    from the original matrices.  Returns None when the candidate buffer overflowed (caller falls back)."""
+    torch = _lib.require_cuda()
+    single = Pairing(a, b, precise=False)
+    approx = gemm_rowmax(a, b, precise=False)
+    bound = SINGLE_PASS_EPS * torch.sqrt(row_sqnorm(xq)) * torch.sqrt(row_sqnorm(xb).max())
+    thr = (approx - 2.0 * bound).contiguous()
+    from .index import emit_pad
+    hits = HitBuffer(8 * a.rows + emit_pad(), xq.device)
+    gemm_emit_rows(a, b, hits, thr, single)
+    stored, _ = hits.read_counters()
+    if stored > hits.capacity:
+        return None
+    out = torch.empty((max(a.rows, 1),), dtype=torch.float32, device=xq.device)
+    keys = torch.empty((max(a.rows, 1),), dtype=torch.int32, device=xq.device)
+    with torch.cuda.device(xq.device):
+        rc = _lib.load().vsc_rowmax_rescore(xq.data_ptr(), xq.shape[0], xq.stride(0), xb.data_ptr(), xb.shape[0], xb.stride(0),
+                                            xq.shape[1], hits.score.data_ptr(), hits.row.data_ptr(), hits.col.data_ptr(),
+                                            min(stored, hits.capacity), keys.data_ptr(), out.data_ptr(),
+                                            _stream_ptr(torch, xq.device))
+    _lib.check(rc, "vsc_rowmax_rescore")
+    return out[:a.rows]

@@ -86,6 +86,7 @@ class FlatIndex:
         self.d, self.metric_type, self.precise = int(d), int(metric_type), precise
         self._device = device
         self.device_schedule = True   # single GPU: enqueue FAISS's whole batch schedule in one call (csrc/search.cu)
+        self.filtered_rowmax = True   # max_similarity on float32 descriptors: single-product filter + exact re-score
         self._host_chunks: List[np.ndarray] = []
         self._xb = None          # float32 CUDA tensor [ntotal, d]
         self._ntotal = 0
@@ -192,7 +193,14 @@ class FlatIndex:
         """max_j <x_i, db_j> per row as a device tensor -- all score normalisation needs from search(x, 1)."""
         assert self.metric_type == METRIC_INNER_PRODUCT
         xq = self._to_device(x)
-        oa, ob = gemm.prepare_pair(xq, self.database(), self.precise)
+        xb = self.database()
+        oa, ob = gemm.prepare_pair(xq, xb, self.precise)
+        if self.precise and self.filtered_rowmax and xq.shape[0] > 0 and xb.shape[0] > 0 and gemm.Pairing(oa, ob, True).split:
+            # float32 descriptors: two single-product passes + an exact float32 re-score of the few columns that can hold the
+            # maximum (gemm.rowmax_filtered) instead of the three-product GEMM
+            best = gemm.rowmax_filtered(xq if xq.stride(1) == 1 else xq.contiguous(), xb, oa, ob)
+            if best is not None:
+                return best
         return gemm.gemm_rowmax(oa, ob, self.precise)
 
     def _knn_dense(self, xq, xb, oa, ob, k):
