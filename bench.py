@@ -265,8 +265,10 @@ def stage_numbers(dev, peaks):
                      "search_frac_algorithmic": flops / ms_search / 1e9 / peaks["bf16_tflops"],
                      "search_achieved_issued": 2.0 * q.shape[0] * r.shape[0] * split_k / ms_search / 1e9,
                      "gemm_frac_issued": 2.0 * q.shape[0] * r.shape[0] * split_k / ms_gemm / 1e9 / peaks["bf16_tflops"],
-                     "note": "arbitrary float32 descriptors need three fp16 partial products per value pair for "
-                             "float32-class scores: 3x the single-pass FLOPs are issued"}}
+                     "note": "arbitrary float32 descriptors need three fp16 partial products per value pair for float32-class "
+                             "scores; the row maximum of score normalisation and the search batches of >= 4096 query rows run a "
+                             "single-product filter + an exact float32 re-score of the candidates instead (DESIGN.md 4.2); "
+                             "'issued' figures assume the three-product inner dimension throughout"}}
     del sn, index, oa, ob
     del q, r, noise
     torch.cuda.empty_cache()

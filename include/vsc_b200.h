@@ -184,6 +184,17 @@ int vsc_search_global_topk(const void *d_a, int64_t m, const void *d_b, int64_t 
                            float *d_score, int32_t *d_row, int32_t *d_col, float *d_score2, int32_t *d_row2,
                            int32_t *d_col2, uint64_t capacity, void *d_control, int32_t a_row_bytes,
                            const vsc_gemm_format *fmt, vsc_stream_t stream);
+/* The same schedule with batches of at least filter_from_rows query rows filtered: one tensor-core product per value pair
+ * (d_a_single / d_b_single: the hi columns of the panels, k_single) with the thresholds loosened by *d_margin (device scalar:
+ * twice the single-product error bound 2^-10 |a| |b|), then the exact float32 inner products of the candidates from the
+ * original matrices d_a_raw [m][lda_raw] / d_b_raw [n][ldb_raw] (d dimensions) against the real thresholds.  Inner product. */
+int vsc_search_global_topk_filtered(const void *d_a, int64_t m, const void *d_b, int64_t n, int32_t k,
+                                    const void *d_a_single, const void *d_b_single, int32_t k_single,
+                                    const float *d_a_raw, int64_t lda_raw, const float *d_b_raw, int64_t ldb_raw, int32_t d,
+                                    const float *d_margin, int64_t filter_from_rows, int64_t max_results, int64_t min_results,
+                                    float *d_score, int32_t *d_row, int32_t *d_col, float *d_score2, int32_t *d_row2,
+                                    int32_t *d_col2, uint64_t capacity, void *d_control, int32_t a_row_bytes,
+                                    const vsc_gemm_format *fmt, vsc_stream_t stream);
 int vsc_search_control_bytes(void);
 
 /* Score normalisation around the row-max GEMM (vsc/baseline/score_normalization.py:68-104), one pass each:

@@ -381,3 +381,36 @@ def test_reference_index_code_over_the_faiss_stand_in():
         for a, b in zip(got[7:], want[7:]):
             assert np.array_equal(a, b)
         assert len(got[8]) > 20
+
+
+@pytest.mark.parametrize("from_rows", [64, 512])
+def test_filtered_search_batches(from_rows):
+    """Large batches of the device-scheduled search run one tensor-core product per value pair with loosened thresholds and
+    re-score their candidates exactly (vsc_search_global_topk_filtered).  9 600 x 12 000 Gaussian unit rows, filtered from a
+    small batch size on so that most batches take that path: against the float64 top-K (frame pairs may differ only within
+    4e-6 of the K-th score; scores within 4e-6) and against the unfiltered schedule (same pairs up to that band)."""
+    import torch
+    from vsc2022_b200.index import VideoIndex
+    rng = np.random.default_rng(53)
+    unit = lambda x: (x / np.linalg.norm(x, axis=1, keepdims=True)).astype(np.float32)
+    xq, xr = unit(rng.normal(size=(9600, 128))), unit(rng.normal(size=(12000, 128)))
+    xq[100:140] = unit(xr[500:540] + 0.02 * rng.normal(size=(40, 128)))
+    K = 300_000
+    exact = xq.astype(np.float64) @ xr.astype(np.float64).T
+    kth = float(np.partition(exact.ravel(), exact.size - K)[exact.size - K])
+    want = set(zip(*np.nonzero(exact >= kth)))
+
+    def run(rows):
+        index = VideoIndex(128)
+        index.index.filter_from_rows = rows
+        index.index.add(xr)
+        row, col, score = (t.cpu().numpy() for t in index.global_topk_device(torch.from_numpy(xq).cuda(), K))
+        return set(zip(row.tolist(), col.tolist())), dict(zip(zip(row.tolist(), col.tolist()), score.tolist()))
+    got, gs = run(from_rows)
+    plain, ps = run(0)
+    for other in (want, plain):
+        assert all(abs(exact[p] - kth) <= 4e-6 for p in got ^ other), len(got ^ other)
+        assert len(got ^ other) <= max(8, K // 2000)
+    assert max(abs(gs[p] - exact[p]) for p in got) <= 1e-6          # re-scored pairs: float32 dot accuracy
+    assert max(abs(gs[p] - ps[p]) for p in got & plain) <= 4e-6
+    assert len(got) == K

@@ -60,6 +60,7 @@ struct GemmArgs {
     float count_thr, emit_thr;
     const float *thr_ptr;            // when set: {count_thr, emit_thr} are read from device memory (device-driven search)
     const float *row_thr;            // when set (inner product only): row i emits (and counts) the scores beyond row_thr[i]
+    const float *thr_margin;         // when set (inner product only): both thresholds are loosened by *thr_margin (candidate pass)
     int64_t row_offset, col_offset;  // added to the emitted indices
     float *out_score; int32_t *out_row, *out_col;
     unsigned long long capacity;
@@ -146,7 +147,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs &g, float &best, i
         // inner product: the comparisons run on the raw accumulators against thresholds divided by the (power-of-two,
         // hence exact) output scale; only the emitted scores are scaled
         const float inv = g.metric_l2 ? 1.0f : 1.0f / osc;
-        float emit_thr = (g.thr_ptr ? g.thr_ptr[1] : g.emit_thr) * inv, count_thr = (g.thr_ptr ? g.thr_ptr[0] : g.count_thr) * inv;
+        const float loosen = g.thr_margin ? *g.thr_margin : 0.0f;
+        float emit_thr = ((g.thr_ptr ? g.thr_ptr[1] : g.emit_thr) - loosen) * inv, count_thr = ((g.thr_ptr ? g.thr_ptr[0] : g.count_thr) - loosen) * inv;
         const bool two = !g.row_thr && emit_thr != count_thr;  // uniform: the common case has one threshold
         if (g.row_thr) emit_thr = count_thr = (row_ok ? g.row_thr[row] : INFINITY) * inv;   // one threshold per query row
         float an = 0.0f;
@@ -752,10 +754,11 @@ namespace vsc {
 int launch_emit_device(const void *d_a, int64_t m, const void *d_b, int64_t n, int32_t k, const float *d_a_norm,
                        const float *d_b_norm, int32_t metric_l2, const float *d_thr, int64_t row_offset, float *d_score,
                        int32_t *d_row, int32_t *d_col, uint64_t capacity, unsigned long long *d_counters,
-                       const vsc_gemm_format *fmt, cudaStream_t stream) {
+                       const vsc_gemm_format *fmt, cudaStream_t stream, const float *d_margin) {
     GemmArgs g = {};
     apply_format(g, fmt);
     g.M = m; g.N = n; g.K = k;
+    g.thr_margin = metric_l2 ? nullptr : d_margin;
     g.a_norm = d_a_norm; g.b_norm = d_b_norm; g.metric_l2 = metric_l2; g.thr_ptr = d_thr;
     g.row_offset = row_offset; g.out_score = d_score; g.out_row = d_row; g.out_col = d_col;
     g.capacity = capacity; g.counters = d_counters;

@@ -51,4 +51,56 @@ extern "C" int vsc_search_global_topk(const void *d_a, int64_t m, const void *d_
     return search_final_filter(ctl, d_score, d_row, d_col, d_score2, d_row2, d_col2, keep_max, stream);
 }
 
+// The same schedule with the large batches filtered: a batch of at least `filter_from_rows` query rows runs ONE tensor-core
+// product per value pair (the hi parts: d_a_single / d_b_single over k_single) with both thresholds loosened by *d_margin --
+// twice the bound of the single-product error, so nothing the exact scores would accept is missed -- into the twin buffer,
+// and search_rescore_append takes the exact float32 inner products of those candidates from the original matrices
+// (d_a_raw / d_b_raw, d dimensions) and counts / appends them against the real thresholds.  By then the radius is tight: a
+// batch of 4096 x 200k pairs leaves ~1.5 M candidates.  The small early batches, whose radius is loose (every pair of the
+// first batch is a hit), keep the three-product GEMM.  Inner product only.
+extern "C" int vsc_search_global_topk_filtered(const void *d_a, int64_t m, const void *d_b, int64_t n, int32_t k,
+                                               const void *d_a_single, const void *d_b_single, int32_t k_single,
+                                               const float *d_a_raw, int64_t lda_raw, const float *d_b_raw, int64_t ldb_raw,
+                                               int32_t d, const float *d_margin, int64_t filter_from_rows,
+                                               int64_t max_results, int64_t min_results, float *d_score, int32_t *d_row,
+                                               int32_t *d_col, float *d_score2, int32_t *d_row2, int32_t *d_col2,
+                                               uint64_t capacity, void *d_control, int32_t a_row_bytes,
+                                               const vsc_gemm_format *fmt, vsc_stream_t stream_) {
+    using namespace vsc;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (m < 0 || n < 0 || !d_control || !d_score || !d_row || !d_col || !d_score2 || !d_row2 || !d_col2 || !d_a_single ||
+        !d_b_single || !d_a_raw || !d_b_raw || !d_margin || max_results < min_results || min_results < 0 || a_row_bytes <= 0) {
+        set_error("vsc_search_global_topk_filtered: bad arguments"); return VSC_ERR_INVALID;
+    }
+    SearchControl *ctl = static_cast<SearchControl *>(d_control);
+    VSC_CUDA_CHECK(cudaMemsetAsync(ctl, 0, sizeof(SearchControl), stream));
+    const float thr0[2] = {-1e10f, -1e10f};
+    VSC_CUDA_CHECK(cudaMemcpyAsync(ctl->thr, thr0, sizeof thr0, cudaMemcpyHostToDevice, stream));
+    if (m == 0 || n == 0) return VSC_OK;
+    int64_t size = 32;
+    for (int64_t at = 0; at < m;) {
+        const int64_t rows = at + size < m ? size : m - at;
+        int rc;
+        if (rows >= filter_from_rows) {
+            VSC_CUDA_CHECK(cudaMemsetAsync(ctl->cand_counters, 0, sizeof ctl->cand_counters, stream));
+            rc = launch_emit_device(static_cast<const char *>(d_a_single) + at * a_row_bytes, rows, d_b_single, n, k_single,
+                                    nullptr, nullptr, 0, ctl->thr, at, d_score2, d_row2, d_col2, capacity, ctl->cand_counters,
+                                    fmt, stream, d_margin);
+            if (rc == VSC_OK)
+                rc = search_rescore_append(ctl, d_a_raw, lda_raw, d_b_raw, ldb_raw, d, d_score2, d_row2, d_col2, capacity,
+                                           d_score, d_row, d_col, stream);
+        } else {
+            rc = launch_emit_device(static_cast<const char *>(d_a) + at * a_row_bytes, rows, d_b, n, k, nullptr, nullptr, 0,
+                                    ctl->thr, at, d_score, d_row, d_col, capacity, ctl->counters, fmt, stream);
+        }
+        if (rc != VSC_OK) return rc;
+        rc = search_after_batch(ctl, d_score, d_row, d_col, d_score2, d_row2, d_col2, capacity, max_results, min_results, 1,
+                                stream);
+        if (rc != VSC_OK) return rc;
+        at += rows;
+        if (size < 20000) size *= 2;
+    }
+    return search_final_filter(ctl, d_score, d_row, d_col, d_score2, d_row2, d_col2, 1, stream);
+}
+
 extern "C" int vsc_search_control_bytes(void) { return (int)sizeof(vsc::SearchControl); }

@@ -21,12 +21,18 @@ struct SearchControl {
     unsigned long long n_tighten;
     SelectState sel;
     unsigned int hist[2048];
+    // filtered batches (search.cu): candidates of the single-product pass, claimed slots / counted
+    unsigned long long cand_counters[2];
 };
 
 int launch_emit_device(const void *d_a, int64_t m, const void *d_b, int64_t n, int32_t k, const float *d_a_norm,
                        const float *d_b_norm, int32_t metric_l2, const float *d_thr, int64_t row_offset, float *d_score,
                        int32_t *d_row, int32_t *d_col, uint64_t capacity, unsigned long long *d_counters,
-                       const vsc_gemm_format *fmt, cudaStream_t stream);
+                       const vsc_gemm_format *fmt, cudaStream_t stream, const float *d_margin = nullptr);
+// exact float32 scores of the candidates of a single-product pass; those beyond the thresholds of `ctl` are counted / appended
+int search_rescore_append(SearchControl *ctl, const float *d_a_raw, int64_t lda, const float *d_b_raw, int64_t ldb, int32_t d,
+                          const float *cand_s, const int32_t *cand_r, const int32_t *cand_c, uint64_t capacity, float *s,
+                          int32_t *r, int32_t *c, cudaStream_t stream);
 int search_after_batch(SearchControl *ctl, float *s, int32_t *r, int32_t *c, float *s2, int32_t *r2, int32_t *c2,
                        uint64_t capacity, int64_t max_results, int64_t min_results, int keep_max, cudaStream_t stream);
 int search_final_filter(SearchControl *ctl, float *s, int32_t *r, int32_t *c, float *s2, int32_t *r2, int32_t *c2,

@@ -155,6 +155,82 @@ __global__ void search_finish_kernel(SearchControl *c, int always) {
 
 namespace vsc {
 
+// Filtered batch: the candidates (approximate score beyond threshold - margin) get their float32 inner product from the
+// original matrices -- one warp per candidate, lane l over k = l, l+32, ... with fused multiply-adds in ascending k, then a fixed
+// xor-shuffle tree (the arithmetic of vsc_rowmax_rescore: a pair's score does not depend on its batch) -- and those beyond the
+// thresholds of the control block are counted / appended to the survivor buffer exactly as the emit epilogue would have:
+// strict comparisons, one slot claim per 64 candidates.
+namespace {
+constexpr int kRescoreGroup = 64;
+__global__ void __launch_bounds__(256) rescore_append_kernel(SearchControl *ctl, const float *__restrict__ a, int64_t lda,
+                                                             const float *__restrict__ b, int64_t ldb, int d,
+                                                             const float *__restrict__ cand_s, const int32_t *__restrict__ cand_r,
+                                                             const int32_t *__restrict__ cand_c, unsigned long long capacity,
+                                                             float *__restrict__ s_out, int32_t *__restrict__ r_out,
+                                                             int32_t *__restrict__ c_out) {
+    __shared__ float sc[kRescoreGroup];
+    __shared__ int32_t rw[kRescoreGroup], cl[kRescoreGroup];
+    __shared__ unsigned long long base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned long long claimed = ctl->cand_counters[0];
+    if (claimed > capacity) { if (blockIdx.x == 0 && threadIdx.x == 0) ctl->overflow = 1; return; }
+    const float count_thr = ctl->thr[0], emit_thr = ctl->thr[1];
+    for (unsigned long long g0 = (unsigned long long)blockIdx.x * kRescoreGroup; g0 < claimed; g0 += (unsigned long long)gridDim.x * kRescoreGroup) {
+        for (int t = warp; t < kRescoreGroup; t += 8) {
+            const unsigned long long ci = g0 + t;
+            float v = -INFINITY;
+            int32_t i = -1, j = -1;
+            if (ci < claimed && cand_s[ci] > -INFINITY) {     // fillers of the emit epilogue's per-warp blocks carry -inf
+                i = cand_r[ci]; j = cand_c[ci];
+                const float *x = a + (int64_t)i * lda, *y = b + (int64_t)j * ldb;
+                float acc = 0.0f;
+                for (int k = lane; k < d; k += 32) acc = __fmaf_rn(x[k], y[k], acc);
+#pragma unroll
+                for (int sft = 16; sft > 0; sft >>= 1) acc += __shfl_xor_sync(vsc::kFullMask, acc, sft);
+                v = acc;
+            }
+            if (lane == 0) { sc[t] = v; rw[t] = i; cl[t] = j; }
+        }
+        __syncthreads();
+        if (warp == 0) {
+            const float v0 = sc[lane], v1 = sc[lane + 32];
+            const bool e0 = v0 > emit_thr, e1 = v1 > emit_thr;
+            const unsigned m0 = __ballot_sync(vsc::kFullMask, e0), m1 = __ballot_sync(vsc::kFullMask, e1);
+            const int n_emit = __popc(m0) + __popc(m1);
+            const int n_count = __popc(__ballot_sync(vsc::kFullMask, v0 > count_thr)) + __popc(__ballot_sync(vsc::kFullMask, v1 > count_thr));
+            if (lane == 0) {
+                base = n_emit ? atomicAdd(&ctl->counters[0], (unsigned long long)n_emit) : 0ull;
+                if (n_count) atomicAdd(&ctl->counters[1], (unsigned long long)n_count);
+            }
+            __syncwarp();
+            const unsigned long long b0 = base;
+            if (e0) {
+                const unsigned long long at = b0 + __popc(m0 & ((1u << lane) - 1u));
+                if (at < capacity) { s_out[at] = v0; r_out[at] = rw[lane]; c_out[at] = cl[lane]; }
+            }
+            if (e1) {
+                const unsigned long long at = b0 + __popc(m0) + __popc(m1 & ((1u << lane) - 1u));
+                if (at < capacity) { s_out[at] = v1; r_out[at] = rw[lane + 32]; c_out[at] = cl[lane + 32]; }
+            }
+        }
+        __syncthreads();
+    }
+}
+}  // namespace
+
+int search_rescore_append(SearchControl *ctl, const float *d_a_raw, int64_t lda, const float *d_b_raw, int64_t ldb, int32_t d,
+                          const float *cand_s, const int32_t *cand_r, const int32_t *cand_c, uint64_t capacity, float *s,
+                          int32_t *r, int32_t *c, cudaStream_t stream) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    rescore_append_kernel<<<sms * 8, 256, 0, stream>>>(ctl, d_a_raw, lda, d_b_raw, ldb, d, cand_s, cand_r, cand_c,
+                                                        (unsigned long long)capacity, s, r, c);
+    VSC_CUDA_CHECK(cudaGetLastError());
+    vsc::count_launch();
+    return VSC_OK;
+}
+
 // After one range-search launch of the device-driven schedule: FAISS's bookkeeping, and -- when the running total
 // exceeds max_results -- the new radius ((min_results+1)-th best held score, radix selection) and the strict re-filter.
 int search_after_batch(SearchControl *ctl, float *s, int32_t *r, int32_t *c, float *s2, int32_t *r2, int32_t *c2,

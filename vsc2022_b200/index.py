@@ -87,9 +87,14 @@ class FlatIndex:
         self._device = device
         self.device_schedule = True   # single GPU: enqueue FAISS's whole batch schedule in one call (csrc/search.cu)
         self.filtered_rowmax = True   # max_similarity on float32 descriptors: single-product filter + exact re-score
+        # global top-K on float32 descriptors (inner product, single GPU): batches of at least this many query rows run one
+        # tensor-core product per value pair with the thresholds loosened by the error bound, their candidates are re-scored
+        # exactly (csrc/search.cu vsc_search_global_topk_filtered); 0 = every batch takes the three-product GEMM
+        self.filter_from_rows = 4096
         self._host_chunks: List[np.ndarray] = []
         self._xb = None          # float32 CUDA tensor [ntotal, d]
         self._ntotal = 0
+        self._db_operand = None  # (key, prepared panels of the database)
 
     @property
     def ntotal(self) -> int:
@@ -105,6 +110,7 @@ class FlatIndex:
         self._host_chunks.append(x)
         self._ntotal += x.shape[0]
         self._xb = None
+        self._db_operand = None
 
     def add_device(self, x, copy: bool = True):
         """Append descriptors that already live on the device (float32 CUDA tensor [n, d]).  copy=False adopts the
@@ -117,6 +123,7 @@ class FlatIndex:
             self._xb = torch.cat([base, x])
         self._host_chunks = []
         self._ntotal = self._xb.shape[0]
+        self._db_operand = None
 
     def database(self):
         torch = _lib.require_cuda()
@@ -127,6 +134,14 @@ class FlatIndex:
             self._xb = torch.cat([self._xb, torch.from_numpy(np.concatenate(self._host_chunks)).to(self.device())])
         self._host_chunks = []
         return self._xb
+
+    def _operands(self, xq, xb):
+        """GEMM operands of a query matrix and the database; the database panels are converted once per content (FAISS
+        converts at add() time too) and reused by every search until something is added."""
+        key = (xb.data_ptr(), tuple(xb.shape), self._ntotal)
+        if self._db_operand is None or self._db_operand[0] != key:
+            self._db_operand = (key, gemm.prepare(xb, gemm.SIDE_B))
+        return gemm.prepare(xq, gemm.SIDE_A), self._db_operand[1]
 
     # ---- FAISS-style entry points ------------------------------------------------------------------------
     def _to_device(self, x):
@@ -149,7 +164,7 @@ class FlatIndex:
         I = np.full((nq, k), -1, dtype=np.int64)
         if nq == 0 or nb == 0:
             return D, I
-        oa, ob = gemm.prepare_pair(xq, xb, self.precise)
+        oa, ob = self._operands(xq, xb)
         if k == 1 and keep_max:
             best, col = gemm.gemm_rowargmax(oa, ob, self.precise)   # fused epilogue: nothing is materialised
             D[:, 0], I[:, 0] = best.cpu().numpy(), col.cpu().numpy()
@@ -171,7 +186,7 @@ class FlatIndex:
         if nq == 0 or nb == 0:
             return lims, np.zeros(0, np.float32), np.zeros(0, np.int64)
         keep_max = self.metric_type == METRIC_INNER_PRODUCT
-        oa, ob = gemm.prepare_pair(xq, xb, self.precise)
+        oa, ob = self._operands(xq, xb)
         pairing = gemm.Pairing(oa, ob, self.precise)
         qn = bn = None
         if not keep_max:
@@ -194,7 +209,7 @@ class FlatIndex:
         assert self.metric_type == METRIC_INNER_PRODUCT
         xq = self._to_device(x)
         xb = self.database()
-        oa, ob = gemm.prepare_pair(xq, xb, self.precise)
+        oa, ob = self._operands(xq, xb)
         if self.precise and self.filtered_rowmax and xq.shape[0] > 0 and xb.shape[0] > 0 and gemm.Pairing(oa, ob, True).split:
             # float32 descriptors: two single-product passes + an exact float32 re-score of the few columns that can hold the
             # maximum (gemm.rowmax_filtered) instead of the three-product GEMM
@@ -260,7 +275,7 @@ class FlatIndex:
         if nq == 0 or nb == 0:
             z = torch.empty(0, dtype=torch.int64, device=dev)
             return torch.empty(0, device=dev), z, z.clone(), radius
-        oa, ob = gemm.prepare_pair(xq, xb, self.precise)
+        oa, ob = self._operands(xq, xb)
         qn = bn = None
         if not keep_max:
             qn, bn = gemm.row_sqnorm(xq), gemm.row_sqnorm(xb)
@@ -269,7 +284,7 @@ class FlatIndex:
         hits = gemm.HitBuffer(int(capacity), dev)
         pairing = gemm.Pairing(oa, ob, self.precise)
         if ws == 1 and self.device_schedule:
-            done = self._device_schedule(oa, ob, pairing, qn, bn, hits, max_results, min_results, keep_max)
+            done = self._device_schedule(oa, ob, pairing, qn, bn, hits, max_results, min_results, keep_max, xq, xb)
             if done is not None:
                 return done
             hits.counters.zero_()   # a batch overflowed the buffer: batch by batch below, which can split and prune
@@ -327,7 +342,7 @@ class FlatIndex:
             held = self._refilter(hits, held, prune, keep_max)
         return hits.score[:held], hits.row[:held].long(), hits.col[:held].long(), radius
 
-    def _device_schedule(self, oa, ob, pairing, qn, bn, hits, max_results, min_results, keep_max):
+    def _device_schedule(self, oa, ob, pairing, qn, bn, hits, max_results, min_results, keep_max, xq=None, xb=None):
         """The whole FAISS schedule in one engine call (csrc/search.cu): no host round trip until the end.
         Returns None if a batch emitted more than the buffer holds."""
         import ctypes
@@ -340,8 +355,23 @@ class FlatIndex:
         ctl = torch.zeros(((lib.vsc_search_control_bytes() + 7) // 8,), dtype=torch.int64, device=dev)
         s2, r2, c2 = hits.twin
         stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        filtered = (keep_max and pairing.split and self.filter_from_rows > 0 and xq is not None and xb is not None
+                    and oa.rows >= self.filter_from_rows and xq.stride(1) == 1 and xb.stride(1) == 1)
+        if filtered:
+            # twice the single-product error bound for the largest rows of either side (a device scalar: no read back)
+            margin = (2.0 * gemm.SINGLE_PASS_EPS * torch.sqrt(gemm.row_sqnorm(xq).max()) * torch.sqrt(gemm.row_sqnorm(xb).max())
+                      ).reshape(1).float().contiguous()
+            single = gemm.Pairing(oa, ob, precise=False)
+            with torch.cuda.device(dev):
+                rc = lib.vsc_search_global_topk_filtered(
+                    oa.ptr(True), oa.rows, ob.ptr(True), ob.rows, pairing.k, oa.ptr(False), ob.ptr(False), single.k,
+                    xq.data_ptr(), xq.stride(0), xb.data_ptr(), xb.stride(0), xq.shape[1], margin.data_ptr(),
+                    int(self.filter_from_rows), int(max_results), int(min_results), hits.score.data_ptr(),
+                    hits.row.data_ptr(), hits.col.data_ptr(), s2.data_ptr(), r2.data_ptr(), c2.data_ptr(), hits.capacity,
+                    ctl.data_ptr(), oa.ld * 2, pairing.ref(), stream)
+            _lib.check(rc, "vsc_search_global_topk_filtered")
         with torch.cuda.device(dev):
-            rc = lib.vsc_search_global_topk(
+            rc = VSC_OK_RC if filtered else lib.vsc_search_global_topk(
                 oa.ptr(pairing.split), oa.rows, ob.ptr(pairing.split), ob.rows, pairing.k,
                 qn.data_ptr() if qn is not None else None, bn.data_ptr() if bn is not None else None,
                 0 if keep_max else 1, int(max_results), int(min_results), hits.score.data_ptr(), hits.row.data_ptr(),
@@ -413,6 +443,7 @@ def emit_pad() -> int:
     return sms * 8 * 256
 
 
+VSC_OK_RC = 0
 EMIT_PAD = 148 * 8 * 256     # the B200 value; code paths use emit_pad() once a device is in play
 
 
