@@ -169,3 +169,35 @@ def test_growing_operand_scale_overflow_starts_over():
     got = loc.localize_all(cands)
     assert got == want and len(want) >= n
     assert loc._dq.lazy is None          # settled after the overflow
+
+
+def test_mixed_collection_settles_the_lazy_mirror():
+    """A reference collection whose videos are partly row views of one array and partly arrays of their own: the first batch
+    (views only) mirrors the base array lazily, the second batch brings a loose array in -- the mirror goes up whole, becomes
+    an ordinary segment, and both batches give the rows of a collection made of loose arrays only."""
+    from vsc2022_b200.index import VideoFeature
+    from vsc2022_b200.localization import VCSLLocalizationCandidateScore
+    from vsc2022_b200.metrics import CandidatePair
+    rng = np.random.default_rng(31)
+    grid = lambda n: (rng.integers(-16, 17, size=(n, 48)) / 16.0).astype(np.float32)
+    R = grid(5 * 50)
+    ts = np.arange(250) * 1.0
+    extra = grid(64)
+    q = grid(60)
+    q[5:45] = R[110:150]                 # copy of reference video 2
+    q2 = grid(60)
+    q2[10:50] = extra[8:48]              # copy of the loose reference video
+    refs_views = [VideoFeature(video_id=100 + i, feature=R[i * 50:(i + 1) * 50], timestamps=ts[i * 50:(i + 1) * 50]) for i in range(5)]
+    refs_views.append(VideoFeature(video_id=199, feature=extra, timestamps=np.arange(64) * 1.0))
+    queries = [VideoFeature(video_id=1, feature=q, timestamps=np.arange(60) * 1.0),
+               VideoFeature(video_id=2, feature=q2, timestamps=np.arange(60) * 1.0)]
+    cfg = dict(tn_max_step=5, min_length=4, similarity_bias=0.5)
+    loc = VCSLLocalizationCandidateScore(queries, refs_views, "TN", **cfg)
+    first = loc.localize_all([CandidatePair(1, 100 + i, 0.5) for i in range(5)])
+    assert loc._dr.lazy is not None
+    second = loc.localize_all([CandidatePair(2, 199, 0.9), CandidatePair(1, 102, 0.7)])
+    assert loc._dr.lazy is None and len(loc._dr.segments) == 2
+    loose = [VideoFeature(video_id=v.video_id, feature=np.array(v.feature), timestamps=np.array(v.timestamps)) for v in refs_views]
+    ref_loc = VCSLLocalizationCandidateScore(queries, loose, "TN", **cfg)
+    assert first == ref_loc.localize_all([CandidatePair(1, 100 + i, 0.5) for i in range(5)]) and len(first) >= 1
+    assert second == ref_loc.localize_all([CandidatePair(2, 199, 0.9), CandidatePair(1, 102, 0.7)]) and len(second) >= 2
