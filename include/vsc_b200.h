@@ -195,6 +195,22 @@ int vsc_search_global_topk_filtered(const void *d_a, int64_t m, const void *d_b,
                                     float *d_score, int32_t *d_row, int32_t *d_col, float *d_score2, int32_t *d_row2,
                                     int32_t *d_col2, uint64_t capacity, void *d_control, int32_t a_row_bytes,
                                     const vsc_gemm_format *fmt, vsc_stream_t stream);
+/* The schedule step by step, for the query-sharded search over several GPUs: every rank emits ITS rows of a batch
+ * (vsc_search_emit_batch: three-product GEMM, or the filtered form), the ranks all-reduce the hit count, the radix histograms
+ * and the survivor count between the phases of vsc_search_step (views of the control block at the offsets of
+ * vsc_search_control_layout; NCCL on the same stream, no host round trip).  phase -1 begin (arg = metric_l2), 0 decide,
+ * 1 / 2 histogram / pick of radix pass arg, 3 strict re-filter, 4 copy back + finish, 5 end (drop fillers). */
+int vsc_search_step(int32_t phase, int32_t arg, void *d_control, float *d_score, int32_t *d_row, int32_t *d_col,
+                    float *d_score2, int32_t *d_row2, int32_t *d_col2, uint64_t capacity, int64_t max_results,
+                    int64_t min_results, int32_t keep_max, vsc_stream_t stream);
+int vsc_search_emit_batch(const void *d_a, const void *d_b, int64_t n, int32_t k, const void *d_a_single,
+                          const void *d_b_single, int32_t k_single, const float *d_a_raw, int64_t lda_raw,
+                          const float *d_b_raw, int64_t ldb_raw, int32_t d, const float *d_margin, int32_t filtered,
+                          const float *d_a_norm, const float *d_b_norm, int32_t metric_l2, int64_t at, int64_t rows,
+                          float *d_score, int32_t *d_row, int32_t *d_col, float *d_score2, int32_t *d_row2, int32_t *d_col2,
+                          uint64_t capacity, void *d_control, int32_t a_row_bytes, const vsc_gemm_format *fmt,
+                          vsc_stream_t stream);
+int vsc_search_control_layout(int32_t *out7);
 int vsc_search_control_bytes(void);
 
 /* Score normalisation around the row-max GEMM (vsc/baseline/score_normalization.py:68-104), one pass each:

@@ -29,6 +29,25 @@ sharded = flat(cg.query(q, K, group=dist.group.WORLD))     # query rows sharded,
 single = flat(cg.query(q, K))                              # every rank alone
 assert sharded == single and len(single) > 10, "sharded search differs from single-GPU search"
 
+# Gaussian float32 descriptors: the sharded device-side schedule with filtered batches (single-product candidates + exact
+# re-score, every rank its slice of every batch, all-reduced counts / histograms) against the same search on one GPU
+from vsc2022_b200.index import VideoIndex  # noqa: E402
+grng = np.random.default_rng(8)
+unit = lambda x: (x / np.linalg.norm(x, axis=1, keepdims=True)).astype(np.float32)  # noqa: E731
+gq, gr = unit(grng.normal(size=(4800, 64))), unit(grng.normal(size=(6000, 64)))
+gi = VideoIndex(64)
+gi.index.filter_from_rows = 64
+gi.index.add(gr)
+gq_dev = torch.from_numpy(gq).cuda()
+Kg = 150_000
+a = [t.cpu().numpy() for t in gi.global_topk_device(gq_dev, Kg, group=dist.group.WORLD)]
+b = [t.cpu().numpy() for t in gi.global_topk_device(gq_dev, Kg)]
+sa, sb = set(zip(a[0].tolist(), a[1].tolist())), set(zip(b[0].tolist(), b[1].tolist()))
+kth = float(b[2][-1])
+exact = gq.astype(np.float64) @ gr.astype(np.float64).T
+assert len(sa) == Kg and len(sa ^ sb) <= 8 and all(abs(exact[p] - kth) <= 4e-6 for p in sa ^ sb), len(sa ^ sb)
+assert max(abs(float(s) - exact[i, j]) for i, j, s in zip(a[0][::97], a[1][::97], a[2][::97])) <= 4e-6
+
 srng = np.random.default_rng(5)
 sims = [synth.sim_matrix(srng, 64, 64) for _ in range(37)]
 model = vta.build_vta_model("TN", tn_max_step=5, min_length=4)

@@ -23,6 +23,10 @@ struct SearchControl {
     unsigned int hist[2048];
     // filtered batches (search.cu): candidates of the single-product pass, claimed slots / counted
     unsigned long long cand_counters[2];
+    // query-sharded search over several GPUs (vsc_search_step): the survivor count over ALL ranks after a re-filter, written
+    // by the caller (all-reduced copy of `kept`) before the finish step when use_global is set
+    unsigned long long kept_global;
+    int32_t use_global, pad_;
 };
 
 int launch_emit_device(const void *d_a, int64_t m, const void *d_b, int64_t n, int32_t k, const float *d_a_norm,
@@ -35,6 +39,8 @@ int search_rescore_append(SearchControl *ctl, const float *d_a_raw, int64_t lda,
                           int32_t *r, int32_t *c, cudaStream_t stream);
 int search_after_batch(SearchControl *ctl, float *s, int32_t *r, int32_t *c, float *s2, int32_t *r2, int32_t *c2,
                        uint64_t capacity, int64_t max_results, int64_t min_results, int keep_max, cudaStream_t stream);
+int search_phase(int phase, int arg, SearchControl *ctl, float *s, int32_t *r, int32_t *c, float *s2, int32_t *r2, int32_t *c2,
+                 uint64_t capacity, int64_t max_results, int64_t min_results, int keep_max, cudaStream_t stream);
 int search_final_filter(SearchControl *ctl, float *s, int32_t *r, int32_t *c, float *s2, int32_t *r2, int32_t *c2,
                         int keep_max, cudaStream_t stream);
 

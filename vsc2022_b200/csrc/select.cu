@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(256) search_copy_back_kernel(const SearchContr
 __global__ void search_finish_kernel(SearchControl *c, int always) {
     if ((!always && !c->do_tighten) || c->overflow) return;
     c->counters[0] = c->kept;
-    if (!always) { c->total = c->kept; c->thr[1] = c->thr[0]; c->n_tighten += 1; }
+    if (!always) { c->total = c->use_global ? c->kept_global : c->kept; c->thr[1] = c->thr[0]; c->n_tighten += 1; }
     c->do_tighten = 0;
 }
 
@@ -233,23 +233,54 @@ int search_rescore_append(SearchControl *ctl, const float *d_a_raw, int64_t lda,
 
 // After one range-search launch of the device-driven schedule: FAISS's bookkeeping, and -- when the running total
 // exceeds max_results -- the new radius ((min_results+1)-th best held score, radix selection) and the strict re-filter.
-int search_after_batch(SearchControl *ctl, float *s, int32_t *r, int32_t *c, float *s2, int32_t *r2, int32_t *c2,
-                       uint64_t capacity, int64_t max_results, int64_t min_results, int keep_max, cudaStream_t stream) {
+// One phase of the bookkeeping after a batch (the query-sharded search interleaves them with all-reduces, vsc_search_step):
+// 0 decide, 1 histogram of radix pass `arg`, 2 pick of pass `arg`, 3 strict re-filter into the twin buffer, 4 copy back + finish.
+int search_phase(int phase, int arg, SearchControl *ctl, float *s, int32_t *r, int32_t *c, float *s2, int32_t *r2, int32_t *c2,
+                 uint64_t capacity, int64_t max_results, int64_t min_results, int keep_max, cudaStream_t stream) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    search_decide_kernel<<<1, 1, 0, stream>>>(ctl, capacity, (unsigned long long)max_results, (unsigned long long)min_results);
     const int shifts[3] = {21, 10, 0}, bits[3] = {11, 11, 10};
-    for (int p = 0; p < 3; ++p) {
-        select_hist_kernel<<<sms * 4, 512, 0, stream>>>(s, 0, keep_max, shifts[p], bits[p], &ctl->sel, ctl->hist, ctl);
-        select_pick_kernel<<<1, 256, 0, stream>>>(&ctl->sel, ctl->hist, shifts[p], bits[p], keep_max, p == 2, &ctl->thr[0], ctl);
+    switch (phase) {
+        case 0:
+            search_decide_kernel<<<1, 1, 0, stream>>>(ctl, capacity, (unsigned long long)max_results, (unsigned long long)min_results);
+            vsc::count_launch(1);
+            break;
+        case 1:
+            select_hist_kernel<<<sms * 4, 512, 0, stream>>>(s, 0, keep_max, shifts[arg], bits[arg], &ctl->sel, ctl->hist, ctl);
+            vsc::count_launch(1);
+            break;
+        case 2:
+            select_pick_kernel<<<1, 256, 0, stream>>>(&ctl->sel, ctl->hist, shifts[arg], bits[arg], keep_max, arg == 2, &ctl->thr[0], ctl);
+            vsc::count_launch(1);
+            break;
+        case 3:
+            compact_kernel<<<sms * 8, 256, 0, stream>>>(s, r, c, 0, 0.0f, keep_max, s2, r2, c2, &ctl->kept, ctl, 0);
+            vsc::count_launch(1);
+            break;
+        case 4:
+            search_copy_back_kernel<<<sms * 4, 256, 0, stream>>>(ctl, s2, r2, c2, s, r, c, 0);
+            search_finish_kernel<<<1, 1, 0, stream>>>(ctl, 0);
+            vsc::count_launch(2);
+            break;
+        default:
+            vsc::set_error("search_phase: unknown phase %d", phase);
+            return VSC_ERR_INVALID;
     }
-    compact_kernel<<<sms * 8, 256, 0, stream>>>(s, r, c, 0, 0.0f, keep_max, s2, r2, c2, &ctl->kept, ctl, 0);
-    search_copy_back_kernel<<<sms * 4, 256, 0, stream>>>(ctl, s2, r2, c2, s, r, c, 0);
-    search_finish_kernel<<<1, 1, 0, stream>>>(ctl, 0);
     VSC_CUDA_CHECK(cudaGetLastError());
-    vsc::count_launch(10);
     return VSC_OK;
+}
+
+int search_after_batch(SearchControl *ctl, float *s, int32_t *r, int32_t *c, float *s2, int32_t *r2, int32_t *c2,
+                       uint64_t capacity, int64_t max_results, int64_t min_results, int keep_max, cudaStream_t stream) {
+    int rc = search_phase(0, 0, ctl, s, r, c, s2, r2, c2, capacity, max_results, min_results, keep_max, stream);
+    for (int p = 0; p < 3 && rc == VSC_OK; ++p) {
+        rc = search_phase(1, p, ctl, s, r, c, s2, r2, c2, capacity, max_results, min_results, keep_max, stream);
+        if (rc == VSC_OK) rc = search_phase(2, p, ctl, s, r, c, s2, r2, c2, capacity, max_results, min_results, keep_max, stream);
+    }
+    if (rc == VSC_OK) rc = search_phase(3, 0, ctl, s, r, c, s2, r2, c2, capacity, max_results, min_results, keep_max, stream);
+    if (rc == VSC_OK) rc = search_phase(4, 0, ctl, s, r, c, s2, r2, c2, capacity, max_results, min_results, keep_max, stream);
+    return rc;
 }
 
 // End of the schedule: drop the never-accepted fillers of the emit epilogue (strict re-filter with the final radius).

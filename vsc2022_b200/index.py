@@ -288,6 +288,12 @@ class FlatIndex:
             if done is not None:
                 return done
             hits.counters.zero_()   # a batch overflowed the buffer: batch by batch below, which can split and prune
+        elif ws > 1 and self.device_schedule and xq.is_cuda:
+            done = self._device_schedule_sharded(oa, ob, pairing, qn, bn, hits, max_results, min_results, keep_max, xq, xb,
+                                                 group, rank, ws)
+            if done is not None:
+                return done
+            hits.counters.zero_()   # some rank overflowed its buffer: every rank repeats the search the host-driven way
         held, total, prune, padded = 0, 0, radius, False
         unbounded = True   # radius still at its initial value: every pair is a hit, emission size is known
         for b0, b1 in exponential_batches(nq):
@@ -384,6 +390,74 @@ class FlatIndex:
         held = int(head[2])
         if overflow:
             return None
+        return hits.score[:held], hits.row[:held].long(), hits.col[:held].long(), radius
+
+    def _device_schedule_sharded(self, oa, ob, pairing, qn, bn, hits, max_results, min_results, keep_max, xq, xb, group, rank, ws):
+        """The FAISS schedule over several GPUs without a host round trip (csrc/search.cu vsc_search_step): every rank holds
+        all queries and references and emits ITS contiguous slice of the rows of every batch; the hit count, the three radix
+        histograms of a tightening and the survivor count are all-reduced on views of the device-side control block (NCCL
+        calls enqueued between the kernels), so every rank decides and picks the same radius.  Returns this rank's
+        survivors, or None (on every rank) if some rank's buffer overflowed."""
+        import ctypes
+        import torch.distributed as dist
+        from . import distributed as D
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        dev = hits.score.device
+        if getattr(hits, "twin", None) is None:
+            hits.twin = (torch.empty_like(hits.score), torch.empty_like(hits.row), torch.empty_like(hits.col))
+        s2, r2, c2 = hits.twin
+        ctl = torch.zeros(((lib.vsc_search_control_bytes() + 7) // 8,), dtype=torch.int64, device=dev)
+        layout = (ctypes.c_int32 * 7)()
+        lib.vsc_search_control_layout(layout)
+        o_counted, o_hist, o_kept, o_kept_global, o_overflow, o_thr, o_held = list(layout)
+        ctl32 = ctl.view(torch.int32)
+        counted = ctl[o_counted // 8:o_counted // 8 + 1]
+        hist = ctl32[o_hist // 4:o_hist // 4 + 2048]
+        kept, kept_global = ctl[o_kept // 8:o_kept // 8 + 1], ctl[o_kept_global // 8:o_kept_global // 8 + 1]
+        overflow = ctl32[o_overflow // 4:o_overflow // 4 + 1]
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        bufs = (hits.score.data_ptr(), hits.row.data_ptr(), hits.col.data_ptr(), s2.data_ptr(), r2.data_ptr(), c2.data_ptr())
+
+        def step(phase, arg=0):
+            _lib.check(lib.vsc_search_step(phase, arg, ctl.data_ptr(), *bufs, hits.capacity, int(max_results), int(min_results),
+                                           1 if keep_max else 0, stream), "vsc_search_step")
+        can_filter = (keep_max and pairing.split and self.filter_from_rows > 0 and xq.stride(1) == 1 and xb.stride(1) == 1)
+        margin = single = None
+        if can_filter:
+            margin = (2.0 * gemm.SINGLE_PASS_EPS * torch.sqrt(gemm.row_sqnorm(xq).max()) * torch.sqrt(gemm.row_sqnorm(xb).max())
+                      ).reshape(1).float().contiguous()
+            single = gemm.Pairing(oa, ob, precise=False)
+        with torch.cuda.device(dev):
+            step(-1, 0 if keep_max else 1)
+            for b0, b1 in exponential_batches(oa.rows):
+                lo, hi = D.shard_bounds(b1 - b0, rank, ws)
+                filtered = can_filter and (b1 - b0) >= self.filter_from_rows * ws      # by the slice a rank multiplies
+                rc = lib.vsc_search_emit_batch(
+                    oa.ptr(pairing.split), ob.ptr(pairing.split), ob.rows, pairing.k,
+                    oa.ptr(False) if filtered else None, ob.ptr(False) if filtered else None, single.k if filtered else 0,
+                    xq.data_ptr() if filtered else None, xq.stride(0), xb.data_ptr() if filtered else None, xb.stride(0),
+                    xq.shape[1], margin.data_ptr() if filtered else None, 1 if filtered else 0,
+                    qn.data_ptr() if qn is not None else None, bn.data_ptr() if bn is not None else None,
+                    0 if keep_max else 1, b0 + lo, hi - lo, *bufs, hits.capacity, ctl.data_ptr(), oa.ld * 2, pairing.ref(), stream)
+                _lib.check(rc, "vsc_search_emit_batch")
+                dist.all_reduce(counted, group=group)
+                step(0)
+                for p in range(3):
+                    step(1, p)
+                    dist.all_reduce(hist, group=group)
+                    step(2, p)
+                step(3)
+                kept_global.copy_(kept)
+                dist.all_reduce(kept_global, group=group)
+                step(4)
+            step(5)
+            dist.all_reduce(overflow, op=dist.ReduceOp.MAX, group=group)
+        head = ctl.cpu().numpy()                          # the one read back
+        if int(head.view(np.int32)[o_overflow // 4]):
+            return None
+        radius = float(head.view(np.float32)[o_thr // 4])
+        held = int(head[o_held // 8])
         return hits.score[:held], hits.row[:held].long(), hits.col[:held].long(), radius
 
     @staticmethod
