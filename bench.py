@@ -559,6 +559,38 @@ def run_gpu(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    # ---------------- e2e: the reference-facing call on host VideoFeatures, a fresh object per step
+    ts_q = np.tile(np.arange(f, dtype=np.float64), len(q_ids)).copy()     # frame timestamps of all videos, one array
+    ts_r = np.tile(np.arange(f, dtype=np.float64), len(r_ids)).copy()     # per side (what storage.load_features gives)
+    qh, rh = q_host.numpy(), r_host.numpy()
+    queries = [VideoFeature(video_id=f"Q{q:06d}", timestamps=ts_q[i * f:(i + 1) * f], feature=qh[i * f:(i + 1) * f])
+               for i, q in enumerate(q_ids)]
+    refs = [VideoFeature(video_id=f"R{r:06d}", timestamps=ts_r[i * f:(i + 1) * f], feature=rh[i * f:(i + 1) * f])
+            for i, r in enumerate(r_ids)]
+    cands = [CandidatePair(f"Q{int(wl.pair_query[p]):06d}", f"R{int(wl.pair_ref[p]):06d}", 1.0) for p in range(lo, hi)]
+
+    def e2e_step():
+        loc = VCSLLocalizationMaxSim(queries, refs, "TN", tn_max_step=5, min_length=4, concurrency=16, similarity_bias=BIAS)
+        matches = loc.localize_all(cands)
+        return loc, matches
+    for _ in range(2):
+        loc, matches = e2e_step()
+    barrier()
+    e2e_steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    e2e_each = []
+    for _ in range(e2e_steps):
+        t_step = time.perf_counter()
+        loc = matches = None          # the previous step's objects go before the next step starts (still inside the timed region)
+        loc, matches = e2e_step()
+        e2e_each.append(round(1e3 * (time.perf_counter() - t_step), 2))
+    torch.cuda.synchronize(dev)
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    h2d = loc._dq.h2d_bytes + loc._dr.h2d_bytes + meta.nbytes
+    d2h = loc.d2h_bytes
+    n_matches = len(matches)
+    del loc, matches
+
     # ---------------- value: matrices resident in HBM
     warm = max(args.warmup, 3)
     for _ in range(warm):
@@ -606,33 +638,7 @@ def run_gpu(args, rank, local_rank, world):
     bx_ff, nb_ff, ms_ff_scores, _ = res_ff.to_host()
     same_boxes = bool((nb_ff == n_boxes).all()) and bool((bx_ff == boxes_v).all())
 
-    # ---------------- e2e: the reference-facing call on host VideoFeatures, a fresh object per step
-    ts_q = np.tile(np.arange(f, dtype=np.float64), len(q_ids)).copy()     # frame timestamps of all videos, one array
-    ts_r = np.tile(np.arange(f, dtype=np.float64), len(r_ids)).copy()     # per side (what storage.load_features gives)
-    qh, rh = q_host.numpy(), r_host.numpy()
-    queries = [VideoFeature(video_id=f"Q{q:06d}", timestamps=ts_q[i * f:(i + 1) * f], feature=qh[i * f:(i + 1) * f])
-               for i, q in enumerate(q_ids)]
-    refs = [VideoFeature(video_id=f"R{r:06d}", timestamps=ts_r[i * f:(i + 1) * f], feature=rh[i * f:(i + 1) * f])
-            for i, r in enumerate(r_ids)]
-    cands = [CandidatePair(f"Q{int(wl.pair_query[p]):06d}", f"R{int(wl.pair_ref[p]):06d}", 1.0) for p in range(lo, hi)]
-
-    def e2e_step():
-        loc = VCSLLocalizationMaxSim(queries, refs, "TN", tn_max_step=5, min_length=4, concurrency=16, similarity_bias=BIAS)
-        matches = loc.localize_all(cands)
-        return loc, matches
-    for _ in range(2):
-        loc, matches = e2e_step()
-    barrier()
-    e2e_steps = max(1, min(args.steps, 5))
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        loc, matches = e2e_step()
-    torch.cuda.synchronize(dev)
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    h2d = loc._dq.h2d_bytes + loc._dr.h2d_bytes + meta.nbytes
-    d2h = loc.d2h_bytes
-    matches_ok = len(matches) == int(n_boxes.sum())
-
+    matches_ok = n_matches == int(n_boxes.sum())
     # ---------------- max over ranks
     times = torch.tensor([ms, e2e_s * 1e3, ms_ff, ms_ff_boxes], dtype=torch.float64, device=dev)
     if world > 1:
@@ -641,7 +647,7 @@ def run_gpu(args, rank, local_rank, world):
     split_k = pairing.k
     sharded = None
     if world > 1 and not args.no_stages:
-        del sims, Qd, Rd, oq, orr, pairing, loc, matches, res, res_ff
+        del sims, Qd, Rd, oq, orr, pairing, res, res_ff
         torch.cuda.empty_cache()
         sharded = stage_numbers_sharded(dev, measured_peaks()[0], rank, world)
 
@@ -704,7 +710,7 @@ def run_gpu(args, rank, local_rank, world):
             "config": _config(world, n),
             "clocks": sampler.summary(),
             "e2e": {"value": N_PAIRS / (e2e_ms_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_max,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_max, "each_step_ms_rank0": e2e_each,
                     "api": "vsc2022_b200.localization.VCSLLocalizationMaxSim(queries, refs, 'TN', ...).localize_all(candidates): "
                            "%s host descriptors in, Match rows out; a fresh object per step" % ("pinned" if pinned else "pageable")},
             "gpu_launches": launches,
