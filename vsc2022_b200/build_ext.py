@@ -64,6 +64,23 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+HOSTGLUE = os.path.join(CSRC, "_hostglue.so")
+
+
+def build_hostglue(force: bool = False) -> str:
+    """csrc/hostglue.c (CPython API, buffer protocol) -> csrc/_hostglue.so with gcc."""
+    import sysconfig
+    src = os.path.join(CSRC, "hostglue.c")
+    if not force and os.path.exists(HOSTGLUE) and os.path.getmtime(HOSTGLUE) >= os.path.getmtime(src):
+        return HOSTGLUE
+    gcc = shutil.which("gcc") or shutil.which("cc")
+    if not gcc:
+        raise RuntimeError("gcc not found: cannot build _hostglue.so")
+    subprocess.check_call([gcc, "-O2", "-Wall", "-shared", "-fPIC", "-I", sysconfig.get_paths()["include"], src, "-o", HOSTGLUE])
+    return HOSTGLUE
+
+
 if __name__ == "__main__":
     import sys
     print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_hostglue(force="--force" in sys.argv))

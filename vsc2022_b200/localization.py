@@ -22,7 +22,7 @@ from typing import Dict, List
 
 import numpy as np
 
-from . import _lib, gemm
+from . import _hostglue, _lib, gemm
 from .device_features import features_matrix, is_device_tensor, root_of as _root_of
 from .index import VideoFeature
 from .metrics import CandidatePair, Match
@@ -60,8 +60,9 @@ class _DeviceVideos:
     BLOCK = 512     # rows per residency block of a lazily mirrored base array (1 MB at 512-d: PCIe-efficient copies)
     BRIDGE = 4      # blocks nobody asked for that a copy may take along to join two runs (few, large copies)
 
-    def __init__(self, videos: Dict[object, VideoFeature], device):
+    def __init__(self, videos: Dict[object, VideoFeature], device, shared_copier=None):
         self.videos, self.device = videos, device
+        self.shared_copier = shared_copier      # a list shared with the sibling store: holds the common copy stream once made
         self.start: Dict[object, int] = {}
         self.length: Dict[object, int] = {}
         self.segments = []          # device float32 [rows_i, d]
@@ -118,7 +119,11 @@ class _DeviceVideos:
         blocks = (root.shape[0] + self.BLOCK - 1) // self.BLOCK
         # the blocks go up on a stream of their own, so that the copy of the next batch's rows overlaps the kernels of
         # this one; `events` = copies the compute stream has to wait for before it converts the `fresh` rows
-        copier = torch.cuda.Stream(device=self.device)
+        # (one copy stream for the query and the reference store of a localization object: their copies then cross PCIe in
+        # the order they were issued -- chunk by chunk -- instead of two streams taking turns on the one copy engine)
+        copier = self.shared_copier[0] if self.shared_copier else torch.cuda.Stream(device=self.device)
+        if self.shared_copier is not None and not self.shared_copier:
+            self.shared_copier.append(copier)
         copier.wait_stream(torch.cuda.current_stream(self.device))   # the block may have been another tensor's a moment ago
         self.lazy = {"root": root, "dev": d, "first": first, "resident": np.zeros(blocks, dtype=bool), "fresh": [],
                      "copier": copier, "events": []}
@@ -261,6 +266,12 @@ class _DeviceVideos:
             return False
         if known is not None and (self.lazy is None or self.lazy["root"] is not root or self._roots.get(("ts", key)) is not troot):
             return False
+        glue = _hostglue.load()
+        if glue is not None:        # the per-video loop below, in C (csrc/hostglue.c)
+            rows, lens = np.empty(len(new), dtype=np.int64), np.empty(len(new), dtype=np.int64)
+            if glue.vsc_scan_views(videos, new, root, troot, nd, rows, lens) != len(new):
+                return False
+            return self._adopt_views(new, root, troot, key, known, rows, lens)
         rptr, rstride, tptr, tstride = root.ctypes.data, root.strides[0], troot.ctypes.data, troot.strides[0]
         fshape, fstrides, tshape, tstrides = root.shape[1:], root.strides, troot.shape[1:], troot.strides
         rows, lens = [], []
@@ -278,7 +289,9 @@ class _DeviceVideos:
                 return False
             rows.append(row)
             lens.append(n)
-        rows, lens = np.array(rows, dtype=np.int64), np.array(lens, dtype=np.int64)
+        return self._adopt_views(new, root, troot, key, known, np.array(rows, dtype=np.int64), np.array(lens, dtype=np.int64))
+
+    def _adopt_views(self, new, root, troot, key, known, rows, lens) -> bool:
         if known is None:
             if root.shape[0] > self.MAX_WASTE * max(int(lens.sum()), 1) and root.nbytes > (1 << 28):
                 return False
@@ -406,7 +419,8 @@ class VCSLLocalization(LocalizationWithMetadata):
     def _stores(self):
         if self._dq is None:
             dev = self.model._device()
-            self._dq, self._dr = _DeviceVideos(self.queries, dev), _DeviceVideos(self.refs, dev)
+            copier = []
+            self._dq, self._dr = _DeviceVideos(self.queries, dev, copier), _DeviceVideos(self.refs, dev, copier)
         return self._dq, self._dr
 
     def _operands(self):
@@ -527,12 +541,32 @@ class VCSLLocalization(LocalizationWithMetadata):
         tq0, tq1 = dq.timestamps()
         tr0, tr1 = dr.timestamps()
         qs, rs = meta[0][pair_of].astype(np.int64), meta[2][pair_of].astype(np.int64)
+        scorer = type(self).score
+        glue = _hostglue.load()
+        if glue is not None and scorer in (VCSLLocalizationMaxSim.score, VCSLLocalizationCandidateScore.score, VCSLLocalization.score):
+            # the row construction below, in C (csrc/hostglue.c): same objects, same types
+            if scorer is VCSLLocalizationMaxSim.score:
+                scores = maxsim[pair_of, slot] - self.similarity_bias          # float32: iterating yields numpy.float32
+            elif scorer is VCSLLocalizationCandidateScore.score:
+                all_scores = [c.score for c in candidates]
+                scores = [all_scores[p] for p in pair_of.tolist()]
+            else:
+                scores = [1.0] * len(pair_of)
+            was_on = gc.isenabled()
+            gc.disable()
+            try:
+                return glue.vsc_match_rows(Match, q_ids, r_ids, np.ascontiguousarray(pair_of, dtype=np.int64), scores,
+                                           tq0[qs + bx[:, 0]], tq1[qs + bx[:, 2]], tr0[rs + bx[:, 1]], tr1[rs + bx[:, 3]])
+            finally:
+                if was_on:
+                    gc.enable()
+                if prof is not None:
+                    prof["match_rows"] = prof.get("match_rows", 0.0) + time.perf_counter() - t0
         q_start, q_end = tq0[qs + bx[:, 0]].tolist(), tq1[qs + bx[:, 2]].tolist()
         r_start, r_end = tr0[rs + bx[:, 1]].tolist(), tr1[rs + bx[:, 3]].tolist()
         pairs_l = pair_of.tolist()
         qid = np.fromiter(q_ids, dtype=object, count=n)[pair_of].tolist()     # ids pass through untouched (int, str, ...)
         rid = np.fromiter(r_ids, dtype=object, count=n)[pair_of].tolist()
-        scorer = type(self).score
         if scorer is VCSLLocalizationMaxSim.score:        # similarity[x1:x2, y1:y2].max() - bias, float32 like numpy's
             scores = list(maxsim[pair_of, slot] - self.similarity_bias)
         elif scorer is VCSLLocalizationCandidateScore.score:
