@@ -201,3 +201,43 @@ def test_mixed_collection_settles_the_lazy_mirror():
     ref_loc = VCSLLocalizationCandidateScore(queries, loose, "TN", **cfg)
     assert first == ref_loc.localize_all([CandidatePair(1, 100 + i, 0.5) for i in range(5)]) and len(first) >= 1
     assert second == ref_loc.localize_all([CandidatePair(2, 199, 0.9), CandidatePair(1, 102, 0.7)]) and len(second) >= 2
+
+
+def test_custom_scorer_gets_the_similarity_matrix():
+    """A Localization subclass with its own score() (the reference's calling convention, localization.py:66-76: candidate,
+    match, box, similarity matrix): the matrices come back from the device, whole and chunked calls agree, and the values are
+    the float32 matrices of Q.R^T + bias."""
+    from vsc2022_b200.index import VideoFeature
+    from vsc2022_b200.localization import VCSLLocalization
+    from vsc2022_b200.metrics import CandidatePair
+
+    class MeanOfBox(VCSLLocalization):
+        def score(self, candidate, match, box, similarity):
+            x1, y1, x2, y2 = box
+            assert similarity.dtype == np.float32 and similarity.shape == (len(self.queries[candidate.query_id]),
+                                                                            len(self.refs[candidate.ref_id]))
+            return float(similarity[x1:x2 + 1, y1:y2 + 1].mean()) + candidate.score
+
+    rng = np.random.default_rng(12)
+    grid = lambda n: (rng.integers(-16, 17, size=(n, 32)) / 16.0).astype(np.float32)
+    qf = [grid(int(rng.integers(30, 60))) for _ in range(6)]
+    rf = [grid(int(rng.integers(30, 60))) for _ in range(7)]
+    for i in range(6):
+        n = min(len(qf[i]), len(rf[i])) - 6
+        qf[i][3:3 + n] = rf[i][2:2 + n]
+    qs = [VideoFeature(video_id=i, feature=x, timestamps=np.arange(len(x)) * 1.0) for i, x in enumerate(qf)]
+    rs = [VideoFeature(video_id=50 + j, feature=x, timestamps=np.arange(len(x)) * 1.0) for j, x in enumerate(rf)]
+    cands = [CandidatePair(i, 50 + j, 0.25 * j) for i in range(6) for j in range(7)]
+    cfg = dict(tn_max_step=5, min_length=4, similarity_bias=0.5)
+    whole = MeanOfBox(qs, rs, "TN", **cfg).localize_all(cands)
+    chunked = MeanOfBox(qs, rs, "TN", **cfg)
+    chunked.CHUNK = 5
+    assert chunked.localize_all(cands) == whole and len(whole) >= 6
+    by_pair = {}
+    for m in whole:
+        by_pair.setdefault((m.query_id, m.ref_id), []).append(m)
+    for (qi, rj), ms in by_pair.items():
+        sim = qs[qi].feature @ rs[rj - 50].feature.T + np.float32(0.5)       # grid data: exact in float32
+        for m in ms:
+            x1, x2, y1, y2 = int(m.query_start), int(m.query_end), int(m.ref_start), int(m.ref_end)
+            assert m.score == float(sim[x1:x2 + 1, y1:y2 + 1].mean()) + 0.25 * (rj - 50)
