@@ -886,22 +886,65 @@ cudaError_t launch_dp(const Batch &b, const Workspace &w, const WorkList &out, i
 }
 
 // ------------------------------------------------------------------ T3: MaxSim per box
+// max(sims[q0:q1, r0:r1]) per kept box (exclusive upper bounds, localization.py:91), mostly WITHOUT reading the matrix again:
+// the K nodes of a row are its K largest similarities, so (a) if one of them lies in [r0, r1) the row's maximum inside the box
+// is the best such node, and (b) if none does, every element of the row inside the box is <= the row's K-th best.  Pass 1 takes
+// M = the best in-range node over the box's rows from the node records (a few hundred bytes per row instead of the 4*(r1-r0)
+// bytes of the row segment, which were evicted from L2 long ago); pass 2 scans the matrix only for rows of kind (b) whose K-th
+// best exceeds M -- on planted copies none, on noise boxes a few.  Bit-exact: a maximum of float32 values has no rounding.
 __global__ void __launch_bounds__(128) tn_maxsim_kernel(const Batch b, const Workspace w) {
     const int pair = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (pair >= b.n_pairs || w.skip[pair]) return;
-    const int box_cap = b.max_path + 1, lr = b.lr[pair];
+    const int box_cap = b.max_path + 1, lr = b.lr[pair], K = b.topk;
     const float *sims = b.sims + b.off[pair];
+    const size_t nb = (size_t)pair * b.max_nodes;
+    const uint16_t *ref_of = w.ref_of + nb;
+    const unsigned char *rec = static_cast<const unsigned char *>(w.rec) + nb * w.rec_bytes + w.sim_off;
     const int nbx = b.n_boxes[pair];
     for (int k = 0; k < nbx; ++k) {
         const int32_t *g = b.boxes + ((size_t)pair * box_cap + k) * 4;
-        const int h = g[2] - g[0], wd = g[3] - g[1];  // exclusive upper bounds (localization.py:91)
+        const int q0 = g[0], r0 = g[1], q1 = g[2], r1 = g[3];
         float best = -INFINITY;
-        for (int e = lane; e < h * wd; e += 32) {
-            const int r = e / wd, c = e - r * wd;
-            best = fmaxf(best, sims[(size_t)(g[0] + r) * lr + g[1] + c]);
-        }
+        if (q1 > q0 && r1 > r0) {
+            for (int base = q0; base < q1; base += 32) {
+                const int row = base + lane;
+                if (row < q1) {
+                    for (int i = 0; i < K; ++i) {
+                        const int r = ref_of[row * K + i] & kRefMask;
+                        if (r >= r0 && r < r1)
+                            best = fmaxf(best, *reinterpret_cast<const float *>(rec + (size_t)(row * K + i) * w.rec_bytes));
+                    }
+                }
+            }
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) best = fmaxf(best, __shfl_xor_sync(kFullMask, best, d));
+            for (int d = 16; d > 0; d >>= 1) best = fmaxf(best, __shfl_xor_sync(kFullMask, best, d));
+            const float m_nodes = best;
+            for (int base = q0; base < q1; base += 32) {
+                const int row = base + lane;
+                bool scan = false;
+                if (row < q1) {
+                    bool inside = false;
+                    float low = INFINITY;
+                    for (int i = 0; i < K; ++i) {
+                        const int r = ref_of[row * K + i] & kRefMask;
+                        inside = inside || (r >= r0 && r < r1);
+                        low = fminf(low, *reinterpret_cast<const float *>(rec + (size_t)(row * K + i) * w.rec_bytes));
+                    }
+                    scan = !inside && low > m_nodes;
+                }
+                unsigned todo = __ballot_sync(kFullMask, scan);
+                while (todo) {   // the warp scans the row segment together
+                    const int rr = base + __ffs((int)todo) - 1;
+                    todo &= todo - 1;
+                    const float *seg = sims + (size_t)rr * lr;
+                    float m = -INFINITY;
+                    for (int c = r0 + lane; c < r1; c += 32) m = fmaxf(m, seg[c]);
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(kFullMask, m, d));
+                    best = fmaxf(best, m);
+                }
+            }
+        }
         if (lane == 0) b.box_maxsim[(size_t)pair * box_cap + k] = best;
     }
 }
