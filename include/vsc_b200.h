@@ -323,7 +323,8 @@ int64_t vsc_launch_count(void);
  * The frame is resized to rh x rw and the window [top, top+oh) x [left, left+ow) of it is written to d_out
  * [n][oh][ow][3].  d_xbounds / d_xk ([rw][2] / [rw][xksize]) and d_ybounds / d_yk ([rh][2] / [rh][yksize]) are Pillow's
  * (first input pixel, count) windows and 22-bit fixed-point weights (libImaging/Resample.c precompute_coeffs +
- * normalize_coeffs_8bpc; vsc2022_b200/preprocess.py computes them).  d_tmp: n*h*ow*3 bytes of scratch.
+ * normalize_coeffs_8bpc; vsc2022_b200/preprocess.py computes them); weights behind a window's count must be ZERO, as Pillow
+ * leaves them (the horizontal pass runs every window over all xksize taps).  d_tmp: n*h*ow*3 bytes of scratch.
  * The result equals PIL's Image.resize(..., BILINEAR) bit for bit.
  * ------------------------------------------------------------------------- */
 int vsc_resize_u8(const uint8_t *d_in, int32_t n, int32_t h, int32_t w, int32_t rh, int32_t rw,

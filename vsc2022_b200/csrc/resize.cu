@@ -30,9 +30,9 @@ __device__ __forceinline__ uint8_t clip8(int v) {
 // version read its 3 x taps source bytes with single-byte global loads: 244 instructions per output pixel, load/store-unit
 // bound at 1.2 TB/s (profiles/r02_new_kernels_summary.md).
 constexpr int kRowsPerCta = 8;
-__global__ void __launch_bounds__(256) resize_rows_kernel(const uint8_t *__restrict__ in, long long n_rows, int w, int x0, int ow,
+__global__ void __launch_bounds__(512) resize_rows_kernel(const uint8_t *__restrict__ in, long long n_rows, int w, int x0, int ow,
                                                           const int32_t *__restrict__ bounds, const int32_t *__restrict__ kk,
-                                                          int ksize, int span_lo, int span_px, uint8_t *__restrict__ tmp) {
+                                                          int ksize, int taps, int span_lo, int span_px, uint8_t *__restrict__ tmp) {
     extern __shared__ __align__(16) unsigned char rz_smem[];
     int32_t *kw = reinterpret_cast<int32_t *>(rz_smem);                  // [ow][ksize] weights
     int32_t *kb = kw + (size_t)ow * ksize;                               // [ow][2] window start (relative to span_lo), count
@@ -69,12 +69,15 @@ __global__ void __launch_bounds__(256) resize_rows_kernel(const uint8_t *__restr
         __syncthreads();
         const uint8_t *src_row = row_s + head;
         for (int xo = threadIdx.x; xo < ow; xo += blockDim.x) {
-            const int xmin = kb[2 * xo], xmax = kb[2 * xo + 1];
+            const int xmin = kb[2 * xo];
             const int32_t *k = kw + (size_t)xo * ksize;
             const uint8_t *src = src_row + xmin * 3;
             int s0 = 1 << (kPrecisionBits - 1), s1 = s0, s2 = s0;
+            // every window runs over `taps` taps, the longest window of the table: Pillow zero-fills the weights behind a
+            // window's own count (Resample.c: "remaining values should stay empty"), so the trip count is uniform over the
+            // warp; the bytes read behind the last window lie in the slack of the shared buffer and meet a zero weight
 #pragma unroll 4
-            for (int x = 0; x < xmax; ++x) {
+            for (int x = 0; x < taps; ++x) {
                 const int c = k[x];
                 s0 += src[3 * x] * c; s1 += src[3 * x + 1] * c; s2 += src[3 * x + 2] * c;
             }
@@ -142,16 +145,24 @@ extern "C" int vsc_resize_u8(const uint8_t *d_in, int32_t n, int32_t h, int32_t 
     auto lo_of = [&](int x) { int v = (int)(((x + 0.5) * scale) - support + 0.5); return v < 0 ? 0 : v; };
     auto hi_of = [&](int x) { int v = (int)(((x + 0.5) * scale) + support + 0.5); return v > w ? w : v; };
     int span_lo = lo_of(left), span_hi = hi_of(left);
-    for (int x = left; x < left + ow; ++x) { const int a = lo_of(x), b = hi_of(x); span_lo = a < span_lo ? a : span_lo; span_hi = b > span_hi ? b : span_hi; }
+    int taps = 1;
+    for (int x = left; x < left + ow; ++x) {
+        const int a = lo_of(x), b = hi_of(x);
+        span_lo = a < span_lo ? a : span_lo; span_hi = b > span_hi ? b : span_hi;
+        taps = b - a > taps ? b - a : taps;
+    }
+    taps = taps + 1 < xksize ? taps + 1 : xksize;      // (+1: the tables are authoritative, this formula only sizes the loop)
     span_lo = span_lo > 0 ? span_lo - 1 : 0;            // one pixel of slack on either side: the tables are authoritative
     span_hi = span_hi < w ? span_hi + 1 : w;
     const int span_px = span_hi - span_lo;
     const long long n_rows = (long long)n * h;
-    const size_t smem = (size_t)ow * xksize * 4 + (size_t)ow * 8 + 16 + (((size_t)span_px * 3 + 15 + 15) & ~(size_t)15) + 16;
+    const size_t smem = (size_t)ow * xksize * 4 + (size_t)ow * 8 + 16 + (((size_t)span_px * 3 + 15 + 15) & ~(size_t)15) + 16 +
+                        (size_t)xksize * 3 + 16;     // slack behind the span for the zero-weight taps of the last windows
     if (smem > 200 * 1024) { vsc::set_error("vsc_resize_u8: row of %d pixels x %d taps does not fit shared memory", ow, xksize); return VSC_ERR_CAPACITY; }
     VSC_CUDA_CHECK(cudaFuncSetAttribute(resize_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    resize_rows_kernel<<<(unsigned)((n_rows + kRowsPerCta - 1) / kRowsPerCta), 256, smem, stream>>>(
-        d_in, n_rows, w, left, ow, d_xbounds, d_xk, xksize, span_lo, span_px, d_tmp);
+    const int row_threads = ow >= 512 ? 512 : (ow + 31) / 32 * 32;      // one output pixel per thread and row when it fits
+    resize_rows_kernel<<<(unsigned)((n_rows + kRowsPerCta - 1) / kRowsPerCta), row_threads, smem, stream>>>(
+        d_in, n_rows, w, left, ow, d_xbounds, d_xk, xksize, taps, span_lo, span_px, d_tmp);
     VSC_CUDA_CHECK(cudaGetLastError());
     vsc::count_launch();
     const int row_bytes = ow * 3;
