@@ -418,3 +418,46 @@ def test_filtered_search_batches(from_rows, scale_q, scale_r):
     assert max(abs(gs[p] - exact[p]) for p in got) <= tol           # float32-class scores whichever path produced them
     assert max(abs(gs[p] - ps[p]) for p in got & plain) <= tol
     assert len(got) == K
+
+
+def test_c3_full_size_gaussian_properties():
+    """BASELINE.json configs[2] at FULL size (40 000 x 200 000 x 512-d Gaussian float32, K = 1.5 M) through score normalisation
+    and the filtered search, checked by size-independent properties: exactly K distinct pairs, best first; every returned score
+    is the float64 inner product of its rows within the float32-class tolerance; and on a random slab of query rows nothing
+    outside the result beats the K-th score by more than that tolerance while everything clearly above it is inside."""
+    import torch
+    from vsc2022_b200.index import VideoIndex
+    from vsc2022_b200.score_normalization import score_normalize_device
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev); g.manual_seed(3)
+    nq, nr, d = 40_000, 200_000, 512
+    q = torch.randn((nq, d), generator=g, device=dev)
+    r = torch.randn((nr, d), generator=g, device=dev)
+    noise = torch.randn((100_000, d), generator=g, device=dev)
+    for v in range(0, 1250, 20):
+        rv = (v * 7919) % 6250
+        q[v * 32 + 8:v * 32 + 24] = r[rv * 32 + 4:rv * 32 + 20] + 0.1 * torch.randn((16, d), generator=g, device=dev)
+    sq, sr = score_normalize_device(q, r, noise, True, True, 1.2)
+    K = 1_500_000
+    index = VideoIndex(d)
+    index.index.add_device(sr, copy=False)
+    row, col, score = index.global_topk_device(sq, K)
+    assert score.numel() == K
+    assert bool((score[1:] <= score[:-1]).all())
+    assert torch.unique(row * nr + col).numel() == K
+    tol = 4e-6 * float(torch.linalg.norm(sq, dim=1).max() * torch.linalg.norm(sr, dim=1).max())
+    pick = torch.randint(0, K, (20_000,), generator=g, device=dev)
+    exact = (sq[row[pick]].double() * sr[col[pick]].double()).sum(1)
+    assert float((exact - score[pick].double()).abs().max()) <= tol
+    kth = float(score[-1])
+    rows = torch.randperm(nq, generator=g, device=dev)[:256]
+    slab = sq[rows].double() @ sr.double().T                              # 256 x 200 000 exact scores
+    inside = torch.zeros((nq,), dtype=torch.bool, device=dev)
+    member = torch.zeros((256, nr), dtype=torch.bool, device=dev)
+    where = torch.full((nq,), -1, dtype=torch.long, device=dev)
+    where[rows] = torch.arange(256, device=dev)
+    hit = where[row] >= 0
+    member[where[row[hit]], col[hit]] = True
+    assert not bool(((slab > kth + tol) & ~member).any())                 # nothing clearly better was left out
+    assert not bool(((slab < kth - tol) & member).any())                  # nothing clearly worse got in
+    assert int(member.sum()) > 1000

@@ -173,3 +173,29 @@ def test_dp_pairs_per_warp_variants(golden_tn, pairs_per_warp):
         lib.vsc_tn_set_dp_pairs_per_warp(0)
     assert got == want
     assert (status == 0).sum() >= 40      # the 40 full-size pairs at least stay on the fast pipeline
+
+
+def test_c4_full_size_two_kernels_agree():
+    """BASELINE.json configs[3] at FULL size (8000 pairs of 300x300 resident in HBM): the fast pipeline (row top-K, edges,
+    longest-path sweeps with the in-kernel tie order) and the one-CTA-per-pair exact-order kernel (literal Kahn positions) are
+    independent implementations of the oracle's algorithm -- they must give identical boxes and MaxSim scores on every pair;
+    512 of the pairs also go through the oracle itself.  Plus size-independent properties of the result."""
+    import torch
+    from vsc2022_b200 import vta, workloads
+    w = workloads.tn_pairs_device(8000, 300, 300, seed=4, device=torch.device("cuda"))
+    model = vta.build_vta_model("TN", **VSC_CFG)
+    fast = model.align_device(w.sims, w.off, w.lq, w.lr, 8000, 300, 300, want_maxsim=True).to_host()
+    model.force_exact_order = True
+    exact = model.align_device(w.sims, w.off, w.lq, w.lr, 8000, 300, 300, want_maxsim=True).to_host()
+    boxes, n_boxes, maxsim, status = fast
+    assert (status == 0).all() and (exact[3] == 1).all()
+    assert np.array_equal(n_boxes, exact[1])
+    live = np.arange(boxes.shape[1])[None, :] < n_boxes[:, None]
+    assert np.array_equal(boxes[live], exact[0][live]) and np.array_equal(maxsim[live], exact[2][live])
+    b = boxes[live]
+    assert n_boxes.max() <= 11 and (b[:, 0] <= b[:, 2]).all() and (b[:, 1] <= b[:, 3]).all() and b.min() >= 0 and b.max() < 300
+    assert (np.minimum(b[:, 2] - b[:, 0], b[:, 3] - b[:, 1]) > 4).all()            # min_length
+    host = w.sims[:512 * 90000].cpu().numpy().reshape(512, 300, 300)
+    want = tn_fast.tn_batch(list(host), tn_max_step=5, tn_top_k=5, max_path=10, min_sim=0.2, min_length=4, max_iou=0.3)
+    assert all(boxes[i, :n_boxes[i]].tolist() == want[i] for i in range(512))
+    assert n_boxes.sum() > 50_000
