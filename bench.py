@@ -589,6 +589,8 @@ def run_gpu(args, rank, local_rank, world):
     h2d = loc._dq.h2d_bytes + loc._dr.h2d_bytes + meta.nbytes
     d2h = loc.d2h_bytes
     n_matches = len(matches)
+    e2e_head = [(m.query_id, m.ref_id, m.query_start, m.query_end, m.ref_start, m.ref_end, float(m.score))
+                for m in matches[:CPU_SAMPLE * 11]]      # enough rows for the pairs the CPU leg re-does (checked below)
     del loc, matches
 
     # ---------------- value: matrices resident in HBM
@@ -680,6 +682,16 @@ def run_gpu(args, rank, local_rank, world):
             errs = [abs(float(maxsim_v[i, k]) - BIAS - s) for i in range(CPU_SAMPLE) if i not in diff
                     for k, s in enumerate(cpu_scores[i])]
             check["cpu_path_max_score_diff"] = max(errs) if errs else None
+            # the e2e call's Match rows of those pairs against the CPU path: same pairs in the same order, box corners as
+            # timestamps (frame i spans [i, i]: the workload's timestamps are the frame indices), MaxSim score - bias
+            at, same_rows = 0, 0
+            for i in range(CPU_SAMPLE):
+                q_id, r_id = f"Q{int(wl.pair_query[i]):06d}", f"R{int(wl.pair_ref[i]):06d}"
+                want = [(q_id, r_id, float(x1), float(x2), float(y1), float(y2)) for x1, y1, x2, y2 in cpu_boxes[i]]
+                got = e2e_head[at:at + int(n_boxes[i])]
+                at += int(n_boxes[i])
+                same_rows += [g[:6] for g in got] == want and all(abs(g[6] - sc) <= 4e-6 for g, sc in zip(got, cpu_scores[i]))
+            check["e2e_match_rows_equal_cpu_path"] = f"{same_rows} of {CPU_SAMPLE} pairs"
             cpu = {"value": CPU_SAMPLE / dt, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"the first {CPU_SAMPLE} pairs of the workload ({dt:.1f} s): numpy matmul + bias, VCSL TN "
                              f"restated on networkx (real VCSL not installable here) over multiprocessing.Pool({cores}), "
