@@ -120,8 +120,13 @@ class SSCDResNet50:
             cur.wait_stream(side)
             torch.cuda.synchronize(dev)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                static_out = self._forward_batch(static_in)
+            try:
+                with torch.cuda.graph(graph):
+                    static_out = self._forward_batch(static_in)
+            except RuntimeError:            # a driver / allocator state that refuses the capture: same kernels, launched eagerly
+                self.graph_max_batch = 0
+                torch.cuda.synchronize(dev)
+                return self._forward_batch(frames)
             entry = self._graphs[key] = (graph, static_in, static_out)
         graph, static_in, static_out = entry
         static_in.copy_(frames)
